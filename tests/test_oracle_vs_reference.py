@@ -1,0 +1,51 @@
+"""oracle/restated.py against the reference's own python executed live (dev container only:
+skipped where /root/reference is absent, e.g. on the GPU box)."""
+import numpy as np
+import pytest
+
+from oracle import ref_loader, restated as R
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    io, sp, ft = ref_loader.load_data_modules()
+    return dict(io=io, sp=sp, ft=ft, conf=ref_loader.load_conformer_frontend())
+
+
+def test_all_sample_wavs(ref):
+    import os
+    d = os.path.dirname(ref_loader.sample_wav())
+    for name in sorted(os.listdir(d)):
+        x, sr = ref["io"].read(os.path.join(d, name))
+        assert sr == 16000
+        for kw in (dict(), dict(n_fft=400, hop_length=160, pad_mode="reflect"), dict(n_fft=320, hop_length=160)):
+            assert np.array_equal(ref["sp"].stft(x, **kw), R.stft(x, **kw))
+        a = ref["conf"].compute_fbank_feats(x * (1 << 15), 16000, 25, 10, 80)
+        assert np.max(np.abs(a - R.conformer_fbank(x * (1 << 15)))) < 1e-11
+        assert np.max(np.abs(ref["ft"].fbank(x, n_mels=80, n_fft=400, hop_length=160)
+                             - R.fbank(x, n_mels=80, n_fft=400, hop_length=160))) < 1e-11
+
+
+def test_stft_latent_bug_is_fixed_not_replicated(ref):
+    # spectrum.py:237 raises AttributeError for some lengths with hop > n_fft/2
+    x = np.random.default_rng(0).standard_normal(1100)
+    bad = 0
+    for hop in (300, 400, 500):
+        try:
+            a = ref["sp"].stft(x, n_fft=512, hop_length=hop)
+            assert np.array_equal(a, R.stft(x, n_fft=512, hop_length=hop))
+        except AttributeError:
+            bad += 1
+            assert R.stft(x, n_fft=512, hop_length=hop).shape[-1] == 1 + 1100 // hop
+    assert bad >= 1
+
+
+def test_context_window_matches_grouped_conv(ref):
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((3, 7, 50)).astype(np.float32)
+    for l, r in ((3, 5), (4, 4), (5, 3), (0, 0), (5, 5), (0, 3), (2, 0)):
+        assert np.array_equal(ref["ft"].context_window(z, l, r), R.context_window(z, l, r))
+    z4 = rng.standard_normal((2, 3, 7, 20)).astype(np.float32)
+    assert np.array_equal(ref["ft"].context_window(z4, 2, 3), R.context_window(z4, 2, 3))

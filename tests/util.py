@@ -1,0 +1,55 @@
+"""Shared helpers for the parity suites (test infrastructure)."""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# North-star tolerances (BASELINE.json / BASELINE.md section 4):
+#   log-mel / MFCC:  |d| <= 1e-4 * max(1, |ref|)
+#   STFT bins:       max|dX| / max|X| <= 1e-5  (per utterance)
+TOL_LOGMEL = 1e-4
+TOL_STFT = 1e-5
+
+
+def synth(seed, shape, scale=0.05):
+    """Synthetic waveform of SURVEY.md section 8d: clip(0.05*N(0,1), -1, 1) float32."""
+    rng = np.random.default_rng(seed)
+    return np.clip(scale * rng.standard_normal(shape), -1.0, 1.0).astype(np.float32)
+
+
+def mixed_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref)))) if ref.size else 0.0
+
+
+def stft_err(got, ref):
+    ref = np.asarray(ref)
+    return float(np.max(np.abs(np.asarray(got) - ref)) / max(np.max(np.abs(ref)), 1e-30)) if ref.size else 0.0
+
+
+class Golden:
+    """tests/golden/*.npz written by oracle/make_goldens.py (reference python executed in the dev
+    container).  Long arrays are stored on a frame subset: ``take(name, full)`` applies the same
+    subset to a freshly computed full-size result."""
+
+    def __init__(self):
+        self.files = {n[:-4]: np.load(os.path.join(GOLDEN_DIR, n)) for n in os.listdir(GOLDEN_DIR) if n.endswith(".npz")}
+
+    def __getitem__(self, key):
+        fname, name = key.split("/")
+        return self.files[fname][name]
+
+    def wav(self):
+        """BAC009S0002W0122 as io.read returns it: float64 = int16 / 32768."""
+        return self["spectrum/wav_i16"].astype(np.float64) / 32768.0
+
+    def take(self, key, full):
+        fname, name = key.split("/")
+        f = self.files[fname]
+        full = np.asarray(full)
+        if name + "__cols" in f.files:
+            assert tuple(f[name + "__shape"]) == full.shape, (key, tuple(f[name + "__shape"]), full.shape)
+            return full[..., f[name + "__cols"]]
+        return full
