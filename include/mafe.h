@@ -1,0 +1,226 @@
+/*
+ * mafe.h -- C ABI of libmafe.so: MindAudio Front-End feature path on B200 (sm_100a).
+ *
+ * The reference (mindspore-lab/mindaudio) has NO native code and NO FFI on this
+ * path: its boundary is the Python call surface of mindaudio/data/spectrum.py and
+ * mindaudio/data/features.py (numpy in / numpy out) plus the conformer example's
+ * front-end (examples/conformer/dataset.py:56-168) and the CMVN family.  This header
+ * is the thinnest C cut under that surface; every entry point names the reference
+ * interface it serves.  The Python mirror of the reference API that binds these
+ * symbols with ctypes lives in mindaudio_b200/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions across the boundary.
+ *   - every function returns a status (MAFE_OK == 0, negative = error); the message of
+ *     the last error on the calling thread is mafe_last_error().
+ *   - the caller owns every buffer; the library owns only the opaque handles it returns.
+ *   - "dev" pointers are CUDA device pointers on the ctx's device; "host" pointers are
+ *     ordinary host memory.  Work is enqueued on the ctx's stream and is asynchronous
+ *     unless stated otherwise; mafe_ctx_sync() waits for it.
+ *   - ragged batches: utterance u owns samples [sample_offsets[u], sample_offsets[u+1])
+ *     of one flat waveform array and frames [frame_offsets[u], frame_offsets[u+1]) of
+ *     one flat, frame-major output array.  A dense [B, L] batch is the special case of
+ *     equal lengths.
+ *   - fork safety: nothing touches CUDA before the first mafe_ctx_create() of a process.
+ */
+#ifndef MAFE_H_
+#define MAFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAFE_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---- */
+#define MAFE_OK 0
+#define MAFE_E_INVALID_ARG (-1)
+#define MAFE_E_CUDA (-2)
+#define MAFE_E_OOM (-3)
+#define MAFE_E_UNSUPPORTED (-4)
+
+/* ---- enums (plain ints in the structs) ---- */
+/* np.pad / mindspore BorderType modes used by stft (spectrum.py:132,212-232) and Spectrogram */
+#define MAFE_PAD_CONSTANT 0
+#define MAFE_PAD_REFLECT 1
+#define MAFE_PAD_EDGE 2
+#define MAFE_PAD_SYMMETRIC 3
+
+/* what one frame produces */
+#define MAFE_OUT_COMPLEX 0 /* complex64 [n_bins]           -- spectrum.stft            */
+#define MAFE_OUT_POWER 1   /* float |X|^power [n_bins]     -- spectrum.spectrogram     */
+#define MAFE_OUT_MEL 2     /* float mel energies [n_mels]  -- spectrum.melspectrogram  */
+#define MAFE_OUT_LOGMEL 3  /* float log-mel [n_mels]       -- features.fbank / conformer fbank */
+#define MAFE_OUT_MFCC 4    /* float DCT-II of log-mel [n_mfcc] -- features.mfcc        */
+
+/* log applied to mel energies */
+#define MAFE_LOG_NONE 0
+#define MAFE_LOG_LN_EPS_IF_ZERO 1 /* ln(x == 0 ? DBL_EPSILON : x)  conformer/dataset.py:154-155 */
+#define MAFE_LOG_LN_PLUS 2        /* ln(x + log_arg)               features.py:349-350 (log_mels) */
+#define MAFE_LOG_DB 3             /* mult*log10(max(x, amin)) - mult*log10(max(amin, ref)) spectrum.py:73-76 */
+
+/* waveform element types */
+#define MAFE_WAVE_F32 0
+#define MAFE_WAVE_I16 1 /* PCM16; scaled by wave_scale on load (io.py:741-745 gives /32768) */
+
+/* top_db clamp grouping (spectrum.py:78-89) */
+#define MAFE_DBGROUP_NONE 0  /* top_db = None                                             */
+#define MAFE_DBGROUP_UTT 1   /* 2-D input: clamp per utterance                            */
+#define MAFE_DBGROUP_BATCH 2 /* 3-D input: ONE floor for the whole call (batch coupling)  */
+#define MAFE_DBGROUP_MAP 3   /* explicit utt -> group map (4-D input: per leading item)   */
+
+typedef struct mafe_ctx mafe_ctx;
+typedef struct mafe_plan mafe_plan;
+typedef struct mafe_batch mafe_batch;
+
+/*
+ * Immutable description of one front-end configuration.  All table pointers are HOST
+ * pointers read during mafe_plan_create() only.
+ */
+typedef struct mafe_frontend_desc {
+  int32_t n_fft;       /* DFT size (spectrum.py:127; conformer: 512, dataset.py:166)                  */
+  int32_t frame_len;   /* samples taken per frame; < n_fft => zero-padded at the END (np.fft.rfft(n=)) */
+  int32_t hop;         /* frame shift                                                                  */
+  int32_t center;      /* 1: pad n_fft/2 both sides so frame t is centred at t*hop (spectrum.py:181)   */
+  int32_t pad_mode;    /* MAFE_PAD_* for center=1                                                      */
+  int32_t out_kind;    /* MAFE_OUT_*                                                                   */
+  const float* window; /* [frame_len] analysis window, already padded/centred by the caller            */
+
+  double preemph;            /* 0 = off; y[0]=x[0], y[n]=x[n]-c*x[n-1] over the whole utterance (dataset.py:117-119) */
+  int32_t remove_frame_mean; /* 1: subtract ONE scalar = mean of all windowed frame entries (dataset.py:165)        */
+  float dither;              /* 0 = off (reference path); else x += dither * N(0,1), Philox4x32-10       */
+  uint64_t dither_seed;
+
+  float power;      /* MAFE_OUT_POWER/MEL...: |X|^power (2 = re^2+im^2, 1 = magnitude)       */
+  float spec_scale; /* multiplies X before |.|^power (Spectrogram normalized=True); 1 = off */
+
+  int32_t n_mels;       /* rows of mel_fb                                                        */
+  const float* mel_fb;  /* [n_mels][n_fft/2+1] dense filterbank (rows = filters)                 */
+  int32_t log_kind;     /* MAFE_LOG_*                                                            */
+  float log_arg;        /* LN_PLUS: added constant; DB: amin                                     */
+  float log_mult;       /* DB: 10 (power) or 20 (magnitude)                                      */
+  float log_offset;     /* DB: mult*log10(max(amin, ref)) subtracted                             */
+  float top_db;         /* DB: < 0 disables the clamp                                            */
+
+  int32_t n_mfcc;   /* MAFE_OUT_MFCC: columns of dct                                            */
+  const float* dct; /* [n_mels][n_mfcc] (create_dct layout, features.py:337)                    */
+
+  int32_t allow_fast_path; /* 1: use a specialised kernel when the configuration has one        */
+} mafe_frontend_desc;
+
+/* ---- library / errors ---- */
+int mafe_version(void);
+const char* mafe_last_error(void);
+
+/* ---- context: one device + one stream ---- */
+int mafe_ctx_create(int device, mafe_ctx** out);
+int mafe_ctx_destroy(mafe_ctx* ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the ctx's own stream. */
+int mafe_ctx_set_stream(mafe_ctx* ctx, void* cuda_stream);
+int mafe_ctx_sync(mafe_ctx* ctx);
+int mafe_ctx_sm_count(const mafe_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t mafe_ctx_launch_count(const mafe_ctx* ctx);
+
+/* ---- memory plumbing for numpy callers (no torch needed) ---- */
+int mafe_device_malloc(mafe_ctx* ctx, size_t bytes, void** out_dev);
+int mafe_device_free(mafe_ctx* ctx, void* dev);
+int mafe_pinned_malloc(mafe_ctx* ctx, size_t bytes, void** out_host);
+int mafe_pinned_free(mafe_ctx* ctx, void* host);
+int mafe_memcpy_h2d(mafe_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on ctx stream */
+int mafe_memcpy_d2h(mafe_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on ctx stream */
+int mafe_memset(mafe_ctx* ctx, void* dst_dev, int value, size_t bytes);
+
+/* ---- plans ---- */
+int mafe_plan_create(mafe_ctx* ctx, const mafe_frontend_desc* desc, mafe_plan** out);
+int mafe_plan_destroy(mafe_plan* plan);
+/* frames produced for an utterance of n_samples (0 if too short); spectrum.py:298, dataset.py:127 */
+int64_t mafe_plan_num_frames(const mafe_plan* plan, int64_t n_samples);
+/* floats per frame of output (complex counts 2 per bin) */
+int32_t mafe_plan_out_dim(const mafe_plan* plan);
+/* 1 if the specialised sm_100a kernel serves this plan, 0 if the generic mixed-radix kernel does */
+int32_t mafe_plan_is_fast(const mafe_plan* plan);
+
+/* ---- ragged batch layout (host offsets -> device tables) ---- */
+/* sample_offsets_host: int64[n_utts+1].  utt_group_host: int32[n_utts] or NULL (MAFE_DBGROUP_MAP). */
+int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
+                      const int32_t* utt_group_host, mafe_batch** out);
+int mafe_batch_destroy(mafe_batch* batch);
+int64_t mafe_batch_total_frames(const mafe_batch* batch);
+int64_t mafe_batch_total_samples(const mafe_batch* batch);
+/* frame_offsets_host_out: int64[n_utts+1] */
+int mafe_batch_frame_offsets(const mafe_batch* batch, int64_t* frame_offsets_host_out);
+/* device copy of the frame offsets (int64[n_utts+1]) for the CMVN calls below */
+const int64_t* mafe_batch_frame_offsets_dev(const mafe_batch* batch);
+
+/*
+ * The hot path.  wave_dev: flat waveform (MAFE_WAVE_*), wave_scale multiplies every sample on
+ * load (1.0f; 32768.0f reproduces read()*(1<<15), dataset.py:389-390, from float input in [-1,1)).
+ * out_dev: [total_frames][out_dim] floats, frame-major (time-major), ragged by frame offsets.
+ * db_group: MAFE_DBGROUP_* (only for log_kind == MAFE_LOG_DB with top_db >= 0).
+ * Serves: spectrum.stft (spectrum.py:125-278), spectrum.spectrogram (:547-606),
+ * spectrum.melspectrogram (:609-698), features.fbank (features.py:196-270), features.mfcc
+ * (:273-373, without deltas/context), conformer compute_fbank_feats (dataset.py:159-168).
+ */
+int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, const void* wave_dev, int32_t wave_dtype,
+                      float wave_scale, float* out_dev, int32_t db_group);
+
+/* ---- spectral element-wise ops on device arrays ---- */
+/* spectrum.magphase iscomplex=True (spectrum.py:720-732): n complex64 -> mag^power, unit phase (0 -> 1+0j). */
+int mafe_magphase(mafe_ctx* ctx, const float* z_dev, int64_t n, float power, float* mag_dev, float* phase_dev);
+/* spectrum.amplitude_to_dB (spectrum.py:59-90): n_groups contiguous groups of group_size elements;
+ * top_db < 0 disables the clamp.  in == out allowed. */
+int mafe_amplitude_to_db(mafe_ctx* ctx, const float* x_dev, float* out_dev, int64_t n_groups, int64_t group_size,
+                         float mult, float amin, float db_offset, float top_db);
+/* spectrum.dB_to_amplitude (spectrum.py:108-113): ref * (10^(0.1 x))^power */
+int mafe_db_to_amplitude(mafe_ctx* ctx, const float* x_dev, float* out_dev, int64_t n, float ref, float power);
+
+/* spectrum.melscale (spectrum.py:738-774): spec [n_mats][n_bins][t] (time contiguous) -> out [n_mats][n_mels][t];
+ * mel_fb_host: HOST [n_mels][n_bins] dense filterbank. */
+int mafe_melscale(mafe_ctx* ctx, const float* spec_dev, float* out_dev, int32_t n_mats, int32_t n_bins, int32_t t,
+                  const float* mel_fb_host, int32_t n_mels);
+/* layout helper: in [n_mats][rows][cols] -> out [n_mats][cols][rows] (frame-major <-> the reference's [.., freq, time]);
+ * out_mat_stride: floats between consecutive output matrices (>= rows*cols; 0 = dense). */
+int mafe_transpose(mafe_ctx* ctx, const float* in_dev, float* out_dev, int32_t n_mats, int32_t rows, int32_t cols,
+                   int64_t out_mat_stride);
+
+/* ---- istft (spectrum.py:346-474) ---- */
+/* spec_dev: [n_utts][n_frames][n_fft/2+1] complex64 frame-major; window: HOST [n_fft] (padded);
+ * y_dev: [n_utts][n_fft + hop*(n_frames-1)] floats = overlap-added, window-sum-square normalised signal
+ * (the caller trims n_fft/2 / length as the reference does). */
+int mafe_istft(mafe_ctx* ctx, const float* spec_dev, int32_t n_utts, int32_t n_frames, int32_t n_fft, int32_t hop,
+               const float* window_host, float* y_dev);
+
+/* ---- CMVN family ---- */
+/* Per-utterance, per-dim mean (and population-std) normalisation in place
+ * (examples/ECAPA-TDNN/spec_augment.py:43-70).  feats_dev: [total_frames][dim] frame-major. */
+int mafe_cmvn_utt(mafe_ctx* ctx, float* feats_dev, const int64_t* frame_offsets_dev, int32_t n_utts, int32_t dim,
+                  int32_t mean_norm, int32_t std_norm);
+/* Per-utterance scalar (x - mean)/std over ALL elements of the utterance, optional log1p first
+ * (examples/deepspeech2/dataset.py:43-47). */
+int mafe_cmvn_scalar(mafe_ctx* ctx, float* feats_dev, const int64_t* frame_offsets_dev, int32_t n_utts, int32_t dim,
+                     int32_t log1p_first);
+/* Global statistics (examples/conformer/compute_cmvn_stats.py:61-63,108-112): stats_dev is
+ * double[2*dim+1] = {sum x[dim], sum x^2[dim], frame count}; ACCUMULATES (caller zeroes). */
+int mafe_cmvn_stats_accumulate(mafe_ctx* ctx, const float* feats_dev, int64_t total_frames, int32_t dim,
+                               double* stats_dev);
+/* (x - mean) * istd in place (mindaudio/models/layers/cmvn.py:33-36); istd_dev NULL = mean only. */
+int mafe_cmvn_apply(mafe_ctx* ctx, float* feats_dev, int64_t total_frames, int32_t dim, const float* mean_dev,
+                    const float* istd_dev);
+
+/* ---- feature post-processing ("next" row f1: features.py:69-193) ---- */
+/* compute_deltas: n_mats matrices of [rows][t] (time contiguous), matrix strides in floats (0 = dense) so the
+ * result can be written straight into the concatenated [.., 3*rows, t] array of features.py:264-267. */
+int mafe_compute_deltas(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32_t n_mats, int32_t rows, int32_t t,
+                        int64_t x_mat_stride, int64_t out_mat_stride, int32_t win_length, int32_t pad_mode);
+/* context_window: in [n_mats][f][t] -> out [n_mats][f*(l+r+1)][t] (features.py:94-155 gather form). */
+int mafe_context_window(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32_t n_mats, int32_t f, int32_t t,
+                        int32_t left, int32_t right);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAFE_H_ */

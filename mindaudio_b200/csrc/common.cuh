@@ -1,0 +1,170 @@
+// common.cuh -- shared host/device plumbing of libmafe (see include/mafe.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mafe.h"
+
+namespace mafe {
+
+void set_error(const char* fmt, ...);
+
+#define MAFE_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::mafe::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return _e == cudaErrorMemoryAllocation ? MAFE_E_OOM : MAFE_E_CUDA;                        \
+    }                                                                                           \
+  } while (0)
+
+#define MAFE_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      ::mafe::set_error(__VA_ARGS__); \
+      return MAFE_E_INVALID_ARG;     \
+    }                                \
+  } while (0)
+
+#define MAFE_LAUNCH_CHECK(ctx)                 \
+  do {                                         \
+    (ctx)->launches++;                         \
+    MAFE_CUDA_CHECK(cudaGetLastError());       \
+  } while (0)
+
+// one tile of the ragged batch: up to `tile_frames` consecutive frames of one utterance
+struct Tile {
+  int32_t utt;
+  int32_t frame0;
+};
+
+// sparse mel filterbank, two forms
+struct MelCSR {         // by filter (generic kernel)
+  int32_t* row_ptr = nullptr;  // [n_mels+1]
+  int32_t* col = nullptr;      // [nnz]
+  float* val = nullptr;        // [nnz]
+  int32_t nnz = 0;
+};
+
+}  // namespace mafe
+
+struct mafe_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+};
+
+struct mafe_plan {
+  mafe_frontend_desc d;  // table pointers nulled after creation
+  int device = 0;
+  int n_bins = 0;
+  int out_dim = 0;
+  bool fast = false;
+  // generic kernel
+  std::vector<int> radices;
+  int* radices_dev = nullptr;
+  int n_stages = 0;
+  int pairs_per_tile = 0;  // complex FFTs per CTA; tile_frames = 2 * pairs
+  int tile_frames = 0;
+  size_t smem_bytes = 0;
+  float2* twiddle_dev = nullptr;  // [n_fft] W_N^k
+  float* window_dev = nullptr;    // [frame_len]
+  mafe::MelCSR mel;
+  float* dct_dev = nullptr;  // [n_mels][n_mfcc]
+  // fast path tables (fbank512.cu)
+  void* fast_tables = nullptr;
+};
+
+struct mafe_batch {
+  int device = 0;
+  int32_t n_utts = 0;
+  int64_t total_frames = 0;
+  int64_t total_samples = 0;
+  int32_t n_tiles = 0;
+  int32_t n_groups = 0;
+  std::vector<int64_t> frame_offsets_host;
+  int64_t* sample_offsets_dev = nullptr;  // [n_utts+1]
+  int64_t* frame_offsets_dev = nullptr;   // [n_utts+1]
+  mafe::Tile* tiles_dev = nullptr;        // [n_tiles]
+  int32_t* utt_group_dev = nullptr;       // [n_utts] or null
+  double* utt_sum_dev = nullptr;          // [n_utts] frame-mean accumulators
+  int32_t* group_max_dev = nullptr;       // [max(n_utts,1)] ordered-int keys of the dB maxima
+  float* scratch_dev = nullptr;           // MFCC intermediate [total_frames][n_mels]
+  size_t scratch_bytes = 0;
+  int32_t* work_counter_dev = nullptr;    // persistent-kernel tile counter
+};
+
+namespace mafe {
+// generic.cu
+int generic_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* desc);
+void generic_plan_free(mafe_plan* p);
+int generic_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale,
+                float* out, int out_kind_override, int db_group);
+int frame_mean_prepass(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype,
+                       float wave_scale);
+int db_clamp_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, float* data, int dim, int db_group);
+int dct_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const float* logmel, float* out, int db_group);
+// fbank512.cu
+bool fast_plan_supported(const mafe_frontend_desc* desc);
+int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* desc);
+void fast_plan_free(mafe_plan* p);
+int fast_tile_frames();
+int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale,
+             float* out);
+}  // namespace mafe
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+namespace mafe {
+
+__device__ __forceinline__ int ordered_key(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// np.pad index map for a centred frame: s in [-(pad), L+pad) -> [0, L) or -1 (zero)
+__device__ __forceinline__ int64_t pad_index(int64_t s, int64_t L, int mode) {
+  if (s >= 0 && s < L) return s;
+  switch (mode) {
+    case MAFE_PAD_REFLECT:
+      if (L == 1) return 0;
+      { int64_t period = 2 * (L - 1); int64_t m = s % period; if (m < 0) m += period; return m < L ? m : period - m; }
+    case MAFE_PAD_SYMMETRIC:
+      { int64_t period = 2 * L; int64_t m = s % period; if (m < 0) m += period; return m < L ? m : period - 1 - m; }
+    case MAFE_PAD_EDGE:
+      return s < 0 ? 0 : L - 1;
+    default:
+      return -1;
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), same constants as oracle/restated.py
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                              uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// standard-normal dither sample i of utterance utt (oracle/restated.py: dither_noise)
+__device__ __forceinline__ float dither_normal(uint64_t i, uint32_t utt, uint64_t seed) {
+  uint32_t c0 = (uint32_t)i, c1 = (uint32_t)(i >> 32), c2 = utt, c3 = 0;
+  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float u1 = ((float)(c0 >> 8) + 1.0f) * 5.9604644775390625e-08f;  // ((w0>>8)+1) * 2^-24, in (0,1], exact
+  float u2 = (float)(c1 >> 8) * 5.9604644775390625e-08f;
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+}  // namespace mafe
+#endif

@@ -1,0 +1,417 @@
+// generic.cu -- the general front-end kernel: any n_fft (mixed radix 2/3/4/5 + prime fallback),
+// any window / pad mode / hop, every output kind of include/mafe.h.  One CTA owns a tile of
+// 2*P consecutive frames of one utterance; frame pairs are packed (a + i*b) into one complex
+// shared-memory Stockham FFT and separated afterwards (X_a = (Z[k]+conj Z[N-k])/2, ...).
+//
+// Serves (reference file:line): spectrum.stft (mindaudio/data/spectrum.py:125-278), the
+// Spectrogram/MelScale pair behind spectrum.spectrogram/melspectrogram (:547-698), features.fbank /
+// features.mfcc (mindaudio/data/features.py:196-373) and, as the non-specialised route, the
+// conformer front-end (examples/conformer/dataset.py:117-168).  FP32 arithmetic; twiddles and
+// tables are rounded from float64.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "fft_generic.cuh"
+
+namespace mafe {
+
+constexpr int kGenericThreads = 256;
+
+struct GenericParams {
+  const void* wave;
+  int wave_dtype;
+  float wave_scale;
+  const int64_t* sample_offsets;
+  const int64_t* frame_offsets;
+  const Tile* tiles;
+  const double* utt_sum;
+  int n_fft, frame_len, hop, center, pad_mode, n_bins;
+  float pre_hi, pre_lo;  // pre-emphasis coefficient split hi+lo (double -> 2 floats)
+  int preemph_on, remove_mean;
+  float dither;
+  uint64_t seed;
+  const float* window;
+  const float2* tw;
+  FftStages fft;
+  int pairs;
+  int out_kind;
+  float power, spec_scale;
+  int n_mels;
+  const int* row_ptr;
+  const int* col;
+  const float* val;
+  int log_kind;
+  float log_arg, log_mult, log_offset;
+  float* out;
+  int out_dim;
+  int* group_max;
+  const int* utt_group;
+  int db_group;
+};
+
+__device__ __forceinline__ float raw_sample(const GenericParams& P, int64_t off, int64_t m, uint32_t utt) {
+  float v = P.wave_dtype == MAFE_WAVE_I16 ? (float)((const int16_t*)P.wave)[off + m] : ((const float*)P.wave)[off + m];
+  v *= P.wave_scale;
+  if (P.dither != 0.0f) v = fmaf(P.dither, dither_normal((uint64_t)m, utt, P.seed), v);
+  return v;
+}
+
+// y(m): dithered, pre-emphasised sample m of the utterance (dataset.py:117-119: y[0] = x[0])
+__device__ __forceinline__ float signal_sample(const GenericParams& P, int64_t off, int64_t m, uint32_t utt) {
+  float v = raw_sample(P, off, m, utt);
+  if (P.preemph_on && m > 0) {
+    float vp = raw_sample(P, off, m - 1, utt);
+    v = fmaf(-P.pre_lo, vp, fmaf(-P.pre_hi, vp, v));
+  }
+  return v;
+}
+
+// windowed entry n of frame f (before the scalar mean is removed); 0 outside the utterance's frames
+__device__ __forceinline__ float frame_entry(const GenericParams& P, int64_t off, int64_t L, int64_t T, int64_t f, int n,
+                                             uint32_t utt) {
+  if (f >= T || n >= P.frame_len) return 0.0f;
+  int64_t s = f * P.hop + n;
+  if (P.center) {
+    s = pad_index(s - P.n_fft / 2, L, P.pad_mode);
+    if (s < 0) return 0.0f;
+  }
+  return signal_sample(P, off, s, utt) * P.window[n];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass: sum of all windowed frame entries per utterance (conformer/dataset.py:165 needs the
+// mean of the WHOLE [T, frame_len] matrix before the FFT).  double accumulation.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGenericThreads) frame_sum_kernel(GenericParams P, double* utt_sum, int tile_frames) {
+  const Tile tile = P.tiles[blockIdx.x];
+  const int64_t off = P.sample_offsets[tile.utt];
+  const int64_t L = P.sample_offsets[tile.utt + 1] - off;
+  const int64_t T = P.frame_offsets[tile.utt + 1] - P.frame_offsets[tile.utt];
+  double acc = 0.0;
+  const int total = tile_frames * P.frame_len;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    int f = idx / P.frame_len, n = idx - f * P.frame_len;
+    acc += (double)frame_entry(P, off, L, T, tile.frame0 + f, n, (uint32_t)tile.utt);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double warp_sums[kGenericThreads / 32];
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kGenericThreads / 32; ++w) s += warp_sums[w];
+    atomicAdd(&utt_sum[tile.utt], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main generic kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(GenericParams P) {
+  extern __shared__ float2 smem[];
+  const int N = P.n_fft;
+  const int pairs = P.pairs;
+  float2* cur = smem;
+  float2* nxt = smem + (size_t)pairs * N;
+
+  const Tile tile = P.tiles[blockIdx.x];
+  const uint32_t utt = (uint32_t)tile.utt;
+  const int64_t off = P.sample_offsets[utt];
+  const int64_t L = P.sample_offsets[utt + 1] - off;
+  const int64_t fo = P.frame_offsets[utt];
+  const int64_t T = P.frame_offsets[utt + 1] - fo;
+  float mu = 0.0f;
+  if (P.remove_mean) mu = (float)(P.utt_sum[utt] / ((double)T * (double)P.frame_len));
+
+  // ---- load: frame pair p -> complex sequence a + i b, windowed, scalar mean removed ----
+  for (int idx = threadIdx.x; idx < pairs * N; idx += blockDim.x) {
+    int p = idx / N, n = idx - p * N;
+    int64_t fa = tile.frame0 + 2 * p;
+    float a = frame_entry(P, off, L, T, fa, n, utt);
+    float b = frame_entry(P, off, L, T, fa + 1, n, utt);
+    if (n < P.frame_len) {
+      if (fa < T) a -= mu;
+      if (fa + 1 < T) b -= mu;
+    }
+    cur[idx] = make_float2(a, b);
+  }
+  __syncthreads();
+
+  // ---- Stockham autosort stages ----
+  {
+    float2* res = stockham_fft(cur, nxt, pairs, N, P.fft, P.tw);
+    if (res != cur) { nxt = cur; cur = res; }
+  }
+
+  // ---- separate the pair, emit ----
+  const int nb = P.n_bins;
+  float* pw = reinterpret_cast<float*>(nxt);  // [2*pairs][nb] power spectra (aliases the idle buffer)
+  const float sc = P.spec_scale;
+  for (int idx = threadIdx.x; idx < pairs * nb; idx += blockDim.x) {
+    int p = idx / nb, k = idx - p * nb;
+    float2 za = cur[(size_t)p * N + k];
+    float2 zr = cur[(size_t)p * N + (k == 0 ? 0 : N - k)];
+    float2 xa = make_float2(0.5f * (za.x + zr.x) * sc, 0.5f * (za.y - zr.y) * sc);
+    float2 xb = make_float2(0.5f * (za.y + zr.y) * sc, -0.5f * (za.x - zr.x) * sc);
+    int64_t fa = tile.frame0 + 2 * p;
+    if (P.out_kind == MAFE_OUT_COMPLEX) {
+      if (fa < T) reinterpret_cast<float2*>(P.out + (fo + fa) * P.out_dim)[k] = xa;
+      if (fa + 1 < T) reinterpret_cast<float2*>(P.out + (fo + fa + 1) * P.out_dim)[k] = xb;
+    } else {
+      float pa = fmaf(xa.x, xa.x, xa.y * xa.y), pb = fmaf(xb.x, xb.x, xb.y * xb.y);
+      if (P.power != 2.0f) {
+        if (P.power == 1.0f) { pa = sqrtf(pa); pb = sqrtf(pb); }
+        else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
+      }
+      if (P.out_kind == MAFE_OUT_POWER) {
+        if (fa < T) P.out[(fo + fa) * P.out_dim + k] = pa;
+        if (fa + 1 < T) P.out[(fo + fa + 1) * P.out_dim + k] = pb;
+      } else {
+        pw[(2 * p) * nb + k] = pa;
+        pw[(2 * p + 1) * nb + k] = pb;
+      }
+    }
+  }
+  if (P.out_kind <= MAFE_OUT_POWER) return;
+  __syncthreads();
+
+  // ---- sparse mel projection (CSR by filter) + log ----
+  float vmax = -INFINITY;
+  const int nm = P.n_mels;
+  for (int idx = threadIdx.x; idx < 2 * pairs * nm; idx += blockDim.x) {
+    int f = idx / nm, m = idx - f * nm;
+    if (tile.frame0 + f >= T) continue;
+    const float* row = pw + f * nb;
+    float acc = 0.f;
+    for (int i = P.row_ptr[m]; i < P.row_ptr[m + 1]; ++i) acc = fmaf(__ldg(&P.val[i]), row[__ldg(&P.col[i])], acc);
+    float o = acc;
+    switch (P.log_kind) {
+      case MAFE_LOG_LN_EPS_IF_ZERO: o = logf(acc == 0.f ? 2.220446049250313e-16f : acc); break;
+      case MAFE_LOG_LN_PLUS: o = logf(acc + P.log_arg); break;
+      case MAFE_LOG_DB: o = P.log_mult * log10f(fmaxf(acc, P.log_arg)) - P.log_offset; vmax = fmaxf(vmax, o); break;
+      default: break;
+    }
+    P.out[(fo + tile.frame0 + f) * P.out_dim + m] = o;
+  }
+  if (P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE) {
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) {
+      int g = P.db_group == MAFE_DBGROUP_UTT ? (int)utt : (P.db_group == MAFE_DBGROUP_BATCH ? 0 : P.utt_group[utt]);
+      atomicMax(&P.group_max[g], ordered_key(vmax));
+    }
+  }
+}
+
+// top_db clamp in place: x = max(x, groupmax - top_db)   (spectrum.py:78-89)
+__global__ void db_clamp_kernel(float* data, int dim, const Tile* tiles, const int64_t* frame_offsets, int tile_frames,
+                                const int* group_max, const int* utt_group, int db_group, float top_db) {
+  const Tile tile = tiles[blockIdx.x];
+  const int64_t fo = frame_offsets[tile.utt];
+  const int64_t T = frame_offsets[tile.utt + 1] - fo;
+  int nf = (int)min((int64_t)tile_frames, T - tile.frame0);
+  int g = db_group == MAFE_DBGROUP_UTT ? tile.utt : (db_group == MAFE_DBGROUP_BATCH ? 0 : utt_group[tile.utt]);
+  const float floor_v = key_to_float(group_max[g]) - top_db;
+  float* base = data + (fo + tile.frame0) * dim;
+  for (int i = threadIdx.x; i < nf * dim; i += blockDim.x) base[i] = fmaxf(base[i], floor_v);
+}
+
+// MFCC: out[f][c] = sum_m clamp(logmel[f][m]) * dct[m][c]   (features.py:356-361)
+__global__ void dct_kernel(const float* logmel, float* out, int n_mels, int n_mfcc, const float* dct, const Tile* tiles,
+                           const int64_t* frame_offsets, int tile_frames, const int* group_max, const int* utt_group,
+                           int db_group, float top_db) {
+  extern __shared__ float sm[];
+  float* sd = sm;                       // [n_mels][n_mfcc]
+  float* sx = sm + n_mels * n_mfcc;     // [tile_frames][n_mels]
+  const Tile tile = tiles[blockIdx.x];
+  const int64_t fo = frame_offsets[tile.utt];
+  const int64_t T = frame_offsets[tile.utt + 1] - fo;
+  int nf = (int)min((int64_t)tile_frames, T - tile.frame0);
+  float floor_v = -INFINITY;
+  if (db_group != MAFE_DBGROUP_NONE) {
+    int g = db_group == MAFE_DBGROUP_UTT ? tile.utt : (db_group == MAFE_DBGROUP_BATCH ? 0 : utt_group[tile.utt]);
+    floor_v = key_to_float(group_max[g]) - top_db;
+  }
+  for (int i = threadIdx.x; i < n_mels * n_mfcc; i += blockDim.x) sd[i] = dct[i];
+  const float* src = logmel + (fo + tile.frame0) * n_mels;
+  for (int i = threadIdx.x; i < nf * n_mels; i += blockDim.x) sx[i] = fmaxf(src[i], floor_v);
+  __syncthreads();
+  float* dst = out + (fo + tile.frame0) * n_mfcc;
+  for (int i = threadIdx.x; i < nf * n_mfcc; i += blockDim.x) {
+    int f = i / n_mfcc, c = i - f * n_mfcc;
+    float acc = 0.f;
+    for (int m = 0; m < n_mels; ++m) acc = fmaf(sx[f * n_mels + m], sd[m * n_mfcc + c], acc);
+    dst[i] = acc;
+  }
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static void factorize(int n, std::vector<int>& out) {
+  out.clear();
+  while (n % 4 == 0) { out.push_back(4); n /= 4; }
+  while (n % 2 == 0) { out.push_back(2); n /= 2; }
+  while (n % 3 == 0) { out.push_back(3); n /= 3; }
+  while (n % 5 == 0) { out.push_back(5); n /= 5; }
+  for (int f = 7; (long long)f * f <= n; f += 2)
+    while (n % f == 0) { out.push_back(f); n /= f; }
+  if (n > 1) out.push_back(n);
+}
+
+template <typename T>
+static int upload(T** dev, const T* host, size_t n) {
+  MAFE_CUDA_CHECK(cudaMalloc((void**)dev, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) MAFE_CUDA_CHECK(cudaMemcpy(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return MAFE_OK;
+}
+
+int generic_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
+  const int N = d->n_fft;
+  factorize(N, p->radices);
+  MAFE_REQUIRE((int)p->radices.size() <= kMaxStages, "n_fft=%d has too many factors", N);
+  p->n_stages = (int)p->radices.size();
+  // tile size: as many frame pairs as fit ~64 KB of ping-pong buffers, 1..8
+  size_t per_pair = (size_t)N * sizeof(float2) * 2;
+  int pairs = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / per_pair));
+  p->pairs_per_tile = pairs;
+  p->tile_frames = 2 * pairs;
+  p->smem_bytes = per_pair * pairs;
+  if (p->smem_bytes > 200 * 1024) {
+    set_error("n_fft=%d needs %zu bytes of shared memory per frame pair (max n_fft is 8192)", N, p->smem_bytes);
+    return MAFE_E_UNSUPPORTED;
+  }
+  if (d->out_kind >= MAFE_OUT_MEL) {
+    // the power buffer [2*pairs][n_bins] aliases one ping-pong buffer: always fits (n_bins <= N)
+  }
+  std::vector<float2> tw(N);
+  for (int k = 0; k < N; ++k) {
+    double a = -2.0 * M_PI * (double)k / (double)N;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  int rc = upload(&p->twiddle_dev, tw.data(), tw.size());
+  if (rc) return rc;
+  rc = upload(&p->window_dev, d->window, (size_t)d->frame_len);
+  if (rc) return rc;
+  if (d->out_kind >= MAFE_OUT_MEL) {
+    std::vector<int> row_ptr(d->n_mels + 1, 0), col;
+    std::vector<float> val;
+    for (int m = 0; m < d->n_mels; ++m) {
+      for (int k = 0; k < p->n_bins; ++k) {
+        float w = d->mel_fb[(size_t)m * p->n_bins + k];
+        if (w != 0.0f) { col.push_back(k); val.push_back(w); }
+      }
+      row_ptr[m + 1] = (int)col.size();
+    }
+    p->mel.nnz = (int)col.size();
+    if ((rc = upload(&p->mel.row_ptr, row_ptr.data(), row_ptr.size()))) return rc;
+    if ((rc = upload(&p->mel.col, col.data(), col.size()))) return rc;
+    if ((rc = upload(&p->mel.val, val.data(), val.size()))) return rc;
+  }
+  if (d->out_kind == MAFE_OUT_MFCC) {
+    if ((rc = upload(&p->dct_dev, d->dct, (size_t)d->n_mels * d->n_mfcc))) return rc;
+  }
+  if (p->smem_bytes > 48 * 1024)
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(generic_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)p->smem_bytes));
+  (void)ctx;
+  return MAFE_OK;
+}
+
+void generic_plan_free(mafe_plan* p) {
+  cudaFree(p->twiddle_dev);
+  cudaFree(p->window_dev);
+  cudaFree(p->mel.row_ptr);
+  cudaFree(p->mel.col);
+  cudaFree(p->mel.val);
+  cudaFree(p->dct_dev);
+}
+
+static void fill_params(GenericParams& P, const mafe_plan* p, const mafe_batch* b, const void* wave, int wave_dtype,
+                        float wave_scale) {
+  const mafe_frontend_desc& d = p->d;
+  P.wave = wave; P.wave_dtype = wave_dtype; P.wave_scale = wave_scale;
+  P.sample_offsets = b->sample_offsets_dev; P.frame_offsets = b->frame_offsets_dev; P.tiles = b->tiles_dev;
+  P.utt_sum = b->utt_sum_dev;
+  P.n_fft = d.n_fft; P.frame_len = d.frame_len; P.hop = d.hop; P.center = d.center; P.pad_mode = d.pad_mode;
+  P.n_bins = p->n_bins;
+  P.pre_hi = (float)d.preemph; P.pre_lo = (float)(d.preemph - (double)P.pre_hi);
+  P.preemph_on = d.preemph != 0.0; P.remove_mean = d.remove_frame_mean;
+  P.dither = d.dither; P.seed = d.dither_seed;
+  P.window = p->window_dev; P.tw = p->twiddle_dev;
+  for (int i = 0; i < kMaxStages; ++i) P.fft.radices[i] = i < p->n_stages ? p->radices[i] : 1;
+  P.fft.n_stages = p->n_stages; P.pairs = p->pairs_per_tile;
+  P.out_kind = d.out_kind; P.power = d.power; P.spec_scale = d.spec_scale;
+  P.n_mels = d.n_mels; P.row_ptr = p->mel.row_ptr; P.col = p->mel.col; P.val = p->mel.val;
+  P.log_kind = d.log_kind; P.log_arg = d.log_arg; P.log_mult = d.log_mult; P.log_offset = d.log_offset;
+  P.out = nullptr; P.out_dim = p->out_dim;
+  P.group_max = b->group_max_dev; P.utt_group = b->utt_group_dev; P.db_group = MAFE_DBGROUP_NONE;
+}
+
+int frame_mean_prepass(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype,
+                       float wave_scale) {
+  if (b->n_tiles == 0) return MAFE_OK;
+  GenericParams P;
+  fill_params(P, p, b, wave, wave_dtype, wave_scale);
+  MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
+  frame_sum_kernel<<<b->n_tiles, kGenericThreads, 0, ctx->stream>>>(P, b->utt_sum_dev, p->tile_frames);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int generic_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale,
+                float* out, int out_kind_override, int db_group) {
+  if (b->n_tiles == 0) return MAFE_OK;
+  GenericParams P;
+  fill_params(P, p, b, wave, wave_dtype, wave_scale);
+  if (p->d.remove_frame_mean) {
+    int rc = frame_mean_prepass(ctx, p, b, wave, wave_dtype, wave_scale);
+    if (rc) return rc;
+  }
+  P.out = out;
+  if (out_kind_override >= 0) {
+    P.out_kind = out_kind_override;
+    P.out_dim = out_kind_override == MAFE_OUT_LOGMEL ? p->d.n_mels : p->out_dim;
+  }
+  P.db_group = (p->d.log_kind == MAFE_LOG_DB && p->d.top_db >= 0.f) ? db_group : MAFE_DBGROUP_NONE;
+  if (P.db_group != MAFE_DBGROUP_NONE) {
+    int n = std::max(b->n_groups, 1);
+    fill_int_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->group_max_dev, n, (int)0x80000000);
+    MAFE_LAUNCH_CHECK(ctx);
+  }
+  generic_frontend_kernel<<<b->n_tiles, kGenericThreads, p->smem_bytes, ctx->stream>>>(P);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int db_clamp_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, float* data, int dim, int db_group) {
+  if (b->n_tiles == 0 || db_group == MAFE_DBGROUP_NONE || p->d.top_db < 0.f) return MAFE_OK;
+  db_clamp_kernel<<<b->n_tiles, 256, 0, ctx->stream>>>(data, dim, b->tiles_dev, b->frame_offsets_dev, p->tile_frames,
+                                                       b->group_max_dev, b->utt_group_dev, db_group, p->d.top_db);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int dct_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const float* logmel, float* out, int db_group) {
+  if (b->n_tiles == 0) return MAFE_OK;
+  const int nm = p->d.n_mels, nc = p->d.n_mfcc;
+  size_t smem = sizeof(float) * ((size_t)nm * nc + (size_t)p->tile_frames * nm);
+  if (smem > 48 * 1024) {
+    MAFE_REQUIRE(smem <= 200 * 1024, "DCT table %dx%d does not fit in shared memory", nm, nc);
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  bool clamp = p->d.log_kind == MAFE_LOG_DB && p->d.top_db >= 0.f && db_group != MAFE_DBGROUP_NONE;
+  dct_kernel<<<b->n_tiles, 256, smem, ctx->stream>>>(logmel, out, nm, nc, p->dct_dev, b->tiles_dev, b->frame_offsets_dev,
+                                                     p->tile_frames, b->group_max_dev, b->utt_group_dev,
+                                                     clamp ? db_group : MAFE_DBGROUP_NONE, p->d.top_db);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+}  // namespace mafe

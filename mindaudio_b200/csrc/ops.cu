@@ -1,0 +1,446 @@
+// ops.cu -- element-wise spectral ops, the CMVN family and the feature post-processing kernels.
+// HBM-bound integer/float streaming work: coalesced, vectorised where alignment allows, grids
+// sized in multiples of the SM count, warp/block reductions for the statistics.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mafe {
+
+static inline int grid_for(const mafe_ctx* ctx, int64_t work_items, int per_block, int max_waves = 32) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)ctx->sm_count * max_waves;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+// ------------------------------------------------------------------ magphase (spectrum.py:720-732)
+__global__ void magphase_kernel(const float2* __restrict__ z, int64_t n, float power, float* __restrict__ mag,
+                                float2* __restrict__ phase) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 v = z[i];
+    float m = hypotf(v.x, v.y);
+    float zero = m == 0.f ? 1.f : 0.f;
+    float den = m + zero;
+    if (phase) phase[i] = make_float2(v.x / den + zero, v.y / den);
+    if (mag) mag[i] = power == 1.f ? m : (power == 2.f ? m * m : powf(m, power));
+  }
+}
+
+// ------------------------------------------------------------------ amplitude_to_dB (spectrum.py:59-90)
+__global__ void to_db_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t group_size, int blocks_per_group,
+                             float mult, float amin, float db_offset, int* group_max) {
+  const int64_t g = blockIdx.x / blocks_per_group;
+  const int chunk = blockIdx.x - (int)(g * blocks_per_group);
+  const int64_t per = (group_size + blocks_per_group - 1) / blocks_per_group;
+  const int64_t lo = chunk * per, hi = min(group_size, lo + per);
+  const float* xs = x + g * group_size;
+  float* os = out + g * group_size;
+  float vmax = -INFINITY;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float v = mult * log10f(fmaxf(xs[i], amin)) - db_offset;
+    os[i] = v;
+    vmax = fmaxf(vmax, v);
+  }
+  if (group_max) {
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&group_max[g], ordered_key(vmax));
+  }
+}
+
+__global__ void clamp_group_kernel(float* __restrict__ out, int64_t group_size, int blocks_per_group, const int* group_max,
+                                   float top_db) {
+  const int64_t g = blockIdx.x / blocks_per_group;
+  const int chunk = blockIdx.x - (int)(g * blocks_per_group);
+  const int64_t per = (group_size + blocks_per_group - 1) / blocks_per_group;
+  const int64_t lo = chunk * per, hi = min(group_size, lo + per);
+  const float floor_v = key_to_float(group_max[g]) - top_db;
+  float* os = out + g * group_size;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) os[i] = fmaxf(os[i], floor_v);
+}
+
+__global__ void fill_i32_kernel(int* p, int64_t n, int v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------ dB_to_amplitude (spectrum.py:108-113)
+__global__ void from_db_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, float ref, float power) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ref * powf(exp10f(0.1f * x[i]), power);
+}
+
+// ------------------------------------------------------------------ utterance CMVN (spec_augment.py:43-70)
+// one CTA per utterance; thread (r, d) strides over frames r, r+rows, ...; double accumulators;
+// the second pass re-reads the utterance's features (L2-resident: <= a few hundred KB).
+constexpr int kCmvnThreads = 256;
+
+__global__ void __launch_bounds__(kCmvnThreads) cmvn_utt_kernel(float* __restrict__ feats, const int64_t* __restrict__ fo,
+                                                                int dim, int mean_norm, int std_norm) {
+  __shared__ double sh[2 * kCmvnThreads];   // partial sums / sums of squares per thread
+  __shared__ float s_mean[2 * kCmvnThreads]; // (mean, 1/std) per column of the current tile
+  const int u = blockIdx.x;
+  const int64_t f0 = fo[u];
+  const int T = (int)(fo[u + 1] - f0);
+  if (T <= 0) return;
+  float* x = feats + f0 * dim;
+  // column tiles of up to kCmvnThreads dims; rows = threads / min(dim, threads)
+  for (int d0 = 0; d0 < dim; d0 += kCmvnThreads) {
+    const int dw = min(dim - d0, kCmvnThreads);
+    const int rows = kCmvnThreads / dw;
+    const int r = threadIdx.x / dw, d = threadIdx.x - r * dw;
+    double s1 = 0.0, s2 = 0.0;
+    if (r < rows) {
+      for (int f = r; f < T; f += rows) {
+        double v = (double)x[(int64_t)f * dim + d0 + d];
+        s1 += v;
+        s2 += v * v;
+      }
+    }
+    sh[threadIdx.x] = s1;
+    sh[kCmvnThreads + threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < dw) {
+      double a = 0.0, b = 0.0;
+      for (int rr = 0; rr < rows; ++rr) { a += sh[rr * dw + threadIdx.x]; b += sh[kCmvnThreads + rr * dw + threadIdx.x]; }
+      double mean = a / T;
+      double var = b / T - mean * mean;  // population variance (np.std, ddof=0)
+      if (var < 0.0) var = 0.0;
+      float m = mean_norm ? (float)mean : 0.f;
+      float inv = std_norm ? (float)(1.0 / sqrt(var)) : 1.f;  // NO eps: spec_augment.py:54 divides by the raw std
+      // second pass for this column tile
+      s_mean[2 * threadIdx.x] = m;
+      s_mean[2 * threadIdx.x + 1] = inv;
+    }
+    __syncthreads();
+    if (r < rows) {
+      const float m = s_mean[2 * d], inv = s_mean[2 * d + 1];
+      for (int f = r; f < T; f += rows) {
+        int64_t i = (int64_t)f * dim + d0 + d;
+        x[i] = (x[i] - m) * inv;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ scalar norm (deepspeech2/dataset.py:43-47)
+__global__ void __launch_bounds__(kCmvnThreads) cmvn_scalar_kernel(float* __restrict__ feats, const int64_t* __restrict__ fo,
+                                                                   int dim, int log1p_first) {
+  __shared__ double s1s[kCmvnThreads / 32], s2s[kCmvnThreads / 32];
+  __shared__ float s_m, s_inv;
+  const int u = blockIdx.x;
+  const int64_t n = (fo[u + 1] - fo[u]) * dim;
+  if (n <= 0) return;
+  float* x = feats + fo[u] * dim;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = x[i];
+    if (log1p_first) v = log1pf(v);
+    s1 += (double)v;
+    s2 += (double)v * (double)v;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { s1s[threadIdx.x >> 5] = s1; s2s[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < kCmvnThreads / 32; ++w) { a += s1s[w]; b += s2s[w]; }
+    double mean = a / (double)n, var = b / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_m = (float)mean;
+    s_inv = (float)(1.0 / sqrt(var));
+  }
+  __syncthreads();
+  const float m = s_m, inv = s_inv;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = x[i];
+    if (log1p_first) v = log1pf(v);
+    x[i] = (v - m) * inv;
+  }
+}
+
+// ------------------------------------------------------------------ global CMVN stats (compute_cmvn_stats.py:61-63)
+__global__ void __launch_bounds__(kCmvnThreads) cmvn_stats_kernel(const float* __restrict__ feats, int64_t total_frames,
+                                                                  int dim, double* __restrict__ stats) {
+  // frames are split evenly over the grid; thread (r, d) as in cmvn_utt_kernel
+  __shared__ double sh[2 * kCmvnThreads];
+  const int64_t per = (total_frames + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * per, hi = min(total_frames, lo + per);
+  for (int d0 = 0; d0 < dim; d0 += kCmvnThreads) {
+    const int dw = min(dim - d0, kCmvnThreads);
+    const int rows = kCmvnThreads / dw;
+    const int r = threadIdx.x / dw, d = threadIdx.x - r * dw;
+    double s1 = 0.0, s2 = 0.0;
+    if (r < rows)
+      for (int64_t f = lo + r; f < hi; f += rows) {
+        double v = (double)feats[f * dim + d0 + d];
+        s1 += v;
+        s2 += v * v;
+      }
+    sh[threadIdx.x] = s1;
+    sh[kCmvnThreads + threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < dw) {
+      double a = 0.0, b = 0.0;
+      for (int rr = 0; rr < rows; ++rr) { a += sh[rr * dw + threadIdx.x]; b += sh[kCmvnThreads + rr * dw + threadIdx.x]; }
+      atomicAdd(&stats[d0 + threadIdx.x], a);
+      atomicAdd(&stats[dim + d0 + threadIdx.x], b);
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[2 * dim], (double)total_frames);
+}
+
+// ------------------------------------------------------------------ global CMVN apply (cmvn.py:33-36)
+__global__ void cmvn_apply_kernel(float* __restrict__ feats, int64_t n, int dim, const float* __restrict__ mean,
+                                  const float* __restrict__ istd) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int d = (int)(i % dim);
+    float v = feats[i] - mean[d];
+    if (istd) v *= istd[d];
+    feats[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ compute_deltas (features.py:158-193, A8)
+__global__ void deltas_kernel(const float* __restrict__ x, float* __restrict__ out, int n_mats, int rows, int t, int64_t xs,
+                              int64_t os, int n, float inv_denom, int pad_mode) {
+  const int64_t per = (int64_t)rows * t;
+  const int64_t total = (int64_t)n_mats * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t mat = i / per, rem = i - mat * per;
+    int64_t r = rem / t;
+    int c = (int)(rem - r * t);
+    const float* row = x + mat * xs + r * t;
+    float acc = 0.f;
+    for (int k = -n; k <= n; ++k) {
+      int64_t j = pad_index(c + k, t, pad_mode);
+      if (j >= 0) acc = fmaf((float)k, row[j], acc);
+    }
+    out[mat * os + rem] = acc * inv_denom;
+  }
+}
+
+// ------------------------------------------------------------------ context_window (features.py:94-155 as a gather)
+__global__ void context_kernel(const float* __restrict__ x, float* __restrict__ out, int n_mats, int f, int t, int csize, int ksz,
+                               int mf, int roll) {
+  const int64_t total = (int64_t)n_mats * f * csize * t;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int tt = (int)(i % t);
+    int64_t q = i / t;
+    int c = (int)(q % csize);
+    int64_t fm = q / csize;  // mat * f + row
+    int tap = (c + roll) % ksz;
+    int src = tt + tap - mf;
+    out[i] = (src >= 0 && src < t) ? x[fm * t + src] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ melscale (spectrum.py:738-774)
+__global__ void melscale_kernel(const float* __restrict__ spec, float* __restrict__ out, int n_mats, int n_bins, int t, int n_mels,
+                                const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val) {
+  const int64_t total = (int64_t)n_mats * n_mels * t;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int tt = (int)(i % t);
+    int64_t q = i / t;
+    int m = (int)(q % n_mels);
+    int64_t mat = q / n_mels;
+    const float* base = spec + mat * n_bins * (int64_t)t + tt;
+    float acc = 0.f;
+    for (int j = row_ptr[m]; j < row_ptr[m + 1]; ++j) acc = fmaf(val[j], base[(int64_t)col[j] * t], acc);
+    out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ transpose [rows][cols] -> [cols][rows]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int64_t os) {
+  __shared__ float tile[32][33];
+  const float* src = in + (int64_t)blockIdx.z * rows * cols;
+  float* dst = out + (int64_t)blockIdx.z * os;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[(int64_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(int64_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace mafe
+
+using namespace mafe;
+
+extern "C" {
+
+int mafe_magphase(mafe_ctx* ctx, const float* z, int64_t n, float power, float* mag, float* phase) {
+  MAFE_REQUIRE(ctx && (z || n == 0), "mafe_magphase: NULL argument");
+  MAFE_REQUIRE(power >= 0.f, "power must be non-negative");
+  if (n == 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  magphase_kernel<<<grid_for(ctx, n, 256 * 4), 256, 0, ctx->stream>>>((const float2*)z, n, power, mag, (float2*)phase);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_amplitude_to_db(mafe_ctx* ctx, const float* x, float* out, int64_t n_groups, int64_t group_size, float mult,
+                         float amin, float db_offset, float top_db) {
+  MAFE_REQUIRE(ctx && ((x && out) || n_groups * group_size == 0), "mafe_amplitude_to_db: NULL argument");
+  if (n_groups <= 0 || group_size <= 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  // enough blocks per group to fill the machine, chunks of >= 4096 elements
+  int64_t want = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 8 + n_groups - 1) / n_groups);
+  int bpg = (int)std::max<int64_t>(1, std::min<int64_t>(want, (group_size + 4095) / 4096));
+  MAFE_REQUIRE(n_groups * bpg < (int64_t)INT32_MAX, "too many groups");
+  int* gmax = nullptr;
+  if (top_db >= 0.f) {
+    MAFE_CUDA_CHECK(cudaMallocAsync((void**)&gmax, n_groups * sizeof(int), ctx->stream));
+    fill_i32_kernel<<<(int)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(gmax, n_groups, (int)0x80000000);
+    MAFE_LAUNCH_CHECK(ctx);
+  }
+  to_db_kernel<<<(int)(n_groups * bpg), 256, 0, ctx->stream>>>(x, out, group_size, bpg, mult, amin, db_offset, gmax);
+  MAFE_LAUNCH_CHECK(ctx);
+  if (gmax) {
+    clamp_group_kernel<<<(int)(n_groups * bpg), 256, 0, ctx->stream>>>(out, group_size, bpg, gmax, top_db);
+    MAFE_LAUNCH_CHECK(ctx);
+    MAFE_CUDA_CHECK(cudaFreeAsync(gmax, ctx->stream));
+  }
+  return MAFE_OK;
+}
+
+int mafe_db_to_amplitude(mafe_ctx* ctx, const float* x, float* out, int64_t n, float ref, float power) {
+  MAFE_REQUIRE(ctx && ((x && out) || n == 0), "mafe_db_to_amplitude: NULL argument");
+  if (n == 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  from_db_kernel<<<grid_for(ctx, n, 256 * 4), 256, 0, ctx->stream>>>(x, out, n, ref, power);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_cmvn_utt(mafe_ctx* ctx, float* feats, const int64_t* fo, int32_t n_utts, int32_t dim, int32_t mean_norm,
+                  int32_t std_norm) {
+  MAFE_REQUIRE(ctx && fo && (feats || n_utts == 0), "mafe_cmvn_utt: NULL argument");
+  MAFE_REQUIRE(dim >= 1, "dim=%d", dim);
+  if (n_utts <= 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  cmvn_utt_kernel<<<n_utts, kCmvnThreads, 0, ctx->stream>>>(feats, fo, dim, mean_norm, std_norm);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_cmvn_scalar(mafe_ctx* ctx, float* feats, const int64_t* fo, int32_t n_utts, int32_t dim, int32_t log1p_first) {
+  MAFE_REQUIRE(ctx && fo && (feats || n_utts == 0), "mafe_cmvn_scalar: NULL argument");
+  if (n_utts <= 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  cmvn_scalar_kernel<<<n_utts, kCmvnThreads, 0, ctx->stream>>>(feats, fo, dim, log1p_first);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_cmvn_stats_accumulate(mafe_ctx* ctx, const float* feats, int64_t total_frames, int32_t dim, double* stats) {
+  MAFE_REQUIRE(ctx && stats && (feats || total_frames == 0), "mafe_cmvn_stats_accumulate: NULL argument");
+  if (total_frames <= 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, std::max<int64_t>(1, total_frames / 64));
+  cmvn_stats_kernel<<<grid, kCmvnThreads, 0, ctx->stream>>>(feats, total_frames, dim, stats);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_cmvn_apply(mafe_ctx* ctx, float* feats, int64_t total_frames, int32_t dim, const float* mean, const float* istd) {
+  MAFE_REQUIRE(ctx && mean && (feats || total_frames == 0), "mafe_cmvn_apply: NULL argument");
+  if (total_frames <= 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  int64_t n = total_frames * dim;
+  cmvn_apply_kernel<<<grid_for(ctx, n, 256 * 4), 256, 0, ctx->stream>>>(feats, n, dim, mean, istd);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_melscale(mafe_ctx* ctx, const float* spec, float* out, int32_t n_mats, int32_t n_bins, int32_t t, const float* fb,
+                  int32_t n_mels) {
+  MAFE_REQUIRE(ctx && fb, "mafe_melscale: NULL argument");
+  MAFE_REQUIRE(n_bins >= 1 && n_mels >= 1, "bad filterbank shape %dx%d", n_mels, n_bins);
+  if (n_mats <= 0 || t <= 0) return MAFE_OK;
+  MAFE_REQUIRE(spec && out, "mafe_melscale: NULL buffer");
+  cudaSetDevice(ctx->device);
+  std::vector<int> row_ptr(n_mels + 1, 0), col;
+  std::vector<float> val;
+  for (int m = 0; m < n_mels; ++m) {
+    for (int k = 0; k < n_bins; ++k)
+      if (fb[(size_t)m * n_bins + k] != 0.f) { col.push_back(k); val.push_back(fb[(size_t)m * n_bins + k]); }
+    row_ptr[m + 1] = (int)col.size();
+  }
+  if (col.empty()) { col.push_back(0); val.push_back(0.f); }
+  int *d_rp = nullptr, *d_col = nullptr;
+  float* d_val = nullptr;
+  cudaStream_t st = ctx->stream;
+  MAFE_CUDA_CHECK(cudaMallocAsync((void**)&d_rp, row_ptr.size() * 4, st));
+  MAFE_CUDA_CHECK(cudaMallocAsync((void**)&d_col, col.size() * 4, st));
+  MAFE_CUDA_CHECK(cudaMallocAsync((void**)&d_val, val.size() * 4, st));
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(d_rp, row_ptr.data(), row_ptr.size() * 4, cudaMemcpyHostToDevice, st));
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice, st));
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(d_val, val.data(), val.size() * 4, cudaMemcpyHostToDevice, st));
+  int64_t total = (int64_t)n_mats * n_mels * t;
+  melscale_kernel<<<grid_for(ctx, total, 256), 256, 0, st>>>(spec, out, n_mats, n_bins, t, n_mels, d_rp, d_col, d_val);
+  MAFE_LAUNCH_CHECK(ctx);
+  MAFE_CUDA_CHECK(cudaStreamSynchronize(st));  // host CSR vectors must outlive the copies
+  MAFE_CUDA_CHECK(cudaFreeAsync(d_rp, st));
+  MAFE_CUDA_CHECK(cudaFreeAsync(d_col, st));
+  MAFE_CUDA_CHECK(cudaFreeAsync(d_val, st));
+  return MAFE_OK;
+}
+
+int mafe_transpose(mafe_ctx* ctx, const float* in, float* out, int32_t n_mats, int32_t rows, int32_t cols,
+                   int64_t out_mat_stride) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (n_mats <= 0 || rows <= 0 || cols <= 0) return MAFE_OK;
+  MAFE_REQUIRE(in && out, "mafe_transpose: NULL buffer");
+  MAFE_REQUIRE(n_mats <= 65535 && (rows + 31) / 32 <= 65535, "mafe_transpose: shape too large");
+  cudaSetDevice(ctx->device);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, n_mats), block(32, 8);
+  if (out_mat_stride == 0) out_mat_stride = (int64_t)rows * cols;
+  MAFE_REQUIRE(out_mat_stride >= (int64_t)rows * cols, "out_mat_stride too small");
+  transpose_kernel<<<grid, block, 0, ctx->stream>>>(in, out, rows, cols, out_mat_stride);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_compute_deltas(mafe_ctx* ctx, const float* x, float* out, int32_t n_mats, int32_t rows, int32_t t, int64_t xs,
+                        int64_t os, int32_t win_length, int32_t pad_mode) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(win_length >= 3, "win_length must be no less than 3");
+  MAFE_REQUIRE(pad_mode >= MAFE_PAD_CONSTANT && pad_mode <= MAFE_PAD_SYMMETRIC, "bad pad_mode %d", pad_mode);
+  if (n_mats <= 0 || rows <= 0 || t <= 0) return MAFE_OK;
+  MAFE_REQUIRE(x && out, "mafe_compute_deltas: NULL buffer");
+  cudaSetDevice(ctx->device);
+  if (xs == 0) xs = (int64_t)rows * t;
+  if (os == 0) os = (int64_t)rows * t;
+  int n = (win_length - 1) / 2;
+  float inv = (float)(1.0 / ((double)n * (n + 1) * (2 * n + 1) / 3.0));
+  deltas_kernel<<<grid_for(ctx, (int64_t)n_mats * rows * t, 256 * 2), 256, 0, ctx->stream>>>(x, out, n_mats, rows, t, xs, os, n,
+                                                                                            inv, pad_mode);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_context_window(mafe_ctx* ctx, const float* x, float* out, int32_t n_mats, int32_t f, int32_t t, int32_t left,
+                        int32_t right) {
+  MAFE_REQUIRE(ctx && ((x && out) || n_mats == 0), "mafe_context_window: NULL argument");
+  MAFE_REQUIRE(left >= 0 && right >= 0, "negative context");
+  if (n_mats <= 0 || f <= 0 || t <= 0) return MAFE_OK;
+  cudaSetDevice(ctx->device);
+  int csize = left + right + 1, mf = std::max(left, right), ksz = 2 * mf + 1;
+  int roll = right > left ? right - left : 0;
+  int64_t total = (int64_t)n_mats * f * csize * t;
+  context_kernel<<<grid_for(ctx, total, 256 * 2), 256, 0, ctx->stream>>>(x, out, n_mats, f, t, csize, ksz, mf, roll);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""Drop-in for ``mindaudio.data.features`` (mindaudio/data/features.py) on B200: ``fbank`` (alias
+``fbanks`` -- README.md:41 / features.py:247 use that name), ``mfcc``, ``compute_deltas``,
+``context_window``.  Same signatures, defaults and numpy semantics as the reference; arithmetic
+in libmafe.so.  ``mfcc`` keeps the reference defaults ``deltas=True, context=True``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib as L
+from .. import _tables as T
+from .._engine import get_engine
+from .._enums import BorderType, NormMode
+from . import spectrum as _sp
+
+__all__ = [
+    "context_window",
+    "compute_deltas",
+    "fbank",
+    "fbanks",
+    "mfcc",
+]
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _context_dev(eng, d_in, d_out, n_mats, f, t, left, right):
+    L.check(eng.lib.mafe_context_window(eng.ctx, d_in, d_out, n_mats, f, t, left, right))
+
+
+def context_window(waveforms, left_frames=0, right_frames=0):
+    """``features.py:69-155``: gather +-k frames into one feature vector (the reference's grouped
+    identity-kernel Conv1d, as a pure gather; float32 out).  ``[freq, time]``, ``[batch, freq,
+    time]`` or ``[batch, channel, freq, time]``."""
+    waveforms = np.asarray(waveforms)
+    nd = waveforms.ndim
+    if nd == 2:
+        x = waveforms[None]
+    elif nd == 3:
+        x = waveforms
+    elif nd == 4:
+        # the reference moves channels last, folds (batch, time) and convolves along the channel
+        # axis (features.py:108-126); reproduced literally
+        b, ch, f, t = waveforms.shape
+        x = waveforms.transpose((0, 2, 3, 1)).reshape((b * t, f, ch))
+    else:
+        raise TypeError("Input dimension must be 2, 3 or 4, but got {}".format(nd))
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n_mats, f, t = x.shape
+    csize = left_frames + right_frames + 1
+    out = np.empty((n_mats, f * csize, t), dtype=np.float32)
+    if x.size:
+        eng = get_engine()
+        with eng.lock:
+            dx = eng.buf("wave", x.nbytes)
+            do = eng.buf("out", out.nbytes)
+            keep = eng.h2d(dx, x)
+            _context_dev(eng, dx, do, n_mats, f, t, left_frames, right_frames)
+            eng.d2h(out, do)
+            eng.sync()
+            del keep
+    if nd == 2:
+        return out[0]
+    if nd == 4:
+        b, ch, f4, t4 = waveforms.shape
+        out = out.reshape((b, out.shape[1], t4, out.shape[-1])).transpose((0, 3, 1, 2))
+    return out
+
+
+def compute_deltas(specgram, win_length=5, pad_mode="edge"):
+    """``features.py:158-193`` (``msaudio.ComputeDeltas``): ``(..., freq, time)``."""
+    specgram = np.asarray(specgram)
+    pad_mode = BorderType(pad_mode)
+    if win_length < 3:
+        raise ValueError("win_length must be no less than 3, got {}".format(win_length))
+    x = np.ascontiguousarray(specgram, dtype=np.float32)
+    t = x.shape[-1]
+    rows = x.size // t if t else 0
+    out = np.empty_like(x)
+    if x.size:
+        eng = get_engine()
+        with eng.lock:
+            dx = eng.buf("wave", x.nbytes)
+            do = eng.buf("out", out.nbytes)
+            keep = eng.h2d(dx, x)
+            L.check(eng.lib.mafe_compute_deltas(eng.ctx, dx, do, 1, rows, t, 0, 0, win_length, L.PAD[pad_mode.value]))
+            eng.d2h(out, do)
+            eng.sync()
+            del keep
+    return out.astype(np.float64 if specgram.dtype == np.float64 else np.float32, copy=False)
+
+
+def _postprocess(eng, d_feat, n_mats, t, dim, deltas, context, left, right):
+    """Device-side tail shared by fbank/mfcc: frame-major [n_mats*t, dim] -> [n_mats, D', t] with
+    optional delta/delta-delta rows (features.py:264-267) and context window (:268-269)."""
+    rows = dim * (3 if deltas else 1)
+    d_a = eng.buf("post_a", 4 * n_mats * rows * t)
+    L.check(eng.lib.mafe_transpose(eng.ctx, d_feat, d_a, n_mats, t, dim, rows * t))
+    if deltas:
+        edge = L.PAD["edge"]
+        p1 = C.c_void_p(d_a.value + 4 * dim * t)
+        p2 = C.c_void_p(d_a.value + 8 * dim * t)
+        L.check(eng.lib.mafe_compute_deltas(eng.ctx, d_a, p1, n_mats, dim, t, rows * t, rows * t, 5, edge))
+        L.check(eng.lib.mafe_compute_deltas(eng.ctx, p1, p2, n_mats, dim, t, rows * t, rows * t, 5, edge))
+    if context:
+        csize = left + right + 1
+        d_b = eng.buf("post_b", 4 * n_mats * rows * csize * t)
+        _context_dev(eng, d_a, d_b, n_mats, rows, t, left, right)
+        return d_b, rows * csize
+    return d_a, rows
+
+
+def _features(waveforms, plan_kw, n_out, deltas, context, left_frames, right_frames, win_length, hop_length,
+              window, n_fft):
+    waveforms = np.asarray(waveforms)
+    if waveforms.ndim not in (1, 2, 3):
+        raise TypeError("Unsupported MelSpectrogram shape {}".format(waveforms.ndim + 1))
+    win_length = win_length if win_length is not None else n_fft
+    hop_length = hop_length if hop_length is not None else win_length // 2
+    eng = get_engine()
+    plan = _sp._spectrogram_plan(eng, n_fft, win_length, hop_length, window, 2.0, False, True, "reflect", **plan_kw)
+    x, lead = _sp._flatten_batch(waveforms)
+    if x.shape[-1] < n_fft // 2 + 1:
+        raise ValueError("padding of n_fft // 2 = {} needs a longer input than {}".format(n_fft // 2, x.shape[-1]))
+    n_mats = x.shape[0]
+    # amplitude_to_dB clamp group (spectrum.py:81-86): mel is [.., n_mels, T]
+    #   1-D wave -> 2-D mel: the matrix; 2-D wave -> 3-D mel: the WHOLE batch; 3-D wave -> per batch item
+    utt_group = None
+    if plan_kw.get("log_kind") != L.LOG_DB:
+        db_group = L.DBGROUP_NONE
+    elif waveforms.ndim <= 2:
+        db_group = L.DBGROUP_BATCH
+    else:
+        db_group = L.DBGROUP_MAP
+        utt_group = np.repeat(np.arange(lead[0], dtype=np.int32), lead[1])
+    with eng.lock:
+        b = eng.batch(plan, _sp._dense_offsets(n_mats, x.shape[1]), utt_group)
+        try:
+            t = int(b.frame_offsets[1] - b.frame_offsets[0]) if n_mats else 0
+            dw = eng.buf("wave", x.nbytes)
+            do = eng.buf("out", 4 * max(b.total_frames, 1) * n_out)
+            keep = eng.h2d(dw, x)
+            L.check(eng.lib.mafe_frontend_run(eng.ctx, plan.h, b.h, dw, L.WAVE_F32, 1.0, do, db_group))
+            # [batch, channel, time] input: the reference's 4-D context route convolves along the channel
+            # axis (features.py:108-126) -> done by context_window() on the finished array below
+            ctx_dev = context and waveforms.ndim < 3
+            d_res, rows = _postprocess(eng, do, n_mats, t, n_out, deltas, ctx_dev, left_frames, right_frames)
+            out = np.empty(lead + (rows, t), dtype=np.float32)
+            eng.d2h(out, d_res)
+            eng.sync()
+            del keep
+        finally:
+            b.close()
+    if context and not ctx_dev:
+        out = context_window(out, left_frames, right_frames)
+    return out.astype(_sp._out_dtype(waveforms), copy=False)
+
+
+def fbank(
+    waveforms,
+    deltas=False,
+    context=False,
+    n_mels=40,
+    n_fft=400,
+    sample_rate=16000,
+    f_min=0.0,
+    f_max=None,
+    left_frames=5,
+    right_frames=5,
+    win_length=None,
+    hop_length=None,
+    window="hann",
+):
+    """``features.py:196-270``: ``amplitude_to_dB(melspectrogram(x), "power", ref=1.0, top_db=80)``
+    with optional deltas (x3 rows) and context window; ``[..., n_mels', T]``."""
+    bank = _sp._mel_bank(n_fft, n_mels, sample_rate, f_min, f_max, "none", "htk")
+    kw = dict(out_kind=L.OUT_LOGMEL, mel_fb=bank, log_kind=L.LOG_DB, log_arg=1e-10, log_mult=10.0,
+              log_offset=10.0 * np.log10(max(1e-10, 1.0)), top_db=80.0)
+    out = _features(waveforms, kw, n_mels, deltas, context, left_frames, right_frames, win_length, hop_length,
+                    window, n_fft)
+    return out
+
+
+fbanks = fbank  # README.md:41 and the docstring example (features.py:247) call it ``fbanks``
+
+
+def mfcc(
+    waveforms,
+    deltas=True,
+    context=True,
+    n_mels=23,
+    n_mfcc=20,
+    n_fft=400,
+    sample_rate=16000,
+    f_min=0.0,
+    f_max=None,
+    left_frames=5,
+    right_frames=5,
+    win_length=None,
+    hop_length=None,
+    norm="ortho",
+    log_mels=False,
+):
+    """``features.py:273-373``: DCT-II of the (dB or ``ln(mel + 1e-6)``) mel spectrogram;
+    NOTE the reference defaults ``deltas=True, context=True``."""
+    norm = NormMode(norm)
+    if n_mfcc > n_mels:
+        raise ValueError("The number of MFCC coefficients must be no more than # mel bins.")
+    dct = T.dct_matrix(n_mfcc, n_mels, norm)
+    bank = _sp._mel_bank(n_fft, n_mels, sample_rate, f_min, f_max, "none", "htk")
+    if log_mels:
+        kw = dict(out_kind=L.OUT_MFCC, mel_fb=bank, dct=dct, log_kind=L.LOG_LN_PLUS, log_arg=1e-6)
+    else:
+        kw = dict(out_kind=L.OUT_MFCC, mel_fb=bank, dct=dct, log_kind=L.LOG_DB, log_arg=1e-10, log_mult=10.0,
+                  log_offset=0.0, top_db=80.0)
+    out = _features(waveforms, kw, n_mfcc, deltas, context, left_frames, right_frames, win_length, hop_length,
+                    "hann", n_fft)
+    return out

@@ -1,0 +1,116 @@
+"""The conformer / deepspeech2 front-end (examples/conformer/dataset.py:117-168) on B200.
+
+* ``compute_fbank_feats``  -- drop-in for the example's function (numpy in / numpy out).
+* ``FbankPipeline``        -- the ragged, batched hot path: Kaldi-like 80-mel fbank (+ utterance
+  CMVN, + global-CMVN statistics) over a flat waveform array and an offsets array, device-resident
+  (torch tensors / raw device pointers) or host-to-host through pinned buffers.  This is what
+  ``bench.py`` measures.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import _tables as T
+from ._engine import get_engine
+
+
+def conformer_plan(eng, sample_rate=16000, frame_len_ms=25, frame_shift_ms=10, mel_bin=80, n_fft=512, dither=0.0,
+                   seed=0, allow_fast_path=True, low_freq=20.0, high_freq=8000.0):
+    frame_len = sample_rate * frame_len_ms // 1000
+    hop = sample_rate * frame_shift_ms // 1000
+    if frame_len > n_fft:
+        raise ValueError("frame length {} exceeds the {}-point FFT of the example (dataset.py:166)".format(frame_len, n_fft))
+    # dataset.py:152: get_mel_banks(num_filter, 512, fs * 2, 20, 8000) with fs = sample_rate / 2
+    bank = T.kaldi_triangle_bank(mel_bin, n_fft, float(sample_rate), low_freq, high_freq)
+    return eng.plan(n_fft=n_fft, frame_len=frame_len, hop=hop, center=False, out_kind=L.OUT_LOGMEL,
+                    window=T.povey_window(frame_len), preemph=0.97, remove_frame_mean=True, dither=dither,
+                    dither_seed=seed, power=2.0, mel_fb=bank, log_kind=L.LOG_LN_EPS_IF_ZERO,
+                    allow_fast_path=allow_fast_path)
+
+
+def compute_fbank_feats(wav, sample_rate, frame_len, frame_shift, mel_bin, dither=0.0, seed=0, allow_fast_path=True):
+    """``examples/conformer/dataset.py:159-168``: ``wav`` is the int16-scaled waveform
+    (``read() * (1 << 15)``, ``:389-390``); returns float64 ``[T, mel_bin]`` log-mel energies.
+    ``dither`` is an extension (the reference raises NotImplementedError, ``:557-558``)."""
+    wav = np.asarray(wav)
+    eng = get_engine()
+    plan = conformer_plan(eng, sample_rate, frame_len, frame_shift, mel_bin, dither=dither, seed=seed,
+                          allow_fast_path=allow_fast_path)
+    x = np.ascontiguousarray(wav, dtype=np.float32).reshape(-1)
+    out, _ = eng.run_frontend(plan, x, np.array([0, x.shape[0]], dtype=np.int64))
+    return out.astype(np.float64)
+
+
+class FbankPipeline:
+    """Ragged batched fbank (+CMVN) on one GPU.
+
+    ``layout(lengths)`` builds the device tables of a batch (sample/frame offsets, tile table);
+    ``run(...)`` enqueues the kernels on the engine's stream (set it to torch's current stream
+    with ``use_torch_stream()``); outputs are flat, frame-major ``[sum T_u, mel_bin]`` float32.
+    """
+
+    def __init__(self, sample_rate=16000, frame_len_ms=25, frame_shift_ms=10, mel_bin=80, n_fft=512, dither=0.0,
+                 seed=0, cmvn="utt", mean_norm=True, std_norm=True, allow_fast_path=True, engine=None):
+        self.eng = engine or get_engine()
+        self.plan = conformer_plan(self.eng, sample_rate, frame_len_ms, frame_shift_ms, mel_bin, n_fft, dither, seed,
+                                   allow_fast_path)
+        self.mel_bin = mel_bin
+        self.sample_rate = sample_rate
+        assert cmvn in (None, "utt")
+        self.cmvn, self.mean_norm, self.std_norm = cmvn, mean_norm, std_norm
+
+    # ---- layout ----
+    def layout(self, lengths):
+        so = np.zeros(len(lengths) + 1, dtype=np.int64)
+        np.cumsum(np.asarray(lengths, dtype=np.int64), out=so[1:])
+        return self.eng.batch(self.plan, so)
+
+    def use_torch_stream(self):
+        import torch
+        self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # ---- device-resident ----
+    def run(self, wave_ptr, batch, out_ptr, wave_dtype=L.WAVE_F32, wave_scale=1.0, stats_ptr=None):
+        """wave_ptr / out_ptr: device pointers (ints).  stats_ptr: optional device double[2*D+1]
+        receiving the global-CMVN sufficient statistics of the RAW (pre-utterance-CMVN) features."""
+        eng, lib = self.eng, self.eng.lib
+        L.check(lib.mafe_frontend_run(eng.ctx, self.plan.h, batch.h, C.c_void_p(wave_ptr), wave_dtype,
+                                      float(wave_scale), C.c_void_p(out_ptr), L.DBGROUP_NONE))
+        if stats_ptr is not None:
+            L.check(lib.mafe_cmvn_stats_accumulate(eng.ctx, C.c_void_p(out_ptr), batch.total_frames, self.mel_bin,
+                                                   C.c_void_p(stats_ptr)))
+        if self.cmvn == "utt":
+            L.check(lib.mafe_cmvn_utt(eng.ctx, C.c_void_p(out_ptr), batch.frame_offsets_dev, batch.n_utts, self.mel_bin,
+                                      int(self.mean_norm), int(self.std_norm)))
+
+    def __call__(self, wave, lengths=None, batch=None, out=None, wave_scale=1.0):
+        """torch front door: ``wave`` flat CUDA tensor (float32 or int16)."""
+        import torch
+        own = batch is None
+        if own:
+            batch = self.layout(lengths)
+        try:
+            self.use_torch_stream()
+            if out is None:
+                out = torch.empty((batch.total_frames, self.mel_bin), dtype=torch.float32, device=wave.device)
+            dt = L.WAVE_I16 if wave.dtype == torch.int16 else L.WAVE_F32
+            self.run(wave.data_ptr(), batch, out.data_ptr(), dt, wave_scale)
+            if own:
+                torch.cuda.current_stream().synchronize()
+            return out
+        finally:
+            if own:
+                batch.close()
+
+    # ---- host to host (the end-to-end path) ----
+    def run_host(self, wave_host_ptr, wave_nbytes, batch, out_host_ptr, dev_wave_ptr, dev_out_ptr,
+                 wave_dtype=L.WAVE_F32, wave_scale=1.0):
+        """Pinned host waveform -> H2D -> kernels -> D2H of the features, all on the engine stream."""
+        eng, lib = self.eng, self.eng.lib
+        L.check(lib.mafe_memcpy_h2d(eng.ctx, C.c_void_p(dev_wave_ptr), C.c_void_p(wave_host_ptr), wave_nbytes))
+        self.run(dev_wave_ptr, batch, dev_out_ptr, wave_dtype, wave_scale)
+        L.check(lib.mafe_memcpy_d2h(eng.ctx, C.c_void_p(out_host_ptr), C.c_void_p(dev_out_ptr),
+                                    4 * batch.total_frames * self.mel_bin))

@@ -558,12 +558,13 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 def dither_noise(n, seed, utt_id):
     """Standard-normal dither g[0..n): counter = (i, 0, utt_id, 0), key = (seed_lo, seed_hi);
-    Box-Muller on the first two words: u1 = (w0 + 1) * 2^-32 in (0, 1], u2 = w1 * 2^-32,
+    Box-Muller on the top 24 bits of the first two words (exact in float32 and float64):
+    u1 = ((w0 >> 8) + 1) * 2^-24 in (0, 1], u2 = (w1 >> 8) * 2^-24,
     g = sqrt(-2 ln u1) * cos(2 pi u2).  float32 result (float64 math here)."""
     i = np.arange(n, dtype=np.uint64)
     w0, w1, _, _ = philox4x32_10(i.astype(np.uint32), (i >> np.uint64(32)).astype(np.uint32),
                                  np.uint32(utt_id & 0xFFFFFFFF), np.uint32(0),
                                  seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    u1 = (w0.astype(np.float64) + 1.0) * 2.0 ** -32
-    u2 = w1.astype(np.float64) * 2.0 ** -32
+    u1 = ((w0 >> np.uint32(8)).astype(np.float64) + 1.0) * 2.0 ** -24
+    u2 = (w1 >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
     return (np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * math.pi * u2)).astype(np.float32)

@@ -1,0 +1,176 @@
+"""GPU parity: fbank / mfcc / deltas / context / conformer front-end / CMVN vs oracle and goldens."""
+import numpy as np
+import pytest
+
+from oracle import restated as R
+from tests.util import TOL_LOGMEL, mixed_err, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ma():
+    import __graft_entry__ as entry
+    entry.build()
+    import mindaudio_b200
+    return mindaudio_b200
+
+
+def test_fbank_cfg1_and_ecapa(ma, golden):
+    x = golden.wav()
+    out = ma.fbank(x, n_mels=80, n_fft=400, hop_length=160)            # BASELINE.json configs[0]
+    assert out.shape == (80, 600) and out.dtype == np.float64
+    assert mixed_err(golden.take("features_msop/fbank_cfg1", out), golden["features_msop/fbank_cfg1"]) <= TOL_LOGMEL
+    assert mixed_err(out, R.fbank(x, n_mels=80, n_fft=400, hop_length=160)) <= TOL_LOGMEL
+    assert ma.fbanks(x, n_mels=80, n_fft=400, hop_length=160).shape == (80, 600)
+    xe = synth(4, (4, 48000))
+    out = ma.fbank(xe, deltas=False, n_mels=80, left_frames=0, right_frames=0, n_fft=400, hop_length=160)
+    assert out.shape == (4, 80, 301) and out.dtype == np.float32
+    assert mixed_err(golden.take("features_msop/fbank_ecapa_syn4", out), golden["features_msop/fbank_ecapa_syn4"]) <= TOL_LOGMEL
+    # batch coupling of the top_db floor (spectrum.py:81-86): batched != per utterance when levels differ
+    xs = xe * np.array([1.0, 1e-3, 1.0, 1.0], dtype=np.float32)[:, None]
+    assert mixed_err(ma.fbank(xs, n_mels=80), R.fbank(xs, n_mels=80)) <= TOL_LOGMEL
+    x3 = synth(6, (2, 3, 8000)) * np.array([1.0, 1e-3], dtype=np.float32)[:, None, None]
+    assert mixed_err(ma.fbank(x3, n_mels=23), R.fbank(x3, n_mels=23)) <= TOL_LOGMEL       # 4-D mel: per batch item
+
+
+def test_fbank_mfcc_deltas_context(ma, golden):
+    xm = synth(11, (2, 16000))
+    out = ma.fbank(xm, deltas=True, context=True)
+    ref = golden["features_msop/fbank_default_dc_syn11"]
+    assert out.shape == (2, 1320, 81)
+    assert mixed_err(golden.take("features_msop/fbank_default_dc_syn11", out), ref) <= TOL_LOGMEL
+    out = ma.mfcc(xm)
+    assert out.shape == (2, 660, 81)                        # docstring's 101 frames is stale (features.py:326-329)
+    assert mixed_err(golden.take("features_msop/mfcc_default_syn11", out), golden["features_msop/mfcc_default_syn11"]) <= TOL_LOGMEL
+    x = golden.wav()
+    out = ma.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160)      # configs[3]
+    assert out.shape == (40, 600)
+    assert mixed_err(golden.take("features_msop/mfcc_cfg4", out), golden["features_msop/mfcc_cfg4"]) <= TOL_LOGMEL
+    out = ma.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160, log_mels=True)
+    assert mixed_err(golden.take("features_msop/mfcc_cfg4_logmels", out), golden["features_msop/mfcc_cfg4_logmels"]) <= TOL_LOGMEL
+    out = ma.mfcc(xm, norm="none", left_frames=2, right_frames=4)
+    assert mixed_err(out, R.mfcc(xm, norm="none", left_frames=2, right_frames=4)) <= TOL_LOGMEL
+    x3 = synth(6, (2, 3, 8000))
+    assert mixed_err(ma.mfcc(x3), R.mfcc(x3)) <= TOL_LOGMEL                                # 4-D context route
+
+
+def test_deltas_and_context_standalone(ma, golden):
+    fb = R.fbank(golden.wav(), n_mels=80, n_fft=400, hop_length=160)
+    d = ma.compute_deltas(fb[:, :100], win_length=7, pad_mode="reflect")
+    assert mixed_err(golden.take("features_msop/deltas_syn", d), golden["features_msop/deltas_syn"]) <= 1e-5
+    for mode in ("edge", "constant", "symmetric"):
+        z = np.random.default_rng(3).standard_normal((2, 13, 40)).astype(np.float32)
+        assert mixed_err(ma.compute_deltas(z, 5, mode), R.compute_deltas(z, 5, mode)) <= 1e-5
+    c = ma.context_window(fb[:10, :60].astype(np.float32), 3, 5)
+    assert np.array_equal(c, golden["features_msop/context_3_5"])
+    z = np.random.default_rng(1).standard_normal((3, 7, 50)).astype(np.float32)
+    for l, r in ((3, 5), (4, 4), (5, 3), (0, 0), (5, 5), (0, 3), (2, 0)):
+        assert np.array_equal(ma.context_window(z, l, r), R.context_window(z, l, r))
+    z4 = np.random.default_rng(1).standard_normal((2, 3, 7, 20)).astype(np.float32)
+    assert np.array_equal(ma.context_window(z4, 2, 3), R.context_window(z4, 2, 3))
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_conformer_fbank_golden(ma, golden, fast):
+    x = golden.wav() * (1 << 15)
+    out = ma.compute_fbank_feats(x, 16000, 25, 10, 80, allow_fast_path=fast)
+    assert out.shape == (598, 80) and out.dtype == np.float64
+    assert mixed_err(out, golden["conformer_cmvn/conformer_fbank"]) <= TOL_LOGMEL
+    for i, n in enumerate((16000, 23456, 400, 559, 560)):
+        w = np.round(synth(3, (n,)) * 32768).astype(np.float64)
+        got = ma.compute_fbank_feats(w, 16000, 25, 10, 80, allow_fast_path=fast)
+        ref = golden["conformer_cmvn/conformer_syn3_%d" % i]
+        assert got.shape == ref.shape and mixed_err(got, ref) <= TOL_LOGMEL
+    assert ma.compute_fbank_feats(np.ones(399), 16000, 25, 10, 80, allow_fast_path=fast).shape == (0, 80)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_conformer_ragged_batch(ma, fast):
+    from mindaudio_b200._engine import get_engine
+    rng = np.random.default_rng(3)
+    lens = [int(v) for v in rng.integers(16000, 320001, size=6)] + [400, 399, 0, 561, 100000]
+    waves = [np.round(synth(100 + i, (n,)) * 32768).astype(np.float32) for i, n in enumerate(lens)]
+    pipe = ma.FbankPipeline(cmvn=None, allow_fast_path=fast)
+    assert pipe.plan.is_fast == fast or not fast
+    so = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    out, fo = get_engine().run_frontend(pipe.plan, np.concatenate(waves), so)
+    for u, w in enumerate(waves):
+        ref = R.conformer_fbank(w.astype(np.float64)) if len(w) else np.zeros((0, 80))
+        got = out[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        assert mixed_err(got, ref) <= TOL_LOGMEL, u
+    # int16 staging gives the same features as float32 staging of the same integers
+    i16 = np.concatenate(waves).astype(np.int16)
+    out16, _ = get_engine().run_frontend(pipe.plan, i16, so)
+    assert np.array_equal(out16, out)
+
+
+def test_conformer_dither(ma):
+    from mindaudio_b200._engine import get_engine
+    w = np.round(synth(8, (16000,)) * 32768).astype(np.float32)
+    for fast in (False, True):
+        a = ma.compute_fbank_feats(w, 16000, 25, 10, 80, dither=1.0, seed=1234, allow_fast_path=fast)
+        b = ma.compute_fbank_feats(w, 16000, 25, 10, 80, dither=1.0, seed=1234, allow_fast_path=fast)
+        c = ma.compute_fbank_feats(w, 16000, 25, 10, 80, dither=1.0, seed=99, allow_fast_path=fast)
+        assert np.array_equal(a, b) and not np.array_equal(a, c)         # deterministic, seeded
+        ref = R.conformer_fbank(w.astype(np.float64), dither=1.0, seed=1234, utt_id=0)
+        assert mixed_err(a, ref) <= TOL_LOGMEL
+        off = ma.compute_fbank_feats(w, 16000, 25, 10, 80, dither=0.0, allow_fast_path=fast)
+        assert mixed_err(off, R.conformer_fbank(w.astype(np.float64))) <= TOL_LOGMEL
+
+
+def test_cmvn_family(ma, golden):
+    g = lambda n: golden["conformer_cmvn/" + n]
+    feats = [g("conformer_fbank")] + [g("conformer_syn3_%d" % i) for i in range(5)]
+    stats = ma.compute_cmvn_stats(feats)
+    assert stats.frame_num == int(g("cmvn_frame_num"))
+    assert np.max(np.abs(stats.mean_stat - g("cmvn_mean_stat")) / np.abs(g("cmvn_mean_stat"))) <= 1e-6
+    assert np.max(np.abs(stats.var_stat - g("cmvn_var_stat")) / np.abs(g("cmvn_var_stat"))) <= 1e-6
+    mean, istd = stats.mean_istd()
+    assert np.max(np.abs(mean - g("cmvn_mean"))) <= 1e-5 and np.max(np.abs(istd / g("cmvn_istd") - 1)) <= 1e-5
+    out = ma.GlobalCMVN(g("cmvn_mean"), g("cmvn_istd"))(feats[0])
+    assert out.dtype == np.float32 and mixed_err(out, g("global_cmvn_applied")) <= 1e-5
+    out = ma.GlobalCMVN(g("cmvn_mean"), g("cmvn_istd"), norm_var=False)(feats[0][None])
+    assert mixed_err(out[0], feats[0].astype(np.float32) - g("cmvn_mean").astype(np.float32)) <= 1e-5
+    batch = np.stack([feats[0][:300], feats[0][298:598]])
+    out = ma.InputNormalization(mean_norm=True, std_norm=False, norm_type="sentence").construct(batch.copy())
+    assert mixed_err(out, g("utt_cmvn_mean_only")) <= 1e-5
+    out = ma.InputNormalization(mean_norm=True, std_norm=True, norm_type="sentence")(batch.copy())
+    assert mixed_err(out, g("utt_cmvn_mean_std")) <= 1e-5
+    # ragged utterance CMVN with an offsets array (no padding)
+    flat = np.concatenate(feats[:3])
+    fo = np.concatenate([[0], np.cumsum([f.shape[0] for f in feats[:3]])])
+    out = ma.utterance_cmvn(flat, fo)
+    ref = np.concatenate([R.utt_cmvn(f) for f in feats[:3]])
+    assert mixed_err(out, ref) <= 1e-5
+    # DeepSpeech2 chain: stft 320/160 -> magphase -> log1p -> scalar norm (deepspeech2/dataset.py:36-47)
+    spec = ma.stft(golden.wav(), n_fft=320, hop_length=160, win_length=320)
+    mag, _ = ma.magphase(spec, power=1.0, iscomplex=True)
+    out = ma.scalar_norm(mag)
+    assert mixed_err(golden.take("spectrum/ds2_norm", out), golden["spectrum/ds2_norm"]) <= 1e-4
+    import json, os, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "global_cmvn")
+        ma.save_cmvn_json(stats, p)
+        assert set(json.load(open(p))) == {"mean_stat", "var_stat", "frame_num"}     # compute_cmvn_stats.py:121-128
+        m2, i2 = ma.load_cmvn(p, True)
+        assert np.allclose(m2, mean) and np.allclose(i2, istd)
+
+
+def test_pipeline_with_utt_cmvn_matches_reference_chain(ma):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(5)
+    lens = [int(v) for v in rng.integers(16000, 80000, size=5)]
+    waves = [np.round(synth(200 + i, (n,)) * 32768).astype(np.float32) for i, n in enumerate(lens)]
+    pipe = ma.FbankPipeline(cmvn="utt", mean_norm=True, std_norm=True)
+    wave = torch.from_numpy(np.concatenate(waves)).cuda()
+    batch = pipe.layout(lens)
+    out = pipe(wave, batch=batch)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    fo = batch.frame_offsets
+    for u, w in enumerate(waves):
+        ref = R.utt_cmvn(R.conformer_fbank(w.astype(np.float64)))
+        assert mixed_err(out[fo[u]:fo[u + 1]], ref) <= 2e-4
+    batch.close()

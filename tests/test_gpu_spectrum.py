@@ -1,0 +1,168 @@
+"""GPU parity: mindaudio_b200.data.spectrum (CUDA, through the C ABI) vs the oracle and the goldens."""
+import numpy as np
+import pytest
+
+from oracle import restated as R
+from tests.util import TOL_STFT, mixed_err, stft_err, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ma():
+    import __graft_entry__ as entry
+    entry.build()
+    import mindaudio_b200
+    return mindaudio_b200
+
+
+STFT_CASES = {
+    "stft_default": dict(),
+    "stft_512_256": dict(n_fft=512, hop_length=256),
+    "stft_ds2": dict(n_fft=320, hop_length=160, win_length=320),
+    "stft_400_reflect": dict(n_fft=400, hop_length=160, pad_mode="reflect"),
+    "stft_win400_hamming": dict(n_fft=512, win_length=400, hop_length=160, window="hamming"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STFT_CASES))
+def test_stft_golden(ma, golden, name):
+    x = golden.wav()
+    out = ma.stft(x, **STFT_CASES[name])
+    assert out.dtype == np.complex64
+    ref = golden["spectrum/" + name]
+    assert stft_err(golden.take("spectrum/" + name, out), ref) <= TOL_STFT
+    assert stft_err(out, R.stft(x, **STFT_CASES[name])) <= TOL_STFT
+
+
+def test_stft_shapes_and_layout(ma, golden):
+    x = golden.wav()
+    s = ma.stft(x, n_fft=512)
+    assert s.shape == (257, 750)                 # notebook cell 27 / README.md:83
+    assert s.flags["F_CONTIGUOUS"]               # spectrum.py:249-252: order="F"
+    m, p = ma.magphase(s, 1)
+    assert m.shape == (257, 750) and p.shape == (257, 750)
+    ri = ma.stft(x[:20000], center=False, return_complex=False)
+    assert ri.shape == (257, 153, 2) and ri.dtype == np.float32
+    assert stft_err(golden.take("spectrum/stft_nocenter_ri", ri), golden["spectrum/stft_nocenter_ri"]) <= TOL_STFT
+
+
+@pytest.mark.parametrize("n_fft,hop,win,window,mode", [
+    (512, 256, None, "hann", "constant"), (400, 160, None, "hann", "reflect"), (320, 160, 320, "hann", "constant"),
+    (512, 128, 400, "hamming", "edge"), (1024, 300, 800, "blackman", "symmetric"), (2048, 512, 1200, "hann", "reflect"),
+    (240, 80, None, "hann", "constant"), (600, 150, None, "bartlett", "constant"),     # 2^4*3*5, 2^3*3*5^2
+    (98, 49, None, "hann", "constant"), (202, 50, None, "hann", "reflect"),             # 2*7^2 and 2*101: prime radix
+    (512, 400, None, "hann", "constant"), (512, 500, None, "hann", "constant"),         # hop > n_fft/2 (reference bug)
+    (512, 256, None, "hann", "wrap"),                                                    # host-pad fallback
+])
+def test_stft_batch_vs_oracle(ma, n_fft, hop, win, window, mode):
+    x = synth(2, (3, 16000))
+    kw = dict(n_fft=n_fft, hop_length=hop, win_length=win, window=window, pad_mode=mode)
+    out = ma.stft(x, **kw)
+    ref = R.stft(x, **kw)
+    assert out.shape == ref.shape
+    for b in range(x.shape[0]):
+        assert stft_err(out[b], ref[b]) <= TOL_STFT
+
+
+def test_stft_float64_int_and_edge_lengths(ma):
+    rng = np.random.default_rng(1)
+    for length in (512, 513, 767, 768, 1024, 16001):
+        x = rng.standard_normal(length)
+        assert stft_err(ma.stft(x, n_fft=512, hop_length=256), R.stft(x, n_fft=512, hop_length=256)) <= TOL_STFT
+        assert stft_err(ma.stft(x, n_fft=512, hop_length=256, center=False),
+                        R.stft(x, n_fft=512, hop_length=256, center=False)) <= TOL_STFT
+    xi = (rng.standard_normal(4000) * 1000).astype(np.int16)
+    assert stft_err(ma.stft(xi), R.stft(xi)) <= TOL_STFT
+    assert ma.stft(np.zeros((0, 2048), dtype=np.float32)).shape == (0, 257, 17)
+
+
+def test_istft_roundtrip_reference_assertion(ma, golden):
+    x = golden.wav()
+    res = ma.istft(ma.stft(x))
+    assert res.shape == (95872,) and res.dtype == np.float64
+    assert np.allclose(x[: res.shape[0]], res, atol=2e-8)       # tests/test_spectrum.py:38-41 (FP32 pipeline)
+    assert np.max(np.abs(x[: res.shape[0]] - res)) <= 1e-6 * np.max(np.abs(x))
+
+
+def test_istft_vs_oracle(ma, golden):
+    x = golden.wav()
+    s = R.stft(x)
+    for kw in (dict(), dict(length=90000), dict(length=99000)):
+        ref = R.istft(s, **kw)
+        got = ma.istft(s, **kw)
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 2e-6 * np.max(np.abs(ref))
+    assert np.max(np.abs(golden.take("spectrum/istft_default", ma.istft(s)) - golden["spectrum/istft_default"])) <= 2e-6 * 0.05
+    s2 = R.stft(x, n_fft=320, hop_length=160, win_length=320)
+    ref = R.istft(s2, hop_length=160)
+    assert np.max(np.abs(ma.istft(s2, hop_length=160) - ref)) <= 2e-6 * np.max(np.abs(ref))
+    xb = synth(5, (3, 8000))
+    sb = R.stft(xb, n_fft=400, hop_length=100, center=False)
+    ref = R.istft(sb, hop_length=100, center=False)
+    assert np.max(np.abs(ma.istft(sb, hop_length=100, center=False) - ref)) <= 2e-6 * np.max(np.abs(ref))
+
+
+def test_magphase(ma, golden):
+    s = R.stft(golden.wav(), n_fft=320, hop_length=160, win_length=320)
+    for power in (1.0, 2.0, 0.5):
+        m, p = ma.magphase(s, power)
+        rm, rp = R.magphase(s, power)
+        assert m.dtype == np.float32 and p.dtype == np.complex64
+        assert np.max(np.abs(m - rm)) <= 1e-5 * np.max(np.abs(rm))
+        assert np.max(np.abs(p - rp)) <= 1e-5
+    km, kp = ma.magphase(golden["spectrum/magphase_kat_in"], 2.0)
+    assert np.allclose(km, golden["spectrum/magphase_kat_mag"]) and np.allclose(kp, golden["spectrum/magphase_kat_phase"])
+    assert km[0, 0] == 25 and kp[0, 1] == 1 + 0j                  # zeros -> phase 1+0j
+    m3, p3 = ma.magphase(np.stack([s, s]), 1.0)                  # N-D superset
+    assert m3.shape == (2,) + s.shape
+    mr, ang = ma.magphase(R.stft(golden.wav()[:8000], return_complex=False), 1.0, iscomplex=False)
+    rm, ra = R.magphase_real(R.stft(golden.wav()[:8000], return_complex=False), 1.0)
+    assert np.max(np.abs(mr - rm)) <= 1e-5 * np.max(rm)
+    big = rm > 1e-3 * rm.max()
+    assert np.max(np.abs(ang - ra)[big]) <= 1e-4
+
+
+@pytest.mark.parametrize("nd", ["2d", "3d", "4d"])
+def test_amplitude_to_db(ma, golden, nd):
+    a = golden["spectrum/db_in_" + nd]
+    out = ma.amplitude_to_dB(a)
+    assert out.dtype == np.float64 and out.shape == a.shape
+    assert mixed_err(out, golden["spectrum/db_power_" + nd]) <= 1e-4
+    assert mixed_err(ma.amplitude_to_dB(a, stype="magnitude", ref=2.0, top_db=60.0), golden["spectrum/db_mag_" + nd]) <= 1e-4
+    assert mixed_err(ma.amplitude_to_dB(a.astype(np.float32), ref=np.max), R.amplitude_to_dB(a, ref=np.max)) <= 1e-4
+
+
+def test_db_misc(ma, golden):
+    a = golden["spectrum/db_in_2d"]
+    assert mixed_err(ma.amplitude_to_dB(a, top_db=None), golden["spectrum/db_notop_2d"]) <= 1e-4
+    d = golden["spectrum/db_power_2d"]
+    ref = golden["spectrum/db2amp"]
+    assert np.max(np.abs(ma.dB_to_amplitude(d, 0.5, 0.5) - ref) / np.maximum(np.abs(ref), 1e-30)) <= 1e-4
+    b = golden["spectrum/db_in_3d"]
+    batched = ma.amplitude_to_dB(b)
+    assert not np.allclose(batched, np.stack([ma.amplitude_to_dB(m) for m in b]))    # batch coupling replicated
+    assert ma.amplitude_to_dB(np.zeros((0, 4, 5))).shape == (0, 4, 5)
+
+
+def test_spectrogram_melspectrogram_melscale(ma, golden):
+    x = golden.wav()
+    g = lambda n: golden["features_msop/" + n]
+    t = lambda n, full: golden.take("features_msop/" + n, full)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    s = ma.spectrogram(x)
+    assert s.shape == (201, 480) and s.dtype == np.float64
+    assert rel(t("spectrogram_default", s), g("spectrogram_default")) <= 1e-5
+    s = ma.spectrogram(x.astype(np.float32), n_fft=512, hop_length=128, power=1.0, normalized=True, window="hamming")
+    assert s.dtype == np.float32 and rel(t("spectrogram_512_mag", s), g("spectrogram_512_mag")) <= 1e-5
+    m = ma.melspectrogram(x)
+    assert m.shape == (128, 480) and rel(t("melspectrogram_default", m), g("melspectrogram_default")) <= 1e-5
+    m = ma.melspectrogram(x, n_fft=512, n_mels=40, norm="slaney", mel_type="slaney", f_min=50.0, f_max=7600.0)
+    assert rel(t("melspectrogram_slaney", m), g("melspectrogram_slaney")) <= 1e-5
+    sp = R.spectrogram(x, n_fft=1024)
+    ms = ma.melscale(sp, n_stft=513)
+    assert rel(t("melscale_1024", ms), g("melscale_1024")) <= 1e-5
+    full = ma.spectrogram(x[:8000], onesided=False)
+    assert full.shape[0] == 400 and rel(full, R.spectrogram(x[:8000], onesided=False)) <= 1e-5
+    xb = synth(9, (2, 3, 4000))
+    assert rel(ma.spectrogram(xb, pad=7, power=0.5), R.spectrogram(xb, pad=7, power=0.5)) <= 1e-5
