@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- fbank audio-hours/sec (16 kHz, 80-mel) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2] -- the conformer/deepspeech2 front-end:
+Kaldi-like 80-mel fbank (25 ms / 10 ms, 512-point FFT; examples/conformer/dataset.py:117-168) +
+per-utterance CMVN on a RAGGED batch of synthetic 16 kHz utterances, 1-20 s uniform (seed 3),
+offsets array, no padding.  One step = one pass of the hot path over one chunk of
+``--utts`` utterances per GPU (8192: SURVEY.md section 8d processes the 100k utterances in chunks
+of <= 8192).  Weak scaling: every rank owns its own chunk; no data-path collective.
+
+value   = audio-hours processed by all ranks / device time (inputs resident in HBM), CUDA events,
+          max over ranks.  Inputs (5.5 GB/chunk) are far larger than L2, so no flush is needed.
+e2e     = the same through the host-facing call: pinned host waveform -> H2D -> kernels -> D2H of
+          the features, copies inside the timed region.
+roofline= dominant kernel (fbank512_kernel) timed with CUDA events on its own stream inside this
+          run, algorithmic bytes (960 B/frame) and flops (14 253/frame) from SURVEY.md section 8d.
+cpu_baseline / --impl reference = the reference's algorithm (oracle port, it is pure python and
+          cannot travel to the GPU box) on this host's cores, bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+SR = 16000
+FRAME_LEN, HOP, N_MELS = 400, 160, 80
+BYTES_PER_FRAME = 960.0      # 160 samples * 4 B in + 80 * 4 B out
+FLOP_PER_FRAME = 14253.0     # SURVEY.md 8d (incl. utterance CMVN)
+FP32_PEAK_NOMINAL_TFLOPS = 74.5   # 148 SM * 128 lanes * 2 * 1.965 GHz (not in MEASURED_PEAKS.json)
+METRIC = "fbank audio-hours/sec (16kHz, 80-mel)"
+UNIT = "audio-hours/s"
+
+
+def chunk_lengths(seed, n_utts):
+    """cfg3 length distribution: uniform 1-20 s."""
+    return np.random.default_rng(seed).integers(16000, 320001, size=n_utts).astype(np.int64)
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (via NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as exc:  # NVML missing: report nothing rather than fail the bench
+            self.reasons.add("nvml_unavailable:%s" % type(exc).__name__)
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(n_utts, seed=3):
+    from oracle import cpu_baseline as cb         # the labelled CPU arm: the ONLY use of oracle/ here
+    lens = chunk_lengths(seed, n_utts)
+    r = cb.run_pool(lens, seed=seed)
+    hours = r["audio_s"] / 3600.0
+    return {"value": hours / r["wall_s"], "unit": UNIT, "cores": r["procs"], "kind": "port",
+            "sample": "%d utterances (%.1f audio-min) of the cfg3 workload, fbank + utterance CMVN, reference-structured "
+                      "numpy port (oracle/cpu_baseline.py), multiprocessing.Pool(%d); %.1f s wall, %.1f s CPU"
+                      % (n_utts, r["audio_s"] / 60.0, r["procs"], r["wall_s"], r["cpu_s"]),
+            "wall_s": r["wall_s"], "audio_hours": hours}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this host's cores."""
+    if rank != 0:
+        return
+    n = args.cpu_utts
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(max(n // 4, os.cpu_count() or 1))
+    t_total = 0.0
+    for _ in range(args.steps):
+        r = cpu_baseline(n)
+        vals.append(r)
+        t_total += r["wall_s"]
+    hours = sum(v["audio_hours"] for v in vals)
+    value = hours / t_total
+    last = vals[-1]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": workload_config(n, 1, "host cores"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_utts, world, where):
+    return {"workload": "cfg3: conformer front-end = Kaldi-like 80-mel fbank (25ms/10ms, FFT 512) + utterance CMVN, "
+                        "ragged batch of synthetic 16 kHz utterances 1-20 s (seed 3), offsets array",
+            "utts_per_step_per_gpu": int(n_utts), "ranks": world, "where": where,
+            "l2_policy": "inputs (~5.5 GB per step) exceed L2 (126 MB); no flush needed",
+            "sharding": "by utterance, no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=8192, help="utterances per step per GPU")
+    ap.add_argument("--cpu-utts", type=int, default=768, help="utterances in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # CPU baseline first: it forks worker processes, which must happen before CUDA is initialised
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_utts)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["MAFE_DEVICE"] = str(local)
+
+    import mindaudio_b200 as ma
+    from mindaudio_b200 import _lib as L
+    from mindaudio_b200._engine import get_engine
+    eng = get_engine()
+    pipe = ma.FbankPipeline(cmvn="utt", mean_norm=True, std_norm=True)
+    if not pipe.plan.is_fast:
+        raise RuntimeError("the specialised sm_100a kernel is not serving the headline plan")
+    pipe.use_torch_stream()
+
+    # ---- synthetic chunk of this rank (seeded), resident in HBM ----
+    lens = chunk_lengths(3 + 7919 * rank, args.utts)
+    total = int(lens.sum())
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3 + 7919 * rank)
+    wave = torch.empty(total, dtype=torch.float32, device=dev)
+    step_elems = 1 << 26
+    for s in range(0, total, step_elems):   # x = round(clip(0.05 N(0,1), -1, 1) * 32768): int16-scaled PCM (dataset.py:389-390)
+        e = min(total, s + step_elems)
+        wave[s:e] = torch.round(torch.clamp(0.05 * torch.randn(e - s, generator=gen, device=dev), -1.0, 1.0) * 32768.0)
+    batch = pipe.layout(lens)
+    n_frames = batch.total_frames
+    out = torch.empty((n_frames, N_MELS), dtype=torch.float32, device=dev)
+    audio_hours = total / SR / 3600.0
+
+    def step():
+        pipe.run(wave.data_ptr(), batch, out.data_ptr(), L.WAVE_F32, 1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        hrs = torch.tensor([audio_hours], dtype=torch.float64, device=dev)
+        dist.all_reduce(hrs, op=dist.ReduceOp.SUM)
+        total_hours = float(hrs.item())
+    else:
+        total_hours = audio_hours
+    value = total_hours * args.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch, same steps ----
+    eng.profile(True)
+    eng.profile_reset()
+    for _ in range(args.steps):
+        step()
+    k_ms, k_n = eng.profile_read(L.PROF_FBANK_MAIN)
+    p_ms, p_n = eng.profile_read(L.PROF_FRAME_MEAN)
+    c_ms, c_n = eng.profile_read(L.PROF_CMVN)
+    eng.profile(False)
+    k_avg_s = k_ms / max(k_n, 1) / 1e3
+    hbm_peak, peak_src = measured_peaks()
+    achieved_gbs = BYTES_PER_FRAME * n_frames / k_avg_s / 1e9
+    achieved_tflops = FLOP_PER_FRAME * n_frames / k_avg_s / 1e12
+    # roofline = the slower of bytes at the measured HBM bandwidth and flops at the FP32 peak
+    t_hbm = BYTES_PER_FRAME * n_frames / (hbm_peak * 1e9)
+    t_fp32 = FLOP_PER_FRAME * n_frames / (FP32_PEAK_NOMINAL_TFLOPS * 1e12)
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "fbank512_kernel",
+                "kernel_ms": k_avg_s * 1e3, "frames_per_launch": int(n_frames),
+                "fp32": {"achieved_tflops": achieved_tflops, "nominal_peak_tflops": FP32_PEAK_NOMINAL_TFLOPS,
+                         "frac_of_nominal": achieved_tflops / FP32_PEAK_NOMINAL_TFLOPS,
+                         "note": "FP32 FMA peak is nominal (148 SM x 128 lanes x 2 x 1.965 GHz), not in MEASURED_PEAKS.json"},
+                "frac_of_min_roofline": max(t_hbm, t_fp32) / k_avg_s,
+                "step_share": {"fbank512_kernel_ms": k_ms / max(k_n, 1), "frame_mean_prepass_ms": p_ms / max(p_n, 1),
+                               "cmvn_ms": c_ms / max(c_n, 1), "step_ms": ms / args.steps}}
+
+    # ---- end to end through the host-facing call: pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h_wave = torch.empty(total, dtype=torch.float32, pin_memory=True)
+        h_wave.copy_(wave)
+        h_out = torch.empty((n_frames, N_MELS), dtype=torch.float32, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            b = pipe.layout(lens)          # offsets -> device tables are part of the call
+            pipe.run_host(h_wave.data_ptr(), total * 4, b, h_out.data_ptr(), wave.data_ptr(), out.data_ptr(), L.WAVE_F32, 1.0)
+            return b
+
+        keep = [e2e_step()]
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        ev0.record()
+        for _ in range(n_e2e):
+            keep.append(e2e_step())
+        ev1.record()
+        barrier()
+        e_ms = ev0.elapsed_time(ev1)
+        for b in keep:
+            b.close()
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": total_hours * n_e2e / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(total * 4 + 16 * len(lens)),
+               "d2h_bytes_per_step": int(n_frames * N_MELS * 4), "steps": n_e2e, "ms_per_step": e_ms / n_e2e,
+               "host_dtype": "f32 pinned"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args.utts, world, "B200"),
+                "audio_hours_per_step": total_hours, "frames_per_step_rank0": int(n_frames),
+                "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,18 @@ int mafe_ctx_sm_count(const mafe_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t mafe_ctx_launch_count(const mafe_ctx* ctx);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, every launch of the hot-path kernels is
+ * bracketed by CUDA events on the ctx stream.  mafe_ctx_profile_read() synchronises, then returns the summed
+ * milliseconds and the launch count of kernel class `which` (MAFE_PROF_*) since the last reset. */
+#define MAFE_PROF_FBANK_MAIN 0   /* fbank512_kernel / generic_frontend_kernel */
+#define MAFE_PROF_FRAME_MEAN 1   /* utterance frame-mean pre-pass            */
+#define MAFE_PROF_CMVN 2         /* CMVN kernels                             */
+#define MAFE_PROF_OTHER 3
+#define MAFE_PROF_COUNT 4
+int mafe_ctx_profile_enable(mafe_ctx* ctx, int32_t enable);
+int mafe_ctx_profile_read(mafe_ctx* ctx, int32_t which, double* ms_out, int64_t* launches_out);
+int mafe_ctx_profile_reset(mafe_ctx* ctx);
+
 /* ---- memory plumbing for numpy callers (no torch needed) ---- */
 int mafe_device_malloc(mafe_ctx* ctx, size_t bytes, void** out_dev);
 int mafe_device_free(mafe_ctx* ctx, void* dev);
@@ -188,11 +200,11 @@ int mafe_transpose(mafe_ctx* ctx, const float* in_dev, float* out_dev, int32_t n
                    int64_t out_mat_stride);
 
 /* ---- istft (spectrum.py:346-474) ---- */
-/* spec_dev: [n_utts][n_frames][n_fft/2+1] complex64 frame-major; window: HOST [n_fft] (padded);
- * y_dev: [n_utts][n_fft + hop*(n_frames-1)] floats = overlap-added, window-sum-square normalised signal
- * (the caller trims n_fft/2 / length as the reference does). */
+/* spec_dev: [n_utts][n_frames][n_fft/2+1] complex64 frame-major; window: HOST double[n_fft] (padded);
+ * y_dev: double [n_utts][n_fft + hop*(n_frames-1)] = overlap-added, window-sum-square normalised signal
+ * (the caller trims n_fft/2 / length as the reference does).  float64 arithmetic, like the reference. */
 int mafe_istft(mafe_ctx* ctx, const float* spec_dev, int32_t n_utts, int32_t n_frames, int32_t n_fft, int32_t hop,
-               const float* window_host, float* y_dev);
+               const double* window_host, double* y_dev);
 
 /* ---- CMVN family ---- */
 /* Per-utterance, per-dim mean (and population-std) normalisation in place

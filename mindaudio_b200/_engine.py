@@ -61,6 +61,18 @@ class Engine:
     def sm_count(self):
         return int(self.lib.mafe_ctx_sm_count(self.ctx))
 
+    def profile(self, enable):
+        L.check(self.lib.mafe_ctx_profile_enable(self.ctx, int(bool(enable))))
+
+    def profile_reset(self):
+        L.check(self.lib.mafe_ctx_profile_reset(self.ctx))
+
+    def profile_read(self, which):
+        """(summed device milliseconds, launches) of kernel class ``which`` (L.PROF_*)."""
+        ms, n = C.c_double(), C.c_int64()
+        L.check(self.lib.mafe_ctx_profile_read(self.ctx, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def buf(self, name, nbytes):
         """Grow-only named device buffer (numpy API calls are synchronous, so reuse is safe)."""
         cur = self._bufs.get(name)

@@ -20,6 +20,7 @@ OUT_COMPLEX, OUT_POWER, OUT_MEL, OUT_LOGMEL, OUT_MFCC = range(5)
 LOG_NONE, LOG_LN_EPS_IF_ZERO, LOG_LN_PLUS, LOG_DB = range(4)
 WAVE_F32, WAVE_I16 = 0, 1
 DBGROUP_NONE, DBGROUP_UTT, DBGROUP_BATCH, DBGROUP_MAP = range(4)
+PROF_FBANK_MAIN, PROF_FRAME_MEAN, PROF_CMVN, PROF_OTHER = range(4)
 
 
 class MafeError(RuntimeError):
@@ -51,6 +52,9 @@ _PROTOS = {
     "mafe_ctx_sync": (C.c_int, [_P]),
     "mafe_ctx_sm_count": (C.c_int, [_P]),
     "mafe_ctx_launch_count": (_I64, [_P]),
+    "mafe_ctx_profile_enable": (C.c_int, [_P, _I32]),
+    "mafe_ctx_profile_read": (C.c_int, [_P, _I32, C.POINTER(C.c_double), C.POINTER(_I64)]),
+    "mafe_ctx_profile_reset": (C.c_int, [_P]),
     "mafe_device_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "mafe_device_free": (C.c_int, [_P, _P]),
     "mafe_pinned_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),

@@ -91,6 +91,45 @@ int mafe_ctx_sync(mafe_ctx* ctx) {
 int mafe_ctx_sm_count(const mafe_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 int64_t mafe_ctx_launch_count(const mafe_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mafe_ctx_profile_enable(mafe_ctx* ctx, int32_t enable) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  ctx->profile = enable != 0;
+  return MAFE_OK;
+}
+
+static int prof_drain(mafe_ctx* ctx) {
+  DeviceGuard g(ctx->device);
+  MAFE_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      ctx->prof_ms[p.which] += ms;
+      ctx->prof_n[p.which] += 1;
+    }
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+  }
+  ctx->prof_pending.clear();
+  return MAFE_OK;
+}
+
+int mafe_ctx_profile_read(mafe_ctx* ctx, int32_t which, double* ms_out, int64_t* launches_out) {
+  MAFE_REQUIRE(ctx && which >= 0 && which < MAFE_PROF_COUNT, "mafe_ctx_profile_read: bad argument");
+  int rc = prof_drain(ctx);
+  if (rc) return rc;
+  if (ms_out) *ms_out = ctx->prof_ms[which];
+  if (launches_out) *launches_out = ctx->prof_n[which];
+  return MAFE_OK;
+}
+
+int mafe_ctx_profile_reset(mafe_ctx* ctx) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  int rc = prof_drain(ctx);
+  if (rc) return rc;
+  for (int i = 0; i < MAFE_PROF_COUNT; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+  return MAFE_OK;
+}
+
 // ---------------------------------------------------------------- memory
 int mafe_device_malloc(mafe_ctx* ctx, size_t bytes, void** out_dev) {
   MAFE_REQUIRE(ctx && out_dev, "mafe_device_malloc: NULL argument");

@@ -51,13 +51,43 @@ struct MelCSR {         // by filter (generic kernel)
 
 }  // namespace mafe
 
+struct mafe_prof_pending {
+  int which;
+  cudaEvent_t e0, e1;
+};
+
 struct mafe_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  bool profile = false;
+  double prof_ms[MAFE_PROF_COUNT] = {0, 0, 0, 0};
+  int64_t prof_n[MAFE_PROF_COUNT] = {0, 0, 0, 0};
+  std::vector<mafe_prof_pending> prof_pending;
 };
+
+namespace mafe {
+// RAII bracket: records events around the launches issued while it is alive (only when profiling)
+struct ProfScope {
+  mafe_ctx* ctx;
+  mafe_prof_pending p;
+  bool on;
+  ProfScope(mafe_ctx* c, int which) : ctx(c), on(c->profile) {
+    if (!on) return;
+    p.which = which;
+    cudaEventCreate(&p.e0);
+    cudaEventCreate(&p.e1);
+    cudaEventRecord(p.e0, ctx->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(p.e1, ctx->stream);
+    ctx->prof_pending.push_back(p);
+  }
+};
+}  // namespace mafe
 
 struct mafe_plan {
   mafe_frontend_desc d;  // table pointers nulled after creation

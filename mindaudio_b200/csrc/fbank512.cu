@@ -1,9 +1,467 @@
-// fbank512.cu -- placeholder until the specialised kernel lands (next commit).
+// fbank512.cu -- the specialised sm_100a kernel of the headline path: Kaldi-like log-mel filterbank
+// features (examples/conformer/dataset.py:117-168) with a 512-point FFT, fused end to end:
+//
+//   waveform tile -> [dither] -> pre-emphasis -> shared memory            (phase L)
+//   povey window, scalar frame-mean removal, radix-2 fold                 (phase F, registers)
+//   2 x 256-point FFT per frame PAIR, 16 lanes x 16 points, radix-16^2    (phase F)
+//   pair separation + |X|^2 + sparse mel (<= 2 filters per bin)           (phase S, lanes = frames)
+//   combine partial sums + ln + coalesced store                           (phase C)
+//
+// One CTA = 256 threads = one tile of 32 consecutive frames (16 frame pairs) of one utterance;
+// ragged batches come in through the tile table.  Two real frames (a, b) ride in one complex
+// sequence a + i*b; even and odd output bins come from two 256-point transforms that share one
+// shared-memory slot per pair (see fft512.cuh).  Nothing but the waveform is read from and
+// nothing but the features is written to HBM.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
+#include "fft512.cuh"
+
 namespace mafe {
-bool fast_plan_supported(const mafe_frontend_desc*) { return false; }
-int fast_plan_init(mafe_ctx*, mafe_plan*, const mafe_frontend_desc*) { return MAFE_E_UNSUPPORTED; }
-void fast_plan_free(mafe_plan*) {}
-int fast_tile_frames() { return 32; }
-int fast_run(mafe_ctx*, const mafe_plan*, mafe_batch*, const void*, int, float, float*) { return MAFE_E_UNSUPPORTED; }
+
+constexpr int kFastThreads = 256;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kTileFrames = 32;
+constexpr int kPairs = kTileFrames / 2;
+constexpr int kNfft = 512;
+constexpr int kBins = kNfft / 2 + 1;  // 257
+constexpr int kMaxY = 5632;           // floats of waveform per tile (31*hop + frame_len <= kMaxY)
+constexpr int kPlaneStride = 33;      // [mel][frame] planes padded against bank conflicts
+
+struct BinEntry {   // per FFT bin: contributes w0 to filter f0 and w1 to filter f0+1 (weights pre-scaled by 1/4)
+  int f0;
+  float w0, w1;
+  int pad;
+};
+
+struct FastTablesDev {
+  float* window;      // [512] analysis window, zero beyond frame_len
+  float2* w512;       // [256] W512^n
+  float2* w256t;      // [16][16] W256^(t*kj) stored [kj][t]
+  BinEntry* bins;     // [257]
+  int2* warp_range;   // [8] filters (lo, hi) a warp emits during a sweep
+  int* combine;       // [n_mels] bit0-1: number of contributing warps (0..2), bit2: plane of the first
+};
+
+struct FastParams {
+  const void* wave;
+  int wave_dtype;
+  float wave_scale;
+  const int64_t* sample_offsets;
+  const int64_t* frame_offsets;
+  const Tile* tiles;
+  const double* utt_sum;
+  int frame_len, hop, n_mels, ylen;
+  float pre_hi, pre_lo;
+  int preemph_on, remove_mean;
+  float dither;
+  uint64_t seed;
+  int log_kind;
+  float log_arg;
+  FastTablesDev tab;
+  float* out;
+};
+
+// ---- shared memory carve-up (bytes) ----
+struct FastSmem {
+  static constexpr size_t kZ = sizeof(float2) * kPairs * kSlotStride;  // 34944
+  static constexpr size_t kY = sizeof(float) * kMaxY;                  // 22528 (also the mel planes)
+  static constexpr size_t kWin = sizeof(float) * kNfft;
+  static constexpr size_t kW512 = sizeof(float2) * 256;
+  static constexpr size_t kW256 = sizeof(float2) * 256;
+  static constexpr size_t kBinsB = sizeof(BinEntry) * 264;
+  static constexpr size_t kTotal = kZ + kY + kWin + kW512 + kW256 + kBinsB;
+};
+
+__device__ __forceinline__ float fast_load_sample(const FastParams& P, int64_t g) {
+  return (P.wave_dtype == MAFE_WAVE_I16 ? (float)((const int16_t*)P.wave)[g] : ((const float*)P.wave)[g]) * P.wave_scale;
+}
+
+// One half of the pair's spectrum: 256-point FFT of v (HALF = 0: even bins, 1: odd bins) by the
+// 16-lane group, result left in the pair's slot; then the block-wide sweep of those bins
+// (lanes = frames) into the mel planes.  Must be called by all threads of the CTA.
+template <int HALF>
+__device__ __forceinline__ void fft_half_and_sweep(cpx (&v)[16], float2* Zs, float2* slot, const float2* s_w256,
+                                                   const BinEntry* s_bins, float* my_plane, int2 wr, int n_mels, int t,
+                                                   int lane, int warp) {
+  constexpr int half = HALF;
+  {
+    // radix-16 over j, twiddle W256^(t*kj), transpose through the slot
+    fft16(v);
+#pragma unroll
+    for (int kj = 0; kj < 16; ++kj) {
+      cpx x = v[fft16_pos(kj)];
+      if (kj > 0) {
+        const float2 tw = s_w256[kj * 16 + t];
+        x = cmulf(x, cx(tw.x, tw.y));
+      }
+      slot[kj * kRowStride + t] = make_float2(x.x, x.y);
+    }
+    __syncwarp();
+    cpx u[16];
+#pragma unroll
+    for (int tt = 0; tt < 16; ++tt) {
+      const float2 x = slot[t * kRowStride + tt];
+      u[tt] = cx(x.x, x.y);
+    }
+    __syncwarp();
+    fft16(u);
+#pragma unroll
+    for (int kt = 0; kt < 16; ++kt) {
+      const cpx x = u[fft16_pos(kt)];
+      slot[t + 16 * kt] = make_float2(x.x, x.y);  // bin 2*(t+16kt)+half of this pair's spectrum
+    }
+    __syncthreads();
+
+    // ---- phase S: lanes = frames, this warp sweeps FFT bins k = 2*kk + half, kk in its range ----
+    {
+      const float2* zp = Zs + (lane >> 1) * kSlotStride;
+      const float sgn = (lane & 1) ? -1.f : 1.f;  // frame a: Z[k] + conj Z[N-k];  frame b: Z[k] - conj Z[N-k]
+      int cur = wr.x;
+      float acc_lo = 0.f, acc_hi = 0.f;
+      const int kk_begin = warp * 16;
+      const int kk_end = kk_begin + 16 + ((half == 0 && warp == kFastWarps - 1) ? 1 : 0);  // + Nyquist bin 256
+#pragma unroll 4
+      for (int kk = kk_begin; kk < kk_end; ++kk) {
+        const int k = 2 * kk + half;
+        const int kr = half == 0 ? ((256 - kk) & 255) : (255 - kk);   // slot index of bin 512-k
+        const float2 zk = zp[kk & 255];
+        const float2 zn = zp[kr];
+        const float re = fmaf(sgn, zn.x, zk.x);
+        const float im = fmaf(-sgn, zn.y, zk.y);
+        const float pw = fmaf(re, re, im * im);
+        const BinEntry be = s_bins[k];
+        while (cur < be.f0) {  // warp-uniform: k is the same for all lanes
+          if (cur >= 0 && cur < n_mels) {
+            float* dst = my_plane + cur * kPlaneStride + lane;
+            *dst = half == 0 ? acc_lo : *dst + acc_lo;
+          }
+          acc_lo = acc_hi; acc_hi = 0.f; ++cur;
+        }
+        acc_lo = fmaf(be.w0, pw, acc_lo);
+        acc_hi = fmaf(be.w1, pw, acc_hi);
+      }
+      while (cur <= wr.y) {
+        if (cur >= 0 && cur < n_mels) {
+          float* dst = my_plane + cur * kPlaneStride + lane;
+          *dst = half == 0 ? acc_lo : *dst + acc_lo;
+        }
+        acc_lo = acc_hi; acc_hi = 0.f; ++cur;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kFastThreads, 2) fbank512_kernel(FastParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* Zs = reinterpret_cast<float2*>(smem_raw);
+  float* ybuf = reinterpret_cast<float*>(smem_raw + FastSmem::kZ);
+  float* planes = ybuf;  // aliased: the waveform is dead once every thread holds its points in registers
+  float* s_win = reinterpret_cast<float*>(smem_raw + FastSmem::kZ + FastSmem::kY);
+  float2* s_w512 = reinterpret_cast<float2*>(smem_raw + FastSmem::kZ + FastSmem::kY + FastSmem::kWin);
+  float2* s_w256 = s_w512 + 256;
+  BinEntry* s_bins = reinterpret_cast<BinEntry*>(s_w256 + 256);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Tile tile = P.tiles[blockIdx.x];
+  const uint32_t utt = (uint32_t)tile.utt;
+  const int64_t off = P.sample_offsets[utt];
+  const int64_t L = P.sample_offsets[utt + 1] - off;
+  const int64_t fo = P.frame_offsets[utt];
+  const int T = (int)(P.frame_offsets[utt + 1] - fo);
+  const int frame0 = tile.frame0;
+  const int nf = min(kTileFrames, T - frame0);
+
+  // ---- tables -> shared ----
+  for (int i = tid; i < kNfft; i += kFastThreads) s_win[i] = P.tab.window[i];
+  for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.tab.w512[i]; s_w256[i] = P.tab.w256t[i]; }
+  for (int i = tid; i < kBins; i += kFastThreads) s_bins[i] = P.tab.bins[i];
+
+  // ---- phase L: waveform tile, dither, pre-emphasis ----
+  {
+    const int64_t s0 = (int64_t)frame0 * P.hop;
+    const int need = (nf - 1) * P.hop + P.frame_len;  // samples actually covered by this tile's frames
+    for (int i = tid; i < P.ylen; i += kFastThreads) {
+      const int64_t s = s0 + i;
+      float v = 0.f;
+      if (i < need && s < L) {
+        v = fast_load_sample(P, off + s);
+        if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)s, utt, P.seed), v);
+        if (P.preemph_on) {
+          // x[s-1]: neighbouring lane, except lane 0 (re-read) -- only when no dither (dither needs its own g)
+          float vp = 0.f;
+          if (s > 0) {
+            vp = fast_load_sample(P, off + s - 1);
+            if (P.dither != 0.f) vp = fmaf(P.dither, dither_normal((uint64_t)(s - 1), utt, P.seed), vp);
+            v = fmaf(-P.pre_lo, vp, fmaf(-P.pre_hi, vp, v));
+          }
+        }
+      }
+      ybuf[i] = v;
+    }
+  }
+  float neg_mu = 0.f;
+  if (P.remove_mean) neg_mu = -(float)(P.utt_sum[utt] / ((double)T * (double)P.frame_len));
+  __syncthreads();
+
+  // ---- phase F: every 16-lane group transforms one frame pair ----
+  const int t = lane & 15;
+  const int pair = warp * 2 + (lane >> 4);
+  float2* slot = Zs + pair * kSlotStride;
+  cpx v0[16], v1[16];
+  {
+    const float* ya = ybuf + (2 * pair) * P.hop;
+    const float* yb = ya + P.hop;
+    const int flen = P.frame_len;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = t + 16 * j;
+      const float w = s_win[n];
+      // frames shorter than 512 are zero-padded: entries n >= frame_len stay 0 (no mean removal there)
+      cpx lo = cx(0.f, 0.f), hi = cx(0.f, 0.f);
+      if (n < flen) lo = cx(fmaf(ya[n], w, neg_mu), fmaf(yb[n], w, neg_mu));
+      const int n2 = n + 256;
+      if (n2 < flen) {
+        const float w2 = s_win[n2];
+        hi = cx(fmaf(ya[n2], w2, neg_mu), fmaf(yb[n2], w2, neg_mu));
+      }
+      v0[j] = lo + hi;
+      const float2 tw = s_w512[n];
+      v1[j] = cmulf(lo - hi, cx(tw.x, tw.y));
+    }
+  }
+  __syncthreads();  // ybuf is dead from here on (it becomes the mel planes)
+
+  const int2 wr = P.tab.warp_range[warp];
+  float* my_plane = planes + (warp & 1) * (P.n_mels * kPlaneStride);
+
+  fft_half_and_sweep<0>(v0, Zs, slot, s_w256, s_bins, my_plane, wr, P.n_mels, t, lane, warp);
+  fft_half_and_sweep<1>(v1, Zs, slot, s_w256, s_bins, my_plane, wr, P.n_mels, t, lane, warp);
+
+  // ---- phase C: combine the (<= 2) partial sums of every (frame, filter), log, coalesced store ----
+  {
+    const int nm = P.n_mels;
+    float* dst = P.out + (fo + frame0) * (int64_t)nm;
+    const int total = nf * nm;
+    for (int e = tid; e < total; e += kFastThreads) {
+      const int f = e / nm, m = e - f * nm;
+      const int c = P.tab.combine[m];
+      const int n = c & 3, p0 = (c >> 2) & 1;
+      float acc = 0.f;
+      if (n >= 1) acc = planes[p0 * (nm * kPlaneStride) + m * kPlaneStride + f];
+      if (n == 2) acc += planes[(p0 ^ 1) * (nm * kPlaneStride) + m * kPlaneStride + f];
+      float o;
+      switch (P.log_kind) {
+        case MAFE_LOG_LN_EPS_IF_ZERO: o = logf(acc == 0.f ? 2.220446049250313e-16f : acc); break;
+        case MAFE_LOG_LN_PLUS: o = logf(acc + P.log_arg); break;
+        default: o = acc; break;
+      }
+      dst[e] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast pre-pass: sum over all windowed frame entries of an utterance = sum_s y[s] * c(s), with
+// c(s) = sum of the window over the frames covering sample s (no frame materialisation).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, double* utt_sum) {
+  const Tile tile = P.tiles[blockIdx.x];
+  const uint32_t utt = (uint32_t)tile.utt;
+  const int64_t off = P.sample_offsets[utt];
+  const int T = (int)(P.frame_offsets[utt + 1] - P.frame_offsets[utt]);
+  const int hop = P.hop, flen = P.frame_len;
+  // this tile owns samples [frame0*hop, (frame0+32)*hop), clipped to the framed region of the utterance
+  const int64_t s_lo = (int64_t)tile.frame0 * hop;
+  const int64_t framed_end = (int64_t)(T - 1) * hop + flen;
+  // the utterance's last tile also owns the tail [.., framed_end) that its last frame reaches into
+  const int64_t s_hi = tile.frame0 + kTileFrames >= T ? framed_end : s_lo + (int64_t)kTileFrames * hop;
+  double acc = 0.0;
+  for (int64_t s = s_lo + threadIdx.x; s < s_hi; s += blockDim.x) {
+    float v = fast_load_sample(P, off + s);
+    if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)s, utt, P.seed), v);
+    if (P.preemph_on && s > 0) {
+      float vp = fast_load_sample(P, off + s - 1);
+      if (P.dither != 0.f) vp = fmaf(P.dither, dither_normal((uint64_t)(s - 1), utt, P.seed), vp);
+      v = fmaf(-P.pre_lo, vp, fmaf(-P.pre_hi, vp, v));
+    }
+    // frames t with 0 <= s - t*hop < flen, 0 <= t < T
+    const int t_hi = (int)min((int64_t)T - 1, s / hop);
+    float c = 0.f;
+    for (int tt = t_hi; tt >= 0; --tt) {
+      const int64_t n = s - (int64_t)tt * hop;
+      if (n >= flen) break;
+      c += __ldg(&P.tab.window[n]);
+    }
+    acc += (double)v * (double)c;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += ws[w];
+    atomicAdd(&utt_sum[utt], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct FastTablesHost {
+  FastTablesDev dev;
+  int ylen;
+};
+
+int fast_tile_frames() { return kTileFrames; }
+
+// per-bin form of the filterbank: <= 2 ADJACENT filters per bin, non-decreasing in k
+static bool build_bins(const mafe_frontend_desc* d, std::vector<BinEntry>& bins) {
+  const int nb = kBins, nm = d->n_mels;
+  bins.assign(nb, BinEntry{0, 0.f, 0.f, 0});
+  int prev = -1;
+  for (int k = 0; k < nb; ++k) {
+    int first = -1, count = 0, last = -1;
+    for (int m = 0; m < nm; ++m)
+      if (d->mel_fb[(size_t)m * nb + k] != 0.f) { if (first < 0) first = m; last = m; ++count; }
+    if (count > 2 || (count == 2 && last != first + 1)) return false;
+    BinEntry e{prev, 0.f, 0.f, 0};
+    if (count == 2) {
+      e.f0 = first; e.w0 = d->mel_fb[(size_t)first * nb + k]; e.w1 = d->mel_fb[(size_t)last * nb + k];
+    } else if (count == 1) {
+      // keep f0 monotone: attach the single filter as the upper one when that keeps order, else as the lower
+      if (first - 1 >= prev) { e.f0 = first - 1; e.w1 = d->mel_fb[(size_t)first * nb + k]; }
+      else { e.f0 = first; e.w0 = d->mel_fb[(size_t)first * nb + k]; }
+    } else {
+      e.f0 = prev;  // empty bin: stay where we are
+    }
+    if (e.f0 < prev) return false;
+    prev = e.f0;
+    e.w0 *= 0.25f; e.w1 *= 0.25f;  // the pair separation leaves 2*X: |2X|^2 / 4
+    bins[k] = e;
+  }
+  return true;
+}
+
+// the kernel's emit pattern, replayed on the host (it does not depend on data)
+static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector<int2>& ranges, std::vector<int>& comb) {
+  ranges.assign(kFastWarps, int2{0, -1});
+  std::vector<std::vector<int>> who(nm);
+  for (int w = 0; w < kFastWarps; ++w) {
+    const int k_lo = 32 * w, k_hi = (w == kFastWarps - 1) ? kBins : 32 * w + 32;
+    int lo = bins[k_lo].f0, hi = bins[k_hi - 1].f0 + 1;
+    ranges[w] = int2{lo, hi};
+    for (int m = std::max(lo, 0); m <= std::min(hi, nm - 1); ++m) who[m].push_back(w);
+  }
+  comb.assign(nm, 0);
+  for (int m = 0; m < nm; ++m) {
+    if (who[m].size() > 2) return false;
+    if (who[m].size() == 2 && who[m][1] != who[m][0] + 1) return false;
+    int n = (int)who[m].size();
+    int p0 = n ? (who[m][0] & 1) : 0;
+    comb[m] = n | (p0 << 2);
+  }
+  return true;
+}
+
+bool fast_plan_supported(const mafe_frontend_desc* d) {
+  if (d->n_fft != kNfft || d->center || d->out_kind != MAFE_OUT_LOGMEL || d->power != 2.0f || d->spec_scale != 1.0f)
+    return false;
+  if (!(d->log_kind == MAFE_LOG_LN_EPS_IF_ZERO || d->log_kind == MAFE_LOG_LN_PLUS || d->log_kind == MAFE_LOG_NONE)) return false;
+  if (d->n_mels < 1 || d->n_mels > 128) return false;
+  const int ylen = (kTileFrames - 1) * d->hop + d->frame_len;
+  if (ylen > kMaxY || 2 * d->n_mels * kPlaneStride > kMaxY) return false;
+  std::vector<BinEntry> bins;
+  if (!build_bins(d, bins)) return false;
+  std::vector<int2> ranges;
+  std::vector<int> comb;
+  return build_combine(bins, d->n_mels, ranges, comb);
+}
+
+template <typename T>
+static int up(T** dev, const std::vector<T>& h) {
+  MAFE_CUDA_CHECK(cudaMalloc((void**)dev, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  MAFE_CUDA_CHECK(cudaMemcpy(*dev, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MAFE_OK;
+}
+
+int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
+  (void)ctx;
+  FastTablesHost* th = new FastTablesHost();
+  memset(&th->dev, 0, sizeof(th->dev));
+  th->ylen = (kTileFrames - 1) * d->hop + d->frame_len;
+  p->fast_tables = th;
+  std::vector<float> win(kNfft, 0.f);
+  for (int i = 0; i < d->frame_len; ++i) win[i] = d->window[i];
+  std::vector<float2> w512(256), w256(256);
+  for (int n = 0; n < 256; ++n) {
+    double a = -2.0 * M_PI * n / 512.0;
+    w512[n] = make_float2((float)cos(a), (float)sin(a));
+  }
+  for (int kj = 0; kj < 16; ++kj)
+    for (int t = 0; t < 16; ++t) {
+      double a = -2.0 * M_PI * (double)(t * kj) / 256.0;
+      w256[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
+    }
+  std::vector<BinEntry> bins;
+  std::vector<int2> ranges;
+  std::vector<int> comb;
+  if (!build_bins(d, bins) || !build_combine(bins, d->n_mels, ranges, comb)) {
+    set_error("filterbank is not in per-bin form");
+    return MAFE_E_UNSUPPORTED;
+  }
+  int rc;
+  if ((rc = up(&th->dev.window, win))) return rc;
+  if ((rc = up(&th->dev.w512, w512))) return rc;
+  if ((rc = up(&th->dev.w256t, w256))) return rc;
+  if ((rc = up(&th->dev.bins, bins))) return rc;
+  if ((rc = up(&th->dev.warp_range, ranges))) return rc;
+  if ((rc = up(&th->dev.combine, comb))) return rc;
+  MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastSmem::kTotal));
+  return MAFE_OK;
+}
+
+void fast_plan_free(mafe_plan* p) {
+  FastTablesHost* th = static_cast<FastTablesHost*>(p->fast_tables);
+  if (!th) return;
+  cudaFree(th->dev.window); cudaFree(th->dev.w512); cudaFree(th->dev.w256t);
+  cudaFree(th->dev.bins); cudaFree(th->dev.warp_range); cudaFree(th->dev.combine);
+  delete th;
+  p->fast_tables = nullptr;
+}
+
+int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale, float* out) {
+  if (b->n_tiles == 0) return MAFE_OK;
+  const FastTablesHost* th = static_cast<const FastTablesHost*>(p->fast_tables);
+  const mafe_frontend_desc& d = p->d;
+  FastParams P;
+  P.wave = wave; P.wave_dtype = wave_dtype; P.wave_scale = wave_scale;
+  P.sample_offsets = b->sample_offsets_dev; P.frame_offsets = b->frame_offsets_dev; P.tiles = b->tiles_dev;
+  P.utt_sum = b->utt_sum_dev;
+  P.frame_len = d.frame_len; P.hop = d.hop; P.n_mels = d.n_mels; P.ylen = th->ylen;
+  P.pre_hi = (float)d.preemph; P.pre_lo = (float)(d.preemph - (double)P.pre_hi);
+  P.preemph_on = d.preemph != 0.0; P.remove_mean = d.remove_frame_mean;
+  P.dither = d.dither; P.seed = d.dither_seed;
+  P.log_kind = d.log_kind; P.log_arg = d.log_arg;
+  P.tab = th->dev;
+  P.out = out;
+  if (d.remove_frame_mean) {
+    MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
+    ProfScope ps(ctx, MAFE_PROF_FRAME_MEAN);
+    frame_sum_fast_kernel<<<b->n_tiles, 256, 0, ctx->stream>>>(P, b->utt_sum_dev);
+    MAFE_LAUNCH_CHECK(ctx);
+  }
+  {
+    ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+    fbank512_kernel<<<b->n_tiles, kFastThreads, FastSmem::kTotal, ctx->stream>>>(P);
+    MAFE_LAUNCH_CHECK(ctx);
+  }
+  return MAFE_OK;
+}
+
 }  // namespace mafe

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
 
   // ---- Stockham autosort stages ----
   {
-    float2* res = stockham_fft(cur, nxt, pairs, N, P.fft, P.tw);
+    float2* res = stockham_fft<float2>(cur, nxt, pairs, N, P.fft, P.tw);
     if (res != cur) { nxt = cur; cur = res; }
   }
 
@@ -360,6 +360,7 @@ int frame_mean_prepass(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const v
   GenericParams P;
   fill_params(P, p, b, wave, wave_dtype, wave_scale);
   MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
+  ProfScope ps(ctx, MAFE_PROF_FRAME_MEAN);
   frame_sum_kernel<<<b->n_tiles, kGenericThreads, 0, ctx->stream>>>(P, b->utt_sum_dev, p->tile_frames);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
@@ -385,6 +386,7 @@ int generic_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wa
     fill_int_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->group_max_dev, n, (int)0x80000000);
     MAFE_LAUNCH_CHECK(ctx);
   }
+  ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
   generic_frontend_kernel<<<b->n_tiles, kGenericThreads, p->smem_bytes, ctx->stream>>>(P);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;

@@ -328,6 +328,7 @@ int mafe_cmvn_utt(mafe_ctx* ctx, float* feats, const int64_t* fo, int32_t n_utts
   MAFE_REQUIRE(dim >= 1, "dim=%d", dim);
   if (n_utts <= 0) return MAFE_OK;
   cudaSetDevice(ctx->device);
+  ProfScope ps(ctx, MAFE_PROF_CMVN);
   cmvn_utt_kernel<<<n_utts, kCmvnThreads, 0, ctx->stream>>>(feats, fo, dim, mean_norm, std_norm);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
@@ -347,6 +348,7 @@ int mafe_cmvn_stats_accumulate(mafe_ctx* ctx, const float* feats, int64_t total_
   if (total_frames <= 0) return MAFE_OK;
   cudaSetDevice(ctx->device);
   int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, std::max<int64_t>(1, total_frames / 64));
+  ProfScope ps(ctx, MAFE_PROF_CMVN);
   cmvn_stats_kernel<<<grid, kCmvnThreads, 0, ctx->stream>>>(feats, total_frames, dim, stats);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;

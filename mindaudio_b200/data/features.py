@@ -63,8 +63,8 @@ def context_window(waveforms, left_frames=0, right_frames=0):
             eng.d2h(out, do)
             eng.sync()
             del keep
-    if nd == 2:
-        return out[0]
+    # nd == 2: the reference tests `len(x_shape) == 2` on the EXPANDED shape (features.py:104-106,
+    # 153-154), so the batch axis it added is never squeezed: [F, T] comes back as [1, F*C, T]
     if nd == 4:
         b, ch, f4, t4 = waveforms.shape
         out = out.reshape((b, out.shape[1], t4, out.shape[-1])).transpose((0, 3, 1, 2))
@@ -149,7 +149,8 @@ def _features(waveforms, plan_kw, n_out, deltas, context, left_frames, right_fra
             # axis (features.py:108-126) -> done by context_window() on the finished array below
             ctx_dev = context and waveforms.ndim < 3
             d_res, rows = _postprocess(eng, do, n_mats, t, n_out, deltas, ctx_dev, left_frames, right_frames)
-            out = np.empty(lead + (rows, t), dtype=np.float32)
+            # 2-D features through context_window come back [1, F*C, T] in the reference (see context_window)
+            out = np.empty((((1,) if ctx_dev and not lead else lead)) + (rows, t), dtype=np.float32)
             eng.d2h(out, d_res)
             eng.sync()
             del keep

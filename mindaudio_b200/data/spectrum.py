@@ -155,7 +155,7 @@ def stft(
     plan = eng.plan(n_fft=n_fft, hop=hop_length, center=dev_center, pad_mode=dev_pad if dev_center else "constant",
                     out_kind=L.OUT_COMPLEX, window=fft_window)
     out, fo = eng.run_frontend(plan, x.reshape(-1), _dense_offsets(x.shape[0], x.shape[1]))
-    frames = int(fo[1] - fo[0]) if x.shape[0] else 0
+    frames = plan.num_frames(x.shape[1])
     n_bins = 1 + n_fft // 2
     stft_matrix = _frames_to_ft(out.view(np.complex64), lead, frames, n_bins)
     if return_complex:
@@ -214,7 +214,7 @@ def istft(
         win_length = n_fft
     if hop_length is None:
         hop_length = int(win_length // 4)
-    ifft_window = T.analysis_window(window, win_length, n_fft).astype(np.float32)
+    ifft_window = np.ascontiguousarray(T.analysis_window(window, win_length, n_fft), dtype=np.float64)
     if length:
         padded_length = length + int(n_fft) if center else length
         n_frames = min(stft_matrix.shape[-1], int(np.ceil(padded_length / hop_length)))
@@ -229,18 +229,18 @@ def istft(
     # [.., F, T] -> frame-major [U, T, F] complex64
     z = np.ascontiguousarray(np.swapaxes(stft_matrix[..., :n_frames], -1, -2).reshape((n_utts, n_frames, n_bins)),
                              dtype=np.complex64)
-    y32 = np.empty((n_utts, expected_signal_len), dtype=np.float32)
+    y64 = np.empty((n_utts, expected_signal_len), dtype=np.float64)
     if z.size:
         eng = get_engine()
         with eng.lock:
             dz = eng.buf("wave", z.nbytes)
-            dy = eng.buf("out", y32.nbytes)
+            dy = eng.buf("out", y64.nbytes)
             keep = eng.h2d(dz, z)
             L.check(eng.lib.mafe_istft(eng.ctx, dz, n_utts, n_frames, n_fft, hop_length, _vp(ifft_window), dy))
-            eng.d2h(y32, dy)
+            eng.d2h(y64, dy)
             eng.sync()
             del keep
-    y = y32.astype(np.float64).reshape(lead + (expected_signal_len,))
+    y = y64.reshape(lead + (expected_signal_len,))
     if length is None:
         if center:
             y = y[..., int(n_fft // 2): -int(n_fft // 2)]
@@ -295,8 +295,7 @@ def _run_spec(plan, waveforms, pad, n_fft, center, db_group=L.DBGROUP_NONE, utt_
     eng = plan.engine
     out, fo = eng.run_frontend(plan, x.reshape(-1), _dense_offsets(x.shape[0], x.shape[1]), db_group=db_group,
                                utt_group=utt_group)
-    frames = int(fo[1] - fo[0]) if x.shape[0] else 0
-    return out, lead, frames
+    return out, lead, plan.num_frames(x.shape[1])
 
 
 def spectrogram(

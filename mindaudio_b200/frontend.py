@@ -70,7 +70,8 @@ class FbankPipeline:
 
     def use_torch_stream(self):
         import torch
-        self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        # torch's default stream has handle 0; pass cudaStreamLegacy (0x1) so it is not mistaken for "own stream"
+        self.eng.set_stream(torch.cuda.current_stream().cuda_stream or 1)
 
     # ---- device-resident ----
     def run(self, wave_ptr, batch, out_ptr, wave_dtype=L.WAVE_F32, wave_scale=1.0, stats_ptr=None):

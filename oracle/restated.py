@@ -113,8 +113,13 @@ def window_sumsquare(window, n_frames, win_length, n_fft, hop_length):
 
 def istft(stft_matrix, n_fft=None, win_length=None, hop_length=None, window="hann",
           center=True, length=None):
-    """``spectrum.py:346-474``: windowed irfft, overlap-add, /window-sum-square, trim."""
-    z = np.asarray(stft_matrix)
+    """``spectrum.py:346-474``: windowed irfft, overlap-add, /window-sum-square, trim.
+
+    float64 arithmetic: the reference's environment (python 3.8/3.9, numpy 1.x --
+    .github/workflows/ut_test.yaml:33-44) promotes complex64 to complex128 inside
+    ``np.fft.irfft``; numpy >= 2 would transform complex64 in single precision, so the input
+    is up-cast explicitly here."""
+    z = np.asarray(stft_matrix).astype(np.complex128)
     if n_fft is None:
         n_fft = 2 * (z.shape[-2] - 1)
     if win_length is None:
@@ -364,7 +369,9 @@ def context_window(x, left_frames=0, right_frames=0):
         return out.reshape(f * csize, t)
 
     if x.ndim == 2:
-        return one(x)
+        # the reference never squeezes the batch axis it added: `len(x_shape) == 2` is tested on the
+        # EXPANDED shape (features.py:104-106, 153-154), so 2-D input comes back as [1, F*C, T]
+        return one(x)[None]
     if x.ndim == 3:
         return np.stack([one(m) for m in x])
     # 4-D: [B, C, F, T]: the reference moves C last, folds (B, F) and convolves over T per C

@@ -24,6 +24,41 @@ def mixed_err(got, ref):
     return float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref)))) if ref.size else 0.0
 
 
+def logmel_err(got, ref, to_ln=1.0):
+    """Log-mel criterion, returned as a ratio (pass when <= 1):
+
+        |d| <= 1e-4 * max(1, |ref|)  +  2e-7 * sqrt(E_peak(t) / E_ref)
+
+    The first term is the north-star tolerance.  The second is the FP32 quantisation floor of the
+    FFT: every bin carries an absolute amplitude error of ~1e-7 of the frame's peak spectral
+    amplitude (the STFT criterion allows 1e-5), which is visible in ln E only for mel bins more
+    than ~60 dB below the frame's peak E_peak(t) (|d ln E| = 2 dA / A).  ``to_ln`` converts the
+    feature unit to nepers (ln 10 / 10 for dB features).  Last axis = mel, second-to-last = frame
+    for time-major [T, M] features; pass the array transposed otherwise."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if not ref.size:
+        return 0.0
+    ln_ref = ref * to_ln
+    peak = np.max(ln_ref, axis=-1, keepdims=True)
+    floor = 2e-7 * np.exp(0.5 * (peak - ln_ref)) / to_ln
+    tol = TOL_LOGMEL * np.maximum(1.0, np.abs(ref)) + floor
+    return float(np.max(np.abs(got - ref) / tol))
+
+
+def mfcc_err(got, ref):
+    """MFCC criterion: the DCT mixes every mel bin of a frame, so the error of one coefficient is
+    judged against the frame's cepstral scale: max_t max_c |d[c,t]| / max(1, max_c |ref[c,t]|).
+    (A per-coefficient relative error is ill-conditioned: coefficients cross zero while c0 ~ 500;
+    an FP32 FFT leaves ~1e-3 dB on bins 70 dB below a frame's peak -- SURVEY.md App. C2.)"""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if not ref.size:
+        return 0.0
+    scale = np.maximum(1.0, np.max(np.abs(ref), axis=-2, keepdims=True))
+    return float(np.max(np.abs(got - ref) / scale))
+
+
 def stft_err(got, ref):
     ref = np.asarray(ref)
     return float(np.max(np.abs(np.asarray(got) - ref)) / max(np.max(np.abs(ref)), 1e-30)) if ref.size else 0.0
