@@ -108,6 +108,11 @@ typedef struct mafe_frontend_desc {
   int32_t n_mfcc;   /* MAFE_OUT_MFCC: columns of dct                                            */
   const float* dct; /* [n_mels][n_mfcc] (create_dct layout, features.py:337)                    */
 
+  /* fused per-utterance CMVN of the frame-major output (examples/ECAPA-TDNN/spec_augment.py:43-70):
+   * (x - mean_t) / std_t per feature dim over the utterance's frames; both 0 = off */
+  int32_t utt_cmvn_mean;
+  int32_t utt_cmvn_std;
+
   int32_t allow_fast_path; /* 1: use a specialised kernel when the configuration has one        */
 } mafe_frontend_desc;
 

@@ -37,6 +37,7 @@ class FrontendDesc(C.Structure):
         ("n_mels", C.c_int32), ("mel_fb", C.POINTER(C.c_float)), ("log_kind", C.c_int32),
         ("log_arg", C.c_float), ("log_mult", C.c_float), ("log_offset", C.c_float), ("top_db", C.c_float),
         ("n_mfcc", C.c_int32), ("dct", C.POINTER(C.c_float)),
+        ("utt_cmvn_mean", C.c_int32), ("utt_cmvn_std", C.c_int32),
         ("allow_fast_path", C.c_int32),
     ]
 

@@ -269,6 +269,7 @@ int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, i
   }
   b->total_frames = b->frame_offsets_host[n_utts];
   b->total_samples = n_utts ? so[n_utts] - so[0] : 0;
+  b->wave_len = n_utts ? so[n_utts] : 0;
   b->n_tiles = (int32_t)tiles.size();
   b->n_groups = utt_group ? max_group + 1 : std::max(n_utts, 1);
   cudaStream_t st = ctx->stream;
@@ -299,6 +300,9 @@ int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, i
     if ((e = cudaMalloc((void**)&b->utt_group_dev, (size_t)n_utts * 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMemcpyAsync(b->utt_group_dev, utt_group, (size_t)n_utts * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
   }
+  if ((plan->d.utt_cmvn_mean || plan->d.utt_cmvn_std) && n_utts > 0) {
+    if ((e = cudaMalloc((void**)&b->utt_stats_dev, (size_t)n_utts * 2 * plan->out_dim * sizeof(double))) != cudaSuccess) return fail(e);
+  }
   if (plan->d.out_kind == MAFE_OUT_MFCC && b->total_frames > 0) {
     b->scratch_bytes = (size_t)b->total_frames * plan->d.n_mels * sizeof(float);
     if ((e = cudaMalloc((void**)&b->scratch_dev, b->scratch_bytes)) != cudaSuccess) return fail(e);
@@ -320,6 +324,7 @@ int mafe_batch_destroy(mafe_batch* b) {
   cudaFree(b->group_max_dev);
   cudaFree(b->scratch_dev);
   cudaFree(b->work_counter_dev);
+  cudaFree(b->utt_stats_dev);
   delete b;
   return MAFE_OK;
 }
@@ -344,17 +349,24 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   if (batch->total_frames == 0) return MAFE_OK;
   MAFE_REQUIRE(wave_dev && out_dev, "mafe_frontend_run: NULL buffer");
   DeviceGuard g(ctx->device);
-  if (plan->fast) return fast_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev);
   const mafe_frontend_desc& d = plan->d;
+  const bool cmvn = d.utt_cmvn_mean || d.utt_cmvn_std;
+  MAFE_REQUIRE(!(cmvn && d.out_kind == MAFE_OUT_COMPLEX), "utterance CMVN needs a real-valued output kind");
+  if (plan->fast) return fast_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev);  // CMVN fused inside
+  int rc;
   if (d.out_kind == MAFE_OUT_MFCC) {
-    int rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, batch->scratch_dev, MAFE_OUT_LOGMEL, db_group);
+    rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, batch->scratch_dev, MAFE_OUT_LOGMEL, db_group);
     if (rc) return rc;
-    return dct_run(ctx, plan, batch, batch->scratch_dev, out_dev, db_group);
+    rc = dct_run(ctx, plan, batch, batch->scratch_dev, out_dev, db_group);
+  } else {
+    rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev, -1, db_group);
+    if (rc) return rc;
+    if (d.out_kind == MAFE_OUT_LOGMEL && d.log_kind == MAFE_LOG_DB)
+      rc = db_clamp_run(ctx, plan, batch, out_dev, plan->out_dim, db_group);
   }
-  int rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev, -1, db_group);
   if (rc) return rc;
-  if (d.out_kind == MAFE_OUT_LOGMEL && d.log_kind == MAFE_LOG_DB)
-    return db_clamp_run(ctx, plan, batch, out_dev, plan->out_dim, db_group);
+  if (cmvn)
+    return mafe_cmvn_utt(ctx, out_dev, batch->frame_offsets_dev, batch->n_utts, plan->out_dim, d.utt_cmvn_mean, d.utt_cmvn_std);
   return MAFE_OK;
 }
 

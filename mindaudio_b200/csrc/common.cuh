@@ -115,6 +115,7 @@ struct mafe_batch {
   int32_t n_utts = 0;
   int64_t total_frames = 0;
   int64_t total_samples = 0;
+  int64_t wave_len = 0;  // elements of the flat waveform array the offsets index into (= last offset)
   int32_t n_tiles = 0;
   int32_t n_groups = 0;
   std::vector<int64_t> frame_offsets_host;
@@ -127,6 +128,7 @@ struct mafe_batch {
   float* scratch_dev = nullptr;           // MFCC intermediate [total_frames][n_mels]
   size_t scratch_bytes = 0;
   int32_t* work_counter_dev = nullptr;    // persistent-kernel tile counter
+  double* utt_stats_dev = nullptr;        // [n_utts][2][dim] fused utterance-CMVN statistics
 };
 
 namespace mafe {

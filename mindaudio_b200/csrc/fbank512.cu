@@ -313,9 +313,15 @@ __global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, doubl
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+}  // namespace mafe
+#include "fbank512_baked.cuh"
+namespace mafe {
+
 struct FastTablesHost {
   FastTablesDev dev;
   int ylen;
+  bool baked = false;     // the plan is exactly the conformer configuration the baked kernel was generated for
+  BakedWeights weights;   // (w0, w1) per bin for the baked kernel's parameter bank
 };
 
 int fast_tile_frames() { return kTileFrames; }
@@ -423,6 +429,13 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
   if ((rc = up(&th->dev.warp_range, ranges))) return rc;
   if ((rc = up(&th->dev.combine, comb))) return rc;
   MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastSmem::kTotal));
+  th->baked = d->frame_len == kV2Flen && d->hop == kV2Hop && d->n_mels == kV2Mels;
+  for (int k = 0; k < kBins && th->baked; ++k) th->baked = bins[k].f0 == kF0[k];
+  if (th->baked) {
+    for (int k = 0; k < kBins; ++k) th->weights.w[k] = make_float2(bins[k].w0, bins[k].w1);
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
+  }
   return MAFE_OK;
 }
 
@@ -456,11 +469,40 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     frame_sum_fast_kernel<<<b->n_tiles, 256, 0, ctx->stream>>>(P, b->utt_sum_dev);
     MAFE_LAUNCH_CHECK(ctx);
   }
+  const bool cmvn = d.utt_cmvn_mean || d.utt_cmvn_std;
+  if (th->baked && ((uintptr_t)wave & 15) == 0) {
+    V2Params Q;
+    Q.wave = wave; Q.total_samples = b->wave_len; Q.wave_scale = wave_scale;
+    Q.sample_offsets = b->sample_offsets_dev; Q.frame_offsets = b->frame_offsets_dev; Q.tiles = b->tiles_dev;
+    Q.n_tiles = b->n_tiles; Q.utt_sum = b->utt_sum_dev; Q.utt_stats = cmvn ? b->utt_stats_dev : nullptr;
+    Q.pre_hi = P.pre_hi; Q.pre_lo = P.pre_lo; Q.preemph_on = P.preemph_on; Q.remove_mean = P.remove_mean;
+    Q.dither = P.dither; Q.seed = P.seed; Q.log_kind = P.log_kind; Q.log_arg = P.log_arg;
+    Q.window = th->dev.window; Q.w512 = th->dev.w512; Q.w256t = th->dev.w256t; Q.combine = th->dev.combine;
+    Q.out = out;
+    if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
+    const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
+    {
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      if (wave_dtype == MAFE_WAVE_I16)
+        fbank512_baked_kernel<true><<<grid, kFastThreads, V2Smem::kTotal, ctx->stream>>>(Q, th->weights);
+      else
+        fbank512_baked_kernel<false><<<grid, kFastThreads, V2Smem::kTotal, ctx->stream>>>(Q, th->weights);
+      MAFE_LAUNCH_CHECK(ctx);
+    }
+    if (cmvn) {
+      ProfScope ps(ctx, MAFE_PROF_CMVN);
+      cmvn_utt_apply_kernel<<<std::min(b->n_tiles, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(
+          out, b->tiles_dev, b->n_tiles, b->frame_offsets_dev, b->utt_stats_dev, d.utt_cmvn_mean, d.utt_cmvn_std);
+      MAFE_LAUNCH_CHECK(ctx);
+    }
+    return MAFE_OK;
+  }
   {
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
     fbank512_kernel<<<b->n_tiles, kFastThreads, FastSmem::kTotal, ctx->stream>>>(P);
     MAFE_LAUNCH_CHECK(ctx);
   }
+  if (cmvn) return mafe_cmvn_utt(ctx, out, b->frame_offsets_dev, b->n_utts, d.n_mels, d.utt_cmvn_mean, d.utt_cmvn_std);
   return MAFE_OK;
 }
 

@@ -1,0 +1,456 @@
+// fbank512_baked.cuh -- version 2 of the headline kernel, specialised for the conformer example's
+// exact configuration (400-sample frames, hop 160, 512-point FFT, 80 Kaldi triangles;
+// examples/conformer/dataset.py:117-168).  Included by fbank512.cu.
+//
+//  * persistent CTAs (2 per SM) striding over the tile table;
+//  * the waveform tile of the NEXT work item is prefetched by the TMA engine
+//    (cp.async.bulk global -> shared, mbarrier completion) while the current one is computed;
+//  * frame geometry is compile time (no predicates in the load/fold code);
+//  * the sparse mel projection is STRAIGHT-LINE code: which filters an FFT bin feeds (kF0, generated
+//    by tools/gen_kaldi80_table.py) is baked in, only the weights are run-time data and sit in the
+//    kernel-parameter constant bank, so an FFMA reads them as an immediate constant operand;
+//  * per-utterance CMVN statistics (sum x, sum x^2 per mel bin) are accumulated on the fly.
+#pragma once
+
+namespace mafe {
+
+#include "kaldi80_f0.inc"
+
+constexpr int kV2Flen = 400;
+constexpr int kV2Hop = 160;
+constexpr int kV2Mels = 80;
+constexpr int kV2Ylen = (kTileFrames - 1) * kV2Hop + kV2Flen;  // 5360 samples feed one tile
+constexpr int kV2RawBytes = 21504;                              // (5360 + 1 prev) * 4 + alignment slack, 16 B multiple
+constexpr int kV2StageStride = 84;                              // [frame][80] staging rows, padded (16 B multiple)
+
+struct BakedWeights {  // kernel-parameter resident: c[0][..] operands
+  float2 w[kBins];     // (w0, w1) of every FFT bin, pre-scaled by 1/4
+};
+
+struct V2Params {
+  const void* wave;
+  int64_t total_samples;  // length of the flat waveform array (elements)
+  float wave_scale;
+  const int64_t* sample_offsets;
+  const int64_t* frame_offsets;
+  const Tile* tiles;
+  int n_tiles;
+  const double* utt_sum;  // frame-mean accumulators (pre-pass)
+  double* utt_stats;      // [n_utts][2][80] sum x, sum x^2 of the raw log-mel (or null)
+  float pre_hi, pre_lo;
+  int preemph_on, remove_mean;
+  float dither;
+  uint64_t seed;
+  int log_kind;
+  float log_arg;
+  const float* window;   // [400]
+  const float2* w512;    // [256]
+  const float2* w256t;   // [16][16]
+  const int* combine;    // [80]
+  float* out;
+};
+
+struct V2Smem {
+  static constexpr size_t kRaw0 = 0;
+  static constexpr size_t kRaw1 = kV2RawBytes;
+  static constexpr size_t kY = 2 * kV2RawBytes;                          // float[5376]: pre-emphasised tile, then the mel planes
+  static constexpr size_t kYBytes = sizeof(float) * 5376;
+  static constexpr size_t kZ = kY + kYBytes;                             // float2[16][273], then the output staging
+  static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
+  static constexpr size_t kWin = kZ + kZBytes;                           // float[400]
+  static constexpr size_t kW512 = kWin + sizeof(float) * 400;            // float2[256]
+  static constexpr size_t kW256 = kW512 + sizeof(float2) * 256;          // float2[256]
+  static constexpr size_t kBar = kW256 + sizeof(float2) * 256;           // 2 mbarriers
+  static constexpr size_t kTotal = kBar + 16;
+};
+static_assert(V2Smem::kZ % 16 == 0 && V2Smem::kBar % 8 == 0, "smem alignment");
+static_assert(2 * kV2Mels * kPlaneStride <= 5376, "mel planes must fit in the y buffer");
+static_assert(kTileFrames * kV2StageStride * 4 <= (int)V2Smem::kZBytes, "staging must fit in the Z buffer");
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (SASS: SYNCS.*, UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// geometry of the bytes a tile needs from the flat waveform array
+template <bool I16>
+struct TileSrc {
+  int64_t g0;        // element index of the "previous sample" slot (sample s0 - 1 of the utterance), may be -1
+  int64_t ga_byte;   // 16 B aligned start of the bulk copy
+  uint32_t bytes;    // bulk copy size (multiple of 16), 0 if nothing can be bulk-copied
+  int shift;         // element index of g0 inside the raw buffer
+  int64_t cov_end;   // first element NOT covered by the bulk copy (scalar patch-up from here)
+  int64_t end_elem;  // one past the last element the tile needs
+};
+
+template <bool I16>
+__device__ __forceinline__ TileSrc<I16> tile_src(const V2Params& P, const Tile tile, int64_t off, int T) {
+  constexpr int ES = I16 ? 2 : 4;
+  TileSrc<I16> r;
+  const int nf = min(kTileFrames, T - tile.frame0);
+  const int64_t s0 = (int64_t)tile.frame0 * kV2Hop;
+  const int need = (nf - 1) * kV2Hop + kV2Flen;
+  r.g0 = off + s0 - 1;
+  r.end_elem = off + s0 + need;
+  const int64_t first = r.g0 < 0 ? 0 : r.g0;
+  r.ga_byte = (first * ES) & ~(int64_t)15;
+  const int64_t total_bytes16 = (P.total_samples * ES) & ~(int64_t)15;
+  int64_t gb = (r.end_elem * ES + 15) & ~(int64_t)15;
+  if (gb > total_bytes16) gb = total_bytes16;
+  r.bytes = gb > r.ga_byte ? (uint32_t)(gb - r.ga_byte) : 0u;
+  r.shift = (int)(r.g0 - r.ga_byte / ES);  // -1 only when g0 == -1 (first tile of the first utterance)
+  r.cov_end = r.bytes ? gb / ES : first;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// straight-line sparse mel sweep: warp W, bins k = 2*kk + HALF for kk in [16W, 16W+16) (+ Nyquist)
+// ---------------------------------------------------------------------------------------------
+template <int HALF>
+__device__ __forceinline__ void emit_filter(float* plane, int lane, int m, float v) {
+  float* dst = plane + m * kPlaneStride + lane;
+  if (HALF == 0) *dst = v; else *dst += v;
+}
+
+template <int HALF, int CUR, int HI>
+__device__ __forceinline__ void sweep_tail(float acc_lo, float acc_hi, float* plane, int lane) {
+  if constexpr (CUR <= HI) {
+    if constexpr (CUR >= 0 && CUR < kV2Mels) emit_filter<HALF>(plane, lane, CUR, acc_lo);
+    sweep_tail<HALF, CUR + 1, HI>(acc_hi, 0.f, plane, lane);
+  }
+}
+
+template <int HALF, int KK, int KK_END, int CUR, int HI>
+__device__ __forceinline__ void sweep_step(float acc_lo, float acc_hi, const float2* zp, float sgn, float* plane, int lane,
+                                           const BakedWeights& W) {
+  if constexpr (KK == KK_END) {
+    sweep_tail<HALF, CUR, HI>(acc_lo, acc_hi, plane, lane);
+  } else {
+    constexpr int k = 2 * KK + HALF;
+    if constexpr (CUR < kF0[k]) {
+      if constexpr (CUR >= 0 && CUR < kV2Mels) emit_filter<HALF>(plane, lane, CUR, acc_lo);
+      sweep_step<HALF, KK, KK_END, CUR + 1, HI>(acc_hi, 0.f, zp, sgn, plane, lane, W);
+    } else {
+      constexpr int kr = HALF == 0 ? ((256 - KK) & 255) : (255 - KK);  // slot index of bin 512 - k
+      const float2 zk = zp[KK & 255];
+      const float2 zn = zp[kr];
+      const float re = fmaf(sgn, zn.x, zk.x);
+      const float im = fmaf(-sgn, zn.y, zk.y);
+      const float pw = fmaf(re, re, im * im);
+      acc_lo = fmaf(W.w[k].x, pw, acc_lo);
+      acc_hi = fmaf(W.w[k].y, pw, acc_hi);
+      sweep_step<HALF, KK + 1, KK_END, CUR, HI>(acc_lo, acc_hi, zp, sgn, plane, lane, W);
+    }
+  }
+}
+
+template <int HALF, int WARP>
+__device__ __forceinline__ void sweep_warp(const float2* zp, float sgn, float* planes, int lane, const BakedWeights& W) {
+  constexpr int k_lo = 32 * WARP;
+  constexpr int k_hi = WARP == kFastWarps - 1 ? kBins : 32 * WARP + 32;
+  constexpr int lo = kF0[k_lo], hi = kF0[k_hi - 1] + 1;
+  constexpr int kk_end = 16 * WARP + 16 + ((HALF == 0 && WARP == kFastWarps - 1) ? 1 : 0);
+  float* plane = planes + (WARP & 1) * (kV2Mels * kPlaneStride);
+  sweep_step<HALF, 16 * WARP, kk_end, lo, hi>(0.f, 0.f, zp, sgn, plane, lane, W);
+}
+
+template <int HALF>
+__device__ __forceinline__ void sweep_dispatch(int warp, const float2* zp, float sgn, float* planes, int lane,
+                                               const BakedWeights& W) {
+  switch (warp) {
+    case 0: sweep_warp<HALF, 0>(zp, sgn, planes, lane, W); break;
+    case 1: sweep_warp<HALF, 1>(zp, sgn, planes, lane, W); break;
+    case 2: sweep_warp<HALF, 2>(zp, sgn, planes, lane, W); break;
+    case 3: sweep_warp<HALF, 3>(zp, sgn, planes, lane, W); break;
+    case 4: sweep_warp<HALF, 4>(zp, sgn, planes, lane, W); break;
+    case 5: sweep_warp<HALF, 5>(zp, sgn, planes, lane, W); break;
+    case 6: sweep_warp<HALF, 6>(zp, sgn, planes, lane, W); break;
+    default: sweep_warp<HALF, 7>(zp, sgn, planes, lane, W); break;
+  }
+}
+
+// 256-point transform of v by the 16-lane group; result (bin 2*(t+16kt)+HALF at slot[t+16kt])
+__device__ __forceinline__ void fft256_group(cpx (&v)[16], float2* slot, const float2* s_w256, int t) {
+  fft16(v);
+#pragma unroll
+  for (int kj = 0; kj < 16; ++kj) {
+    cpx x = v[fft16_pos(kj)];
+    if (kj > 0) {
+      const float2 tw = s_w256[kj * 16 + t];
+      x = cmulf(x, cx(tw.x, tw.y));
+    }
+    slot[kj * kRowStride + t] = make_float2(x.x, x.y);
+  }
+  __syncwarp();
+  cpx u[16];
+#pragma unroll
+  for (int tt = 0; tt < 16; ++tt) {
+    const float2 x = slot[t * kRowStride + tt];
+    u[tt] = cx(x.x, x.y);
+  }
+  __syncwarp();
+  fft16(u);
+#pragma unroll
+  for (int kt = 0; kt < 16; ++kt) {
+    const cpx x = u[fft16_pos(kt)];
+    slot[t + 16 * kt] = make_float2(x.x, x.y);
+  }
+}
+
+template <bool I16>
+__device__ __forceinline__ float raw_elem(const unsigned char* raw, int idx, float scale) {
+  if (I16) return (float)reinterpret_cast<const int16_t*>(raw)[idx] * scale;
+  return reinterpret_cast<const float*>(raw)[idx] * scale;
+}
+
+template <bool I16>
+__global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V2Params P, const BakedWeights W) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  auto raw_buf = [&](int b) -> unsigned char* { return smem + (size_t)b * kV2RawBytes; };
+  float* ybuf = reinterpret_cast<float*>(smem + V2Smem::kY);
+  float* planes = ybuf;
+  float2* Zs = reinterpret_cast<float2*>(smem + V2Smem::kZ);
+  float* stage = reinterpret_cast<float*>(smem + V2Smem::kZ);
+  float* s_win = reinterpret_cast<float*>(smem + V2Smem::kWin);
+  float2* s_w512 = reinterpret_cast<float2*>(smem + V2Smem::kW512);
+  float2* s_w256 = reinterpret_cast<float2*>(smem + V2Smem::kW256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + V2Smem::kBar);
+  constexpr int ES = I16 ? 2 : 4;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kV2Flen; i += kFastThreads) s_win[i] = P.window[i];
+  for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // prologue: fetch the first tile
+  int ti = blockIdx.x;
+  if (ti < P.n_tiles && tid == 0) {
+    const Tile tile = P.tiles[ti];
+    const int64_t off = P.sample_offsets[tile.utt];
+    const int T = (int)(P.frame_offsets[tile.utt + 1] - P.frame_offsets[tile.utt]);
+    const TileSrc<I16> src = tile_src<I16>(P, tile, off, T);
+    if (src.bytes) {
+      mbar_expect_tx(&bars[0], src.bytes);
+      tma_bulk_g2s(raw_buf(0), (const unsigned char*)P.wave + src.ga_byte, src.bytes, &bars[0]);
+    } else {
+      mbar_arrive(&bars[0]);
+    }
+  }
+
+  uint32_t phase0 = 0, phase1 = 0;
+  int buf = 0;
+  for (; ti < P.n_tiles; ti += gridDim.x, buf ^= 1) {
+    const Tile tile = P.tiles[ti];
+    const uint32_t utt = (uint32_t)tile.utt;
+    const int64_t off = P.sample_offsets[utt];
+    const int64_t fo = P.frame_offsets[utt];
+    const int T = (int)(P.frame_offsets[utt + 1] - fo);
+    const int frame0 = tile.frame0;
+    const int nf = min(kTileFrames, T - frame0);
+    const TileSrc<I16> src = tile_src<I16>(P, tile, off, T);
+
+    // prefetch the next tile of this CTA into the other buffer (free since the previous iteration's pass P)
+    const int tn = ti + gridDim.x;
+    if (tn < P.n_tiles && tid == 0) {
+      const Tile nt = P.tiles[tn];
+      const int64_t noff = P.sample_offsets[nt.utt];
+      const int nT = (int)(P.frame_offsets[nt.utt + 1] - P.frame_offsets[nt.utt]);
+      const TileSrc<I16> ns = tile_src<I16>(P, nt, noff, nT);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (ns.bytes) {
+        mbar_expect_tx(&bars[buf ^ 1], ns.bytes);
+        tma_bulk_g2s(raw_buf(buf ^ 1), (const unsigned char*)P.wave + ns.ga_byte, ns.bytes, &bars[buf ^ 1]);
+      } else {
+        mbar_arrive(&bars[buf ^ 1]);
+      }
+    }
+
+    // wait for this tile's bytes
+    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    unsigned char* rb = raw_buf(buf);
+    // scalar patch-up of what the 16 B-granular bulk copy could not cover (end of the flat array)
+    if (src.cov_end < src.end_elem) {
+      const int64_t base_elem = src.ga_byte / ES;
+      for (int64_t e = src.cov_end + tid; e < src.end_elem; e += kFastThreads) {
+        if (I16) reinterpret_cast<int16_t*>(rb)[e - base_elem] = ((const int16_t*)P.wave)[e];
+        else reinterpret_cast<float*>(rb)[e - base_elem] = ((const float*)P.wave)[e];
+      }
+      __syncthreads();
+    }
+
+    // ---- pass P: [dither] + pre-emphasis, raw -> ybuf (y[0] = x[0] at the start of an utterance) ----
+    {
+      const int64_t s0 = (int64_t)frame0 * kV2Hop;
+      const int need = (nf - 1) * kV2Hop + kV2Flen;
+      const int sh = src.shift + 1;  // raw index of sample s0
+      for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
+        float x[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int i = i0 - 1 + j;
+          float v = 0.f;
+          if (i < need && (i >= 0 || s0 > 0)) {
+            v = raw_elem<I16>(rb, sh + i, P.wave_scale);
+            if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)(s0 + i), utt, P.seed), v);
+          }
+          x[j] = v;
+        }
+        float4 y;
+        if (P.preemph_on) {
+          y.x = fmaf(-P.pre_lo, x[0], fmaf(-P.pre_hi, x[0], x[1]));
+          y.y = fmaf(-P.pre_lo, x[1], fmaf(-P.pre_hi, x[1], x[2]));
+          y.z = fmaf(-P.pre_lo, x[2], fmaf(-P.pre_hi, x[2], x[3]));
+          y.w = fmaf(-P.pre_lo, x[3], fmaf(-P.pre_hi, x[3], x[4]));
+        } else {
+          y = make_float4(x[1], x[2], x[3], x[4]);
+        }
+        *reinterpret_cast<float4*>(ybuf + i0) = y;
+      }
+    }
+    float neg_mu = 0.f;
+    if (P.remove_mean) neg_mu = -(float)(P.utt_sum[utt] / ((double)T * (double)kV2Flen));
+    __syncthreads();
+
+    // ---- phase F: frame pair -> registers, window, mean removal, radix-2 fold ----
+    const int t = lane & 15;
+    const int pair = warp * 2 + (lane >> 4);
+    float2* slot = Zs + pair * kSlotStride;
+    cpx v0[16], v1[16];
+    {
+      const float* ya = ybuf + (2 * pair) * kV2Hop;
+      const float* yb = ya + kV2Hop;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = t + 16 * j;
+        const float w = s_win[n];
+        const cpx lo = cx(fmaf(ya[n], w, neg_mu), fmaf(yb[n], w, neg_mu));
+        const float2 tw = s_w512[n];
+        if (j < 9) {  // n + 256 < 400 for every lane exactly when j <= 8
+          const float w2 = s_win[n + 256];
+          const cpx hi = cx(fmaf(ya[n + 256], w2, neg_mu), fmaf(yb[n + 256], w2, neg_mu));
+          v0[j] = lo + hi;
+          v1[j] = cmulf(lo - hi, cx(tw.x, tw.y));
+        } else {
+          v0[j] = lo;
+          v1[j] = cmulf(lo, cx(tw.x, tw.y));
+        }
+      }
+    }
+    __syncthreads();  // ybuf is dead: it becomes the mel planes
+
+    const float2* zp = Zs + (lane >> 1) * kSlotStride;
+    const float sgn = (lane & 1) ? -1.f : 1.f;
+    fft256_group(v0, slot, s_w256, t);
+    __syncthreads();
+    sweep_dispatch<0>(warp, zp, sgn, planes, lane, W);
+    __syncthreads();
+    fft256_group(v1, slot, s_w256, t);
+    __syncthreads();
+    sweep_dispatch<1>(warp, zp, sgn, planes, lane, W);
+    __syncthreads();
+
+    // ---- phase C1: combine the (<= 2) partial sums, log, stage [frame][80] ----
+    for (int e = tid; e < kTileFrames * kV2Mels; e += kFastThreads) {
+      const int f = e / kV2Mels, m = e - f * kV2Mels;  // lanes = filters: planes (stride 33) and stage both conflict-free
+      const int c = P.combine[m];
+      const int n = c & 3, p0 = (c >> 2) & 1;
+      float acc = 0.f;
+      if (n >= 1) acc = planes[p0 * (kV2Mels * kPlaneStride) + m * kPlaneStride + f];
+      if (n == 2) acc += planes[(p0 ^ 1) * (kV2Mels * kPlaneStride) + m * kPlaneStride + f];
+      float o;
+      if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) o = __logf(acc == 0.f ? 2.220446049250313e-16f : acc);
+      else if (P.log_kind == MAFE_LOG_LN_PLUS) o = __logf(acc + P.log_arg);
+      else o = acc;
+      stage[f * kV2StageStride + m] = o;
+    }
+    __syncthreads();
+
+    // ---- phase C2: coalesced float4 stores + per-utterance CMVN statistics ----
+    {
+      float4* dst = reinterpret_cast<float4*>(P.out + (fo + frame0) * (int64_t)kV2Mels);
+      const int total4 = nf * (kV2Mels / 4);
+      for (int q = tid; q < total4; q += kFastThreads) {
+        const int f = q / (kV2Mels / 4), m4 = q - f * (kV2Mels / 4);
+        dst[q] = *reinterpret_cast<const float4*>(stage + f * kV2StageStride + 4 * m4);
+      }
+      if (P.utt_stats != nullptr && tid < 2 * kV2Mels) {
+        const int m = tid % kV2Mels, which = tid / kV2Mels;
+        double s = 0.0;
+        for (int f = 0; f < nf; ++f) {
+          const double v = (double)stage[f * kV2StageStride + m];
+          s += which ? v * v : v;
+        }
+        atomicAdd(&P.utt_stats[((size_t)utt * 2 + which) * kV2Mels + m], s);
+      }
+    }
+    __syncthreads();  // stage (Z) and planes (y) are rewritten by the next iteration
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// utterance CMVN from the fused statistics: x = (x - mean) / std, tile-parallel, float4
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cmvn_utt_apply_kernel(float* __restrict__ feats, const Tile* __restrict__ tiles, int n_tiles,
+                                                             const int64_t* __restrict__ frame_offsets,
+                                                             const double* __restrict__ utt_stats, int mean_norm, int std_norm) {
+  __shared__ float s_mean[kV2Mels], s_inv[kV2Mels];
+  for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+    const Tile tile = tiles[ti];
+    const int64_t fo = frame_offsets[tile.utt];
+    const int T = (int)(frame_offsets[tile.utt + 1] - fo);
+    const int nf = min(kTileFrames, T - tile.frame0);
+    if (threadIdx.x < kV2Mels) {
+      const double s1 = utt_stats[((size_t)tile.utt * 2) * kV2Mels + threadIdx.x];
+      const double s2 = utt_stats[((size_t)tile.utt * 2 + 1) * kV2Mels + threadIdx.x];
+      const double mean = s1 / T;
+      double var = s2 / T - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[threadIdx.x] = mean_norm ? (float)mean : 0.f;
+      s_inv[threadIdx.x] = std_norm ? (float)(1.0 / sqrt(var)) : 1.f;
+    }
+    __syncthreads();
+    float4* p = reinterpret_cast<float4*>(feats + (fo + tile.frame0) * (int64_t)kV2Mels);
+    for (int q = threadIdx.x; q < nf * (kV2Mels / 4); q += blockDim.x) {
+      const int m = 4 * (q % (kV2Mels / 4));
+      float4 v = p[q];
+      v.x = (v.x - s_mean[m]) * s_inv[m];
+      v.y = (v.y - s_mean[m + 1]) * s_inv[m + 1];
+      v.z = (v.z - s_mean[m + 2]) * s_inv[m + 2];
+      v.w = (v.w - s_mean[m + 3]) * s_inv[m + 3];
+      p[q] = v;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mafe

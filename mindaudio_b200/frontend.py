@@ -18,7 +18,8 @@ from ._engine import get_engine
 
 
 def conformer_plan(eng, sample_rate=16000, frame_len_ms=25, frame_shift_ms=10, mel_bin=80, n_fft=512, dither=0.0,
-                   seed=0, allow_fast_path=True, low_freq=20.0, high_freq=8000.0):
+                   seed=0, allow_fast_path=True, low_freq=20.0, high_freq=8000.0, utt_cmvn_mean=False,
+                   utt_cmvn_std=False):
     frame_len = sample_rate * frame_len_ms // 1000
     hop = sample_rate * frame_shift_ms // 1000
     if frame_len > n_fft:
@@ -28,7 +29,7 @@ def conformer_plan(eng, sample_rate=16000, frame_len_ms=25, frame_shift_ms=10, m
     return eng.plan(n_fft=n_fft, frame_len=frame_len, hop=hop, center=False, out_kind=L.OUT_LOGMEL,
                     window=T.povey_window(frame_len), preemph=0.97, remove_frame_mean=True, dither=dither,
                     dither_seed=seed, power=2.0, mel_fb=bank, log_kind=L.LOG_LN_EPS_IF_ZERO,
-                    allow_fast_path=allow_fast_path)
+                    utt_cmvn_mean=utt_cmvn_mean, utt_cmvn_std=utt_cmvn_std, allow_fast_path=allow_fast_path)
 
 
 def compute_fbank_feats(wav, sample_rate, frame_len, frame_shift, mel_bin, dither=0.0, seed=0, allow_fast_path=True):
@@ -55,12 +56,16 @@ class FbankPipeline:
     def __init__(self, sample_rate=16000, frame_len_ms=25, frame_shift_ms=10, mel_bin=80, n_fft=512, dither=0.0,
                  seed=0, cmvn="utt", mean_norm=True, std_norm=True, allow_fast_path=True, engine=None):
         self.eng = engine or get_engine()
-        self.plan = conformer_plan(self.eng, sample_rate, frame_len_ms, frame_shift_ms, mel_bin, n_fft, dither, seed,
-                                   allow_fast_path)
-        self.mel_bin = mel_bin
-        self.sample_rate = sample_rate
         assert cmvn in (None, "utt")
         self.cmvn, self.mean_norm, self.std_norm = cmvn, mean_norm, std_norm
+        fused = cmvn == "utt"
+        self.plan = conformer_plan(self.eng, sample_rate, frame_len_ms, frame_shift_ms, mel_bin, n_fft, dither, seed,
+                                   allow_fast_path, utt_cmvn_mean=fused and mean_norm, utt_cmvn_std=fused and std_norm)
+        # the un-normalised plan serves the global-CMVN statistics pass (compute_cmvn_stats.py works on raw fbank)
+        self.raw_plan = self.plan if not fused else conformer_plan(self.eng, sample_rate, frame_len_ms, frame_shift_ms,
+                                                                   mel_bin, n_fft, dither, seed, allow_fast_path)
+        self.mel_bin = mel_bin
+        self.sample_rate = sample_rate
 
     # ---- layout ----
     def layout(self, lengths):
@@ -74,18 +79,20 @@ class FbankPipeline:
         self.eng.set_stream(torch.cuda.current_stream().cuda_stream or 1)
 
     # ---- device-resident ----
-    def run(self, wave_ptr, batch, out_ptr, wave_dtype=L.WAVE_F32, wave_scale=1.0, stats_ptr=None):
-        """wave_ptr / out_ptr: device pointers (ints).  stats_ptr: optional device double[2*D+1]
-        receiving the global-CMVN sufficient statistics of the RAW (pre-utterance-CMVN) features."""
+    def run(self, wave_ptr, batch, out_ptr, wave_dtype=L.WAVE_F32, wave_scale=1.0):
+        """wave_ptr / out_ptr: device pointers (ints); fbank (+ fused utterance CMVN) of the whole batch."""
         eng, lib = self.eng, self.eng.lib
         L.check(lib.mafe_frontend_run(eng.ctx, self.plan.h, batch.h, C.c_void_p(wave_ptr), wave_dtype,
                                       float(wave_scale), C.c_void_p(out_ptr), L.DBGROUP_NONE))
-        if stats_ptr is not None:
-            L.check(lib.mafe_cmvn_stats_accumulate(eng.ctx, C.c_void_p(out_ptr), batch.total_frames, self.mel_bin,
-                                                   C.c_void_p(stats_ptr)))
-        if self.cmvn == "utt":
-            L.check(lib.mafe_cmvn_utt(eng.ctx, C.c_void_p(out_ptr), batch.frame_offsets_dev, batch.n_utts, self.mel_bin,
-                                      int(self.mean_norm), int(self.std_norm)))
+
+    def run_global_stats(self, wave_ptr, batch, out_ptr, stats_ptr, wave_dtype=L.WAVE_F32, wave_scale=1.0):
+        """Raw fbank into out_ptr and its global-CMVN sufficient statistics (sum x, sum x^2, N) ACCUMULATED into
+        the device double[2*D+1] at stats_ptr (examples/conformer/compute_cmvn_stats.py:45-65, 104-112)."""
+        eng, lib = self.eng, self.eng.lib
+        L.check(lib.mafe_frontend_run(eng.ctx, self.raw_plan.h, batch.h, C.c_void_p(wave_ptr), wave_dtype,
+                                      float(wave_scale), C.c_void_p(out_ptr), L.DBGROUP_NONE))
+        L.check(lib.mafe_cmvn_stats_accumulate(eng.ctx, C.c_void_p(out_ptr), batch.total_frames, self.mel_bin,
+                                               C.c_void_p(stats_ptr)))
 
     def __call__(self, wave, lengths=None, batch=None, out=None, wave_scale=1.0):
         """torch front door: ``wave`` flat CUDA tensor (float32 or int16)."""
