@@ -27,6 +27,9 @@ struct BakedWeights {  // kernel-parameter resident: c[0][..] operands
   float2 w[kBins];     // (w0, w1) of every FFT bin, pre-scaled by 1/4
 };
 
+struct SweepStep;
+struct SweepHdr;
+
 struct V2Params {
   const void* wave;
   int64_t total_samples;  // length of the flat waveform array (elements)
@@ -47,25 +50,54 @@ struct V2Params {
   const float2* w512;    // [256]
   const float2* w256t;   // [16][16]
   const int* combine;    // [80]
+  const SweepStep* sweep_steps;  // [2][8][kMaxSteps]
+  const SweepHdr* sweep_hdr;     // [8]
   float* out;
 };
+
+// table-driven sweep: one step per FFT bin of a (half, warp) range
+constexpr int kMaxSteps = 18;
+constexpr int kPlaneRows = kV2Mels + 2;  // filters -1 .. 80: guard rows take the out-of-range emits
+struct SweepStep {
+  float w0, w1;       // weights of filters cur / cur+1 (pre-scaled by 1/4)
+  uint32_t offs;      // byte offset of Z[k] (low 16 bits) and Z[512-k] (high 16 bits) inside the pair's slot
+  int nflush;         // filters to retire BEFORE this bin is accumulated
+};
+struct SweepHdr {
+  int lo;             // first filter the warp emits
+  int nsteps[2];      // bins of the even / odd half
+  int tail[2];        // filters still to retire after the last bin of the half
+  int pad[3];
+};
+
+struct TileInfo {  // geometry of one work item, prepared by thread 0 one iteration ahead
+  int64_t out_row;    // first output row (frame) of the tile
+  int64_t s0;         // first sample of the tile inside its utterance
+  int64_t cov_end, end_elem, base_elem;  // scalar patch-up range / element index of raw[0]
+  int utt, nf, shift;
+  float neg_mu;
+};
+static_assert(sizeof(TileInfo) <= 64, "TileInfo slot");
 
 struct V2Smem {
   static constexpr size_t kRaw0 = 0;
   static constexpr size_t kRaw1 = kV2RawBytes;
-  static constexpr size_t kY = 2 * kV2RawBytes;                          // float[5376]: pre-emphasised tile, then the mel planes
-  static constexpr size_t kYBytes = sizeof(float) * 5376;
+  static constexpr size_t kY = 2 * kV2RawBytes;                          // float[5440]: pre-emphasised tile, then the mel planes
+  static constexpr size_t kYBytes = sizeof(float) * 5440;
   static constexpr size_t kZ = kY + kYBytes;                             // float2[16][273], then the output staging
   static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
   static constexpr size_t kWin = kZ + kZBytes;                           // float[400]
   static constexpr size_t kW512 = kWin + sizeof(float) * 400;            // float2[256]
   static constexpr size_t kW256 = kW512 + sizeof(float2) * 256;          // float2[256]
   static constexpr size_t kBar = kW256 + sizeof(float2) * 256;           // 2 mbarriers
-  static constexpr size_t kTotal = kBar + 16;
+  static constexpr size_t kInfo = kBar + 16;                             // 2 x TileInfo
+  static constexpr size_t kSteps = kInfo + 2 * 64;                       // SweepStep[2][8][kMaxSteps]
+  static constexpr size_t kHdr = kSteps + sizeof(SweepStep) * 2 * kFastWarps * kMaxSteps;  // SweepHdr[8]
+  static constexpr size_t kTotal = kHdr + sizeof(SweepHdr) * kFastWarps;
 };
 static_assert(V2Smem::kZ % 16 == 0 && V2Smem::kBar % 8 == 0, "smem alignment");
-static_assert(2 * kV2Mels * kPlaneStride <= 5376, "mel planes must fit in the y buffer");
-static_assert(kTileFrames * kV2StageStride * 4 <= (int)V2Smem::kZBytes, "staging must fit in the Z buffer");
+static_assert(2 * kPlaneRows * kPlaneStride <= 5440, "mel planes must fit in the y buffer");
+static_assert((kTileFrames * kV2StageStride + 6 * kV2Mels) * 4 <= (int)V2Smem::kZBytes, "staging must fit in the Z buffer");
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy (SASS: SYNCS.*, UBLKCP)
@@ -175,7 +207,7 @@ __device__ __forceinline__ void sweep_warp(const float2* zp, float sgn, float* p
   constexpr int k_hi = WARP == kFastWarps - 1 ? kBins : 32 * WARP + 32;
   constexpr int lo = kF0[k_lo], hi = kF0[k_hi - 1] + 1;
   constexpr int kk_end = 16 * WARP + 16 + ((HALF == 0 && WARP == kFastWarps - 1) ? 1 : 0);
-  float* plane = planes + (WARP & 1) * (kV2Mels * kPlaneStride);
+  float* plane = planes + (WARP & 1) * (kPlaneRows * kPlaneStride);
   sweep_step<HALF, 16 * WARP, kk_end, lo, hi>(0.f, 0.f, zp, sgn, plane, lane, W);
 }
 
@@ -191,6 +223,33 @@ __device__ __forceinline__ void sweep_dispatch(int warp, const float2* zp, float
     case 5: sweep_warp<HALF, 5>(zp, sgn, planes, lane, W); break;
     case 6: sweep_warp<HALF, 6>(zp, sgn, planes, lane, W); break;
     default: sweep_warp<HALF, 7>(zp, sgn, planes, lane, W); break;
+  }
+}
+
+// Table-driven sweep (one copy of the code for every warp: it stays resident in the instruction cache).
+// Control flow depends only on the table, i.e. it is warp-uniform; the votes tell the compiler so.
+template <int HALF>
+__device__ __forceinline__ void sweep_table(const SweepStep* steps, int nsteps, int tail, const unsigned char* zp, float sgn,
+                                            float* dst) {
+  float acc_lo = 0.f, acc_hi = 0.f;
+  for (int s = 0; s < nsteps; ++s) {
+    const SweepStep st = steps[s];
+    int nf = st.nflush;
+    while (__any_sync(0xffffffffu, nf > 0)) {
+      if (HALF == 0) *dst = acc_lo; else *dst += acc_lo;
+      acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride; --nf;
+    }
+    const float2 zk = *reinterpret_cast<const float2*>(zp + (st.offs & 0xffffu));
+    const float2 zn = *reinterpret_cast<const float2*>(zp + (st.offs >> 16));
+    const float re = fmaf(sgn, zn.x, zk.x);
+    const float im = fmaf(-sgn, zn.y, zk.y);
+    const float pw = fmaf(re, re, im * im);
+    acc_lo = fmaf(st.w0, pw, acc_lo);
+    acc_hi = fmaf(st.w1, pw, acc_hi);
+  }
+  while (__any_sync(0xffffffffu, tail > 0)) {
+    if (HALF == 0) *dst = acc_lo; else *dst += acc_lo;
+    acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride; --tail;
   }
 }
 
@@ -228,7 +287,7 @@ __device__ __forceinline__ float raw_elem(const unsigned char* raw, int idx, flo
   return reinterpret_cast<const float*>(raw)[idx] * scale;
 }
 
-template <bool I16>
+template <bool I16, bool TABLE>
 __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V2Params P, const BakedWeights W) {
   extern __shared__ __align__(128) unsigned char smem[];
   auto raw_buf = [&](int b) -> unsigned char* { return smem + (size_t)b * kV2RawBytes; };
@@ -240,11 +299,16 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
   float2* s_w512 = reinterpret_cast<float2*>(smem + V2Smem::kW512);
   float2* s_w256 = reinterpret_cast<float2*>(smem + V2Smem::kW256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + V2Smem::kBar);
+  TileInfo* info = reinterpret_cast<TileInfo*>(smem + V2Smem::kInfo);
+  SweepStep* s_steps = reinterpret_cast<SweepStep*>(smem + V2Smem::kSteps);
+  SweepHdr* s_hdr = reinterpret_cast<SweepHdr*>(smem + V2Smem::kHdr);
   constexpr int ES = I16 ? 2 : 4;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kV2Flen; i += kFastThreads) s_win[i] = P.window[i];
   for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
+  for (int i = tid; i < 2 * kFastWarps * kMaxSteps; i += kFastThreads) s_steps[i] = P.sweep_steps[i];
+  if (tid < kFastWarps) s_hdr[tid] = P.sweep_hdr[tid];
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -252,93 +316,107 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
   }
   __syncthreads();
 
-  // prologue: fetch the first tile
-  int ti = blockIdx.x;
-  if (ti < P.n_tiles && tid == 0) {
-    const Tile tile = P.tiles[ti];
+  // Thread 0 prepares every work item ONE ITERATION AHEAD: it walks the tile -> utterance -> offsets
+  // chain in global memory, launches the TMA copy of the waveform bytes and leaves the geometry in shared
+  // memory, so the other threads never wait on a global load at the top of the loop.
+  auto prepare = [&](int tile_index, int slot) {
+    const Tile tile = P.tiles[tile_index];
     const int64_t off = P.sample_offsets[tile.utt];
-    const int T = (int)(P.frame_offsets[tile.utt + 1] - P.frame_offsets[tile.utt]);
+    const int64_t fo = P.frame_offsets[tile.utt];
+    const int T = (int)(P.frame_offsets[tile.utt + 1] - fo);
     const TileSrc<I16> src = tile_src<I16>(P, tile, off, T);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (src.bytes) {
-      mbar_expect_tx(&bars[0], src.bytes);
-      tma_bulk_g2s(raw_buf(0), (const unsigned char*)P.wave + src.ga_byte, src.bytes, &bars[0]);
+      mbar_expect_tx(&bars[slot], src.bytes);
+      tma_bulk_g2s(raw_buf(slot), (const unsigned char*)P.wave + src.ga_byte, src.bytes, &bars[slot]);
     } else {
-      mbar_arrive(&bars[0]);
+      mbar_arrive(&bars[slot]);
     }
-  }
+    TileInfo ti_;
+    ti_.out_row = fo + tile.frame0;
+    ti_.s0 = (int64_t)tile.frame0 * kV2Hop;
+    ti_.cov_end = src.cov_end;
+    ti_.end_elem = src.end_elem;
+    ti_.base_elem = src.ga_byte / ES;
+    ti_.utt = tile.utt;
+    ti_.nf = min(kTileFrames, T - tile.frame0);
+    ti_.shift = src.shift;
+    ti_.neg_mu = P.remove_mean ? -(float)(P.utt_sum[tile.utt] / ((double)T * (double)kV2Flen)) : 0.f;
+    info[slot] = ti_;
+  };
+
+  int ti = blockIdx.x;
+  if (ti < P.n_tiles && tid == 0) prepare(ti, 0);
+  __syncthreads();
 
   uint32_t phase0 = 0, phase1 = 0;
   int buf = 0;
   for (; ti < P.n_tiles; ti += gridDim.x, buf ^= 1) {
-    const Tile tile = P.tiles[ti];
-    const uint32_t utt = (uint32_t)tile.utt;
-    const int64_t off = P.sample_offsets[utt];
-    const int64_t fo = P.frame_offsets[utt];
-    const int T = (int)(P.frame_offsets[utt + 1] - fo);
-    const int frame0 = tile.frame0;
-    const int nf = min(kTileFrames, T - frame0);
-    const TileSrc<I16> src = tile_src<I16>(P, tile, off, T);
-
-    // prefetch the next tile of this CTA into the other buffer (free since the previous iteration's pass P)
-    const int tn = ti + gridDim.x;
-    if (tn < P.n_tiles && tid == 0) {
-      const Tile nt = P.tiles[tn];
-      const int64_t noff = P.sample_offsets[nt.utt];
-      const int nT = (int)(P.frame_offsets[nt.utt + 1] - P.frame_offsets[nt.utt]);
-      const TileSrc<I16> ns = tile_src<I16>(P, nt, noff, nT);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (ns.bytes) {
-        mbar_expect_tx(&bars[buf ^ 1], ns.bytes);
-        tma_bulk_g2s(raw_buf(buf ^ 1), (const unsigned char*)P.wave + ns.ga_byte, ns.bytes, &bars[buf ^ 1]);
-      } else {
-        mbar_arrive(&bars[buf ^ 1]);
-      }
-    }
+    // the other buffer is free since the previous iteration's pass P: prefetch the next tile into it
+    if (ti + (int)gridDim.x < P.n_tiles && tid == 0) prepare(ti + gridDim.x, buf ^ 1);
+    const TileInfo cur = info[buf];
+    const uint32_t utt = (uint32_t)cur.utt;
+    const int nf = cur.nf;
 
     // wait for this tile's bytes
     if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
     unsigned char* rb = raw_buf(buf);
     // scalar patch-up of what the 16 B-granular bulk copy could not cover (end of the flat array)
-    if (src.cov_end < src.end_elem) {
-      const int64_t base_elem = src.ga_byte / ES;
-      for (int64_t e = src.cov_end + tid; e < src.end_elem; e += kFastThreads) {
-        if (I16) reinterpret_cast<int16_t*>(rb)[e - base_elem] = ((const int16_t*)P.wave)[e];
-        else reinterpret_cast<float*>(rb)[e - base_elem] = ((const float*)P.wave)[e];
+    if (cur.cov_end < cur.end_elem) {
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
+        if (I16) reinterpret_cast<int16_t*>(rb)[e - cur.base_elem] = ((const int16_t*)P.wave)[e];
+        else reinterpret_cast<float*>(rb)[e - cur.base_elem] = ((const float*)P.wave)[e];
       }
       __syncthreads();
     }
 
     // ---- pass P: [dither] + pre-emphasis, raw -> ybuf (y[0] = x[0] at the start of an utterance) ----
     {
-      const int64_t s0 = (int64_t)frame0 * kV2Hop;
+      const int64_t s0 = cur.s0;
       const int need = (nf - 1) * kV2Hop + kV2Flen;
-      const int sh = src.shift + 1;  // raw index of sample s0
-      for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
-        float x[5];
+      const int sh = cur.shift + 1;  // raw index of sample s0
+      if (nf == kTileFrames && s0 > 0 && P.dither == 0.f && P.preemph_on) {
+        // interior tile: every sample and its predecessor exist -- no bounds logic
+        for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
+          const float x0 = raw_elem<I16>(rb, sh + i0 - 1, P.wave_scale);
+          const float x1 = raw_elem<I16>(rb, sh + i0, P.wave_scale);
+          const float x2 = raw_elem<I16>(rb, sh + i0 + 1, P.wave_scale);
+          const float x3 = raw_elem<I16>(rb, sh + i0 + 2, P.wave_scale);
+          const float x4 = raw_elem<I16>(rb, sh + i0 + 3, P.wave_scale);
+          float4 y;
+          y.x = fmaf(-P.pre_lo, x0, fmaf(-P.pre_hi, x0, x1));
+          y.y = fmaf(-P.pre_lo, x1, fmaf(-P.pre_hi, x1, x2));
+          y.z = fmaf(-P.pre_lo, x2, fmaf(-P.pre_hi, x2, x3));
+          y.w = fmaf(-P.pre_lo, x3, fmaf(-P.pre_hi, x3, x4));
+          *reinterpret_cast<float4*>(ybuf + i0) = y;
+        }
+      } else {
+        for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
+          float x[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int i = i0 - 1 + j;
-          float v = 0.f;
-          if (i < need && (i >= 0 || s0 > 0)) {
-            v = raw_elem<I16>(rb, sh + i, P.wave_scale);
-            if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)(s0 + i), utt, P.seed), v);
+          for (int j = 0; j < 5; ++j) {
+            const int i = i0 - 1 + j;
+            float v = 0.f;
+            if (i < need && (i >= 0 || s0 > 0)) {
+              v = raw_elem<I16>(rb, sh + i, P.wave_scale);
+              if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)(s0 + i), utt, P.seed), v);
+            }
+            x[j] = v;
           }
-          x[j] = v;
+          float4 y;
+          if (P.preemph_on) {
+            y.x = fmaf(-P.pre_lo, x[0], fmaf(-P.pre_hi, x[0], x[1]));
+            y.y = fmaf(-P.pre_lo, x[1], fmaf(-P.pre_hi, x[1], x[2]));
+            y.z = fmaf(-P.pre_lo, x[2], fmaf(-P.pre_hi, x[2], x[3]));
+            y.w = fmaf(-P.pre_lo, x[3], fmaf(-P.pre_hi, x[3], x[4]));
+          } else {
+            y = make_float4(x[1], x[2], x[3], x[4]);
+          }
+          *reinterpret_cast<float4*>(ybuf + i0) = y;
         }
-        float4 y;
-        if (P.preemph_on) {
-          y.x = fmaf(-P.pre_lo, x[0], fmaf(-P.pre_hi, x[0], x[1]));
-          y.y = fmaf(-P.pre_lo, x[1], fmaf(-P.pre_hi, x[1], x[2]));
-          y.z = fmaf(-P.pre_lo, x[2], fmaf(-P.pre_hi, x[2], x[3]));
-          y.w = fmaf(-P.pre_lo, x[3], fmaf(-P.pre_hi, x[3], x[4]));
-        } else {
-          y = make_float4(x[1], x[2], x[3], x[4]);
-        }
-        *reinterpret_cast<float4*>(ybuf + i0) = y;
       }
     }
-    float neg_mu = 0.f;
-    if (P.remove_mean) neg_mu = -(float)(P.utt_sum[utt] / ((double)T * (double)kV2Flen));
+    const float neg_mu = cur.neg_mu;
     __syncthreads();
 
     // ---- phase F: frame pair -> registers, window, mean removal, radix-2 fold ----
@@ -370,34 +448,47 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
 
     const float2* zp = Zs + (lane >> 1) * kSlotStride;
     const float sgn = (lane & 1) ? -1.f : 1.f;
+    const SweepHdr hdr = s_hdr[warp];
+    float* plane_dst = planes + (warp & 1) * (kPlaneRows * kPlaneStride) + (hdr.lo + 1) * kPlaneStride + lane;
     fft256_group(v0, slot, s_w256, t);
     __syncthreads();
-    sweep_dispatch<0>(warp, zp, sgn, planes, lane, W);
+    if (TABLE) sweep_table<0>(s_steps + warp * kMaxSteps, hdr.nsteps[0], hdr.tail[0], (const unsigned char*)zp, sgn, plane_dst);
+    else sweep_dispatch<0>(warp, zp, sgn, planes + kPlaneStride, lane, W);
     __syncthreads();
     fft256_group(v1, slot, s_w256, t);
     __syncthreads();
-    sweep_dispatch<1>(warp, zp, sgn, planes, lane, W);
+    if (TABLE) sweep_table<1>(s_steps + (kFastWarps + warp) * kMaxSteps, hdr.nsteps[1], hdr.tail[1], (const unsigned char*)zp, sgn, plane_dst);
+    else sweep_dispatch<1>(warp, zp, sgn, planes + kPlaneStride, lane, W);
     __syncthreads();
 
-    // ---- phase C1: combine the (<= 2) partial sums, log, stage [frame][80] ----
-    for (int e = tid; e < kTileFrames * kV2Mels; e += kFastThreads) {
-      const int f = e / kV2Mels, m = e - f * kV2Mels;  // lanes = filters: planes (stride 33) and stage both conflict-free
+    // ---- phase C1: combine the (<= 2) partial sums, log, stage [frame][80]; thread = (frame group g, filter m) ----
+    float* part = stage + kTileFrames * kV2StageStride;  // [3][2][80] per-group CMVN partial sums
+    if (tid < 3 * kV2Mels) {
+      const int g = tid / kV2Mels, m = tid - g * kV2Mels;
       const int c = P.combine[m];
       const int n = c & 3, p0 = (c >> 2) & 1;
-      float acc = 0.f;
-      if (n >= 1) acc = planes[p0 * (kV2Mels * kPlaneStride) + m * kPlaneStride + f];
-      if (n == 2) acc += planes[(p0 ^ 1) * (kV2Mels * kPlaneStride) + m * kPlaneStride + f];
-      float o;
-      if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) o = __logf(acc == 0.f ? 2.220446049250313e-16f : acc);
-      else if (P.log_kind == MAFE_LOG_LN_PLUS) o = __logf(acc + P.log_arg);
-      else o = acc;
-      stage[f * kV2StageStride + m] = o;
+      const float* pa = planes + p0 * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride;
+      const float* pb = planes + (p0 ^ 1) * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int f = g; f < kTileFrames; f += 3) {
+        float acc = n >= 1 ? pa[f] : 0.f;
+        if (n == 2) acc += pb[f];
+        float o;
+        if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) o = __logf(acc == 0.f ? 2.220446049250313e-16f : acc);
+        else if (P.log_kind == MAFE_LOG_LN_PLUS) o = __logf(acc + P.log_arg);
+        else o = acc;
+        stage[f * kV2StageStride + m] = o;
+        if (f < nf) { s1 += o; s2 = fmaf(o, o, s2); }
+      }
+      part[(g * 2) * kV2Mels + m] = s1;
+      part[(g * 2 + 1) * kV2Mels + m] = s2;
     }
     __syncthreads();
 
     // ---- phase C2: coalesced float4 stores + per-utterance CMVN statistics ----
     {
-      float4* dst = reinterpret_cast<float4*>(P.out + (fo + frame0) * (int64_t)kV2Mels);
+      float4* dst = reinterpret_cast<float4*>(P.out + cur.out_row * (int64_t)kV2Mels);
       const int total4 = nf * (kV2Mels / 4);
       for (int q = tid; q < total4; q += kFastThreads) {
         const int f = q / (kV2Mels / 4), m4 = q - f * (kV2Mels / 4);
@@ -405,15 +496,86 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
       }
       if (P.utt_stats != nullptr && tid < 2 * kV2Mels) {
         const int m = tid % kV2Mels, which = tid / kV2Mels;
-        double s = 0.0;
-        for (int f = 0; f < nf; ++f) {
-          const double v = (double)stage[f * kV2StageStride + m];
-          s += which ? v * v : v;
-        }
+        const double s = (double)part[which * kV2Mels + m] + (double)part[(2 + which) * kV2Mels + m] +
+                         (double)part[(4 + which) * kV2Mels + m];
         atomicAdd(&P.utt_stats[((size_t)utt * 2 + which) * kV2Mels + m], s);
       }
     }
     __syncthreads();  // stage (Z) and planes (y) are rewritten by the next iteration
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame-mean pre-pass for the baked geometry: sum over all windowed frame entries of an utterance
+//   = sum_s y[s] * c(s),  c(s) = sum of the window over the frames covering sample s.
+// Inside an utterance c(s) only depends on s mod hop (table cw[160]); only the first / last tile of an
+// utterance needs the general rule.  One CTA per tile, the tile owns hop*32 samples (+ the tail).
+// ---------------------------------------------------------------------------------------------
+template <bool I16>
+__device__ __forceinline__ float gload(const void* wave, int64_t g, float scale) {
+  if (I16) return (float)__ldg((const int16_t*)wave + g) * scale;
+  return __ldg((const float*)wave + g) * scale;
+}
+
+template <bool I16>
+__global__ void __launch_bounds__(256) frame_sum_baked_kernel(const V2Params P, const float* __restrict__ cw, double* utt_sum) {
+  __shared__ float s_cw[kV2Hop];
+  __shared__ double ws[8];
+  const int tid = threadIdx.x;
+  if (tid < kV2Hop) s_cw[tid] = cw[tid];
+  __syncthreads();
+  for (int ti = blockIdx.x; ti < P.n_tiles; ti += gridDim.x) {
+    const Tile tile = P.tiles[ti];
+    const uint32_t utt = (uint32_t)tile.utt;
+    const int64_t off = P.sample_offsets[utt];
+    const int T = (int)(P.frame_offsets[utt + 1] - P.frame_offsets[utt]);
+    const int64_t s_lo = (int64_t)tile.frame0 * kV2Hop;
+    float acc = 0.f;
+    if (tile.frame0 >= 2 && tile.frame0 + kTileFrames < T && P.dither == 0.f && P.preemph_on) {
+      // interior tile: 5120 owned samples, coverage = cw[s mod 160]
+      const int64_t g = off + s_lo;
+      int r = tid % kV2Hop;
+#pragma unroll 4
+      for (int i = tid; i < kTileFrames * kV2Hop; i += 256) {
+        const float x = gload<I16>(P.wave, g + i, P.wave_scale);
+        float xp = __shfl_up_sync(0xffffffffu, x, 1);
+        if ((tid & 31) == 0) xp = gload<I16>(P.wave, g + i - 1, P.wave_scale);
+        const float y = fmaf(-P.pre_lo, xp, fmaf(-P.pre_hi, xp, x));
+        acc = fmaf(y, s_cw[r], acc);
+        r += 256 - kV2Hop;           // (i + 256) mod 160
+        if (r >= kV2Hop) r -= kV2Hop;
+      }
+    } else {
+      const int64_t framed_end = (int64_t)(T - 1) * kV2Hop + kV2Flen;
+      const int64_t s_hi = tile.frame0 + kTileFrames >= T ? framed_end : s_lo + (int64_t)kTileFrames * kV2Hop;
+      for (int64_t s = s_lo + tid; s < s_hi; s += 256) {
+        float v = gload<I16>(P.wave, off + s, P.wave_scale);
+        if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)s, utt, P.seed), v);
+        if (P.preemph_on && s > 0) {
+          float vp = gload<I16>(P.wave, off + s - 1, P.wave_scale);
+          if (P.dither != 0.f) vp = fmaf(P.dither, dither_normal((uint64_t)(s - 1), utt, P.seed), vp);
+          v = fmaf(-P.pre_lo, vp, fmaf(-P.pre_hi, vp, v));
+        }
+        const int t_hi = (int)min((int64_t)T - 1, s / kV2Hop);
+        float c = 0.f;
+        for (int tt = t_hi; tt >= 0; --tt) {
+          const int64_t n = s - (int64_t)tt * kV2Hop;
+          if (n >= kV2Flen) break;
+          c += __ldg(&P.window[n]);
+        }
+        acc = fmaf(v, c, acc);
+      }
+    }
+    double d = (double)acc;
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((tid & 31) == 0) ws[tid >> 5] = d;
+    __syncthreads();
+    if (tid == 0) {
+      double t8 = 0.0;
+      for (int w = 0; w < 8; ++w) t8 += ws[w];
+      atomicAdd(&utt_sum[utt], t8);
+    }
+    __syncthreads();
   }
 }
 
