@@ -185,6 +185,17 @@ const int64_t* mafe_batch_frame_offsets_dev(const mafe_batch* batch);
 int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, const void* wave_dev, int32_t wave_dtype,
                       float wave_scale, float* out_dev, int32_t db_group);
 
+/*
+ * The same path with HOST buffers (what a numpy / data-loader caller has): wave_host is the flat waveform
+ * in host memory (pinned memory makes the copies asynchronous), out_host receives [total_frames][out_dim].
+ * Utterances are processed in chunks of chunk_utts (<= 0: 512) on three internal streams, so the H2D copy of
+ * chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap.  Synchronous: returns when out_host
+ * is complete.  frame_offsets_host_out: int64[n_utts+1] or NULL.  db_group: MAFE_DBGROUP_NONE / _UTT only.
+ */
+int mafe_frontend_run_host(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
+                           const void* wave_host, int32_t wave_dtype, float wave_scale, float* out_host,
+                           int64_t* frame_offsets_host_out, int32_t chunk_utts, int32_t db_group);
+
 /* ---- spectral element-wise ops on device arrays ---- */
 /* spectrum.magphase iscomplex=True (spectrum.py:720-732): n complex64 -> mag^power, unit phase (0 -> 1+0j). */
 int mafe_magphase(mafe_ctx* ctx, const float* z_dev, int64_t n, float power, float* mag_dev, float* phase_dev);

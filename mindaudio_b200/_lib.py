@@ -75,6 +75,7 @@ _PROTOS = {
     "mafe_batch_frame_offsets": (C.c_int, [_P, _P]),
     "mafe_batch_frame_offsets_dev": (_P, [_P]),
     "mafe_frontend_run": (C.c_int, [_P, _P, _P, _P, _I32, _F, _P, _I32]),
+    "mafe_frontend_run_host": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _F, _P, _P, _I32, _I32]),
     "mafe_magphase": (C.c_int, [_P, _P, _I64, _F, _P, _P]),
     "mafe_amplitude_to_db": (C.c_int, [_P, _P, _P, _I64, _I64, _F, _F, _F, _F]),
     "mafe_db_to_amplitude": (C.c_int, [_P, _P, _P, _I64, _F, _F]),

@@ -70,6 +70,12 @@ int mafe_ctx_destroy(mafe_ctx* ctx) {
   if (!ctx) return MAFE_OK;
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& l : ctx->lanes) {
+    if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+    cudaFree(l.wave_dev);
+    cudaFree(l.out_dev);
+    mafe_batch_destroy(l.batch);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return MAFE_OK;
@@ -245,6 +251,76 @@ int32_t mafe_plan_out_dim(const mafe_plan* p) { return p ? p->out_dim : 0; }
 int32_t mafe_plan_is_fast(const mafe_plan* p) { return p && p->fast ? 1 : 0; }
 
 // ---------------------------------------------------------------- ragged batch layout
+}  // extern "C"
+
+// grow-only device array
+template <typename T>
+static cudaError_t ensure_cap(T** p, size_t* cap, size_t need) {
+  if (need <= *cap && *p) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  size_t n = std::max<size_t>(need + need / 4, 16);
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  *cap = e == cudaSuccess ? n : 0;
+  return e;
+}
+
+extern "C" {
+
+// (Re)fill a batch object: host layout (frame offsets, tile table) + upload on ctx->stream.  Offsets are
+// rebased by `rebase` (the chunked host path uploads one chunk of the flat array at a time).  The device
+// arrays only grow, so a batch can be refilled per chunk without any cudaMalloc/cudaFree.
+static int batch_fill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* b, const int64_t* so, int32_t n_utts,
+                      const int32_t* utt_group, int64_t rebase) {
+  b->n_utts = n_utts;
+  b->frame_offsets_host.assign((size_t)n_utts + 1, 0);
+  b->so_host.resize((size_t)n_utts + 1);
+  b->tiles_host.clear();
+  const int tf = plan->tile_frames;
+  int32_t max_group = -1;
+  b->so_host[0] = n_utts ? so[0] - rebase : 0;
+  for (int32_t u = 0; u < n_utts; ++u) {
+    int64_t len = so[u + 1] - so[u];
+    MAFE_REQUIRE(len >= 0, "sample_offsets must be non-decreasing (utt %d)", u);
+    b->so_host[u + 1] = so[u + 1] - rebase;
+    int64_t t = mafe_plan_num_frames(plan, len);
+    MAFE_REQUIRE(t <= INT32_MAX - tf, "utterance %d has too many frames", u);
+    b->frame_offsets_host[u + 1] = b->frame_offsets_host[u] + t;
+    for (int64_t f0 = 0; f0 < t; f0 += tf) b->tiles_host.push_back(Tile{u, (int32_t)f0});
+    if (utt_group) max_group = std::max(max_group, utt_group[u]);
+  }
+  b->total_frames = b->frame_offsets_host[n_utts];
+  b->total_samples = n_utts ? so[n_utts] - so[0] : 0;
+  b->wave_len = n_utts ? so[n_utts] - rebase : 0;
+  b->n_tiles = (int32_t)b->tiles_host.size();
+  b->n_groups = utt_group ? max_group + 1 : std::max(n_utts, 1);
+  cudaStream_t st = ctx->stream;
+  const size_t no = (size_t)n_utts + 1;
+  MAFE_CUDA_CHECK(ensure_cap(&b->sample_offsets_dev, &b->cap_offsets, no));
+  MAFE_CUDA_CHECK(ensure_cap(&b->frame_offsets_dev, &b->cap_foffsets, no));
+  MAFE_CUDA_CHECK(ensure_cap(&b->tiles_dev, &b->cap_tiles, b->tiles_host.size()));
+  MAFE_CUDA_CHECK(ensure_cap(&b->utt_sum_dev, &b->cap_utt_sum, (size_t)std::max(n_utts, 1)));
+  MAFE_CUDA_CHECK(ensure_cap(&b->group_max_dev, &b->cap_groups, (size_t)std::max(b->n_groups, 1)));
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(b->sample_offsets_dev, b->so_host.data(), no * 8, cudaMemcpyHostToDevice, st));
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(b->frame_offsets_dev, b->frame_offsets_host.data(), no * 8, cudaMemcpyHostToDevice, st));
+  if (!b->tiles_host.empty())
+    MAFE_CUDA_CHECK(cudaMemcpyAsync(b->tiles_dev, b->tiles_host.data(), b->tiles_host.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+  if (utt_group && n_utts) {
+    MAFE_CUDA_CHECK(ensure_cap(&b->utt_group_dev, &b->cap_utt_group, (size_t)n_utts));
+    MAFE_CUDA_CHECK(cudaMemcpyAsync(b->utt_group_dev, utt_group, (size_t)n_utts * 4, cudaMemcpyHostToDevice, st));
+  } else if (!utt_group && b->utt_group_dev) {
+    cudaFree(b->utt_group_dev); b->utt_group_dev = nullptr; b->cap_utt_group = 0;
+  }
+  if ((plan->d.utt_cmvn_mean || plan->d.utt_cmvn_std) && n_utts > 0)
+    MAFE_CUDA_CHECK(ensure_cap(&b->utt_stats_dev, &b->cap_utt_stats, (size_t)n_utts * 2 * plan->out_dim));
+  if (plan->d.out_kind == MAFE_OUT_MFCC && b->total_frames > 0) {
+    MAFE_CUDA_CHECK(ensure_cap(&b->scratch_dev, &b->cap_scratch, (size_t)b->total_frames * plan->d.n_mels));
+    b->scratch_bytes = b->cap_scratch * sizeof(float);
+  }
+  // pageable sources: cudaMemcpyAsync has staged them before returning, the host vectors may be reused
+  return MAFE_OK;
+}
+
 int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, int32_t n_utts, const int32_t* utt_group,
                       mafe_batch** out) {
   MAFE_REQUIRE(ctx && plan && out && (so || n_utts == 0), "mafe_batch_create: NULL argument");
@@ -253,62 +329,9 @@ int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, i
   mafe_batch* b = new (std::nothrow) mafe_batch();
   if (!b) { set_error("out of host memory"); return MAFE_E_OOM; }
   b->device = ctx->device;
-  b->n_utts = n_utts;
-  b->frame_offsets_host.assign((size_t)n_utts + 1, 0);
-  std::vector<Tile> tiles;
-  const int tf = plan->tile_frames;
-  int32_t max_group = -1;
-  for (int32_t u = 0; u < n_utts; ++u) {
-    int64_t len = so[u + 1] - so[u];
-    if (len < 0) { delete b; set_error("sample_offsets must be non-decreasing (utt %d)", u); return MAFE_E_INVALID_ARG; }
-    int64_t t = mafe_plan_num_frames(plan, len);
-    if (t > INT32_MAX - tf) { delete b; set_error("utterance %d has too many frames", u); return MAFE_E_INVALID_ARG; }
-    b->frame_offsets_host[u + 1] = b->frame_offsets_host[u] + t;
-    for (int64_t f0 = 0; f0 < t; f0 += tf) tiles.push_back(Tile{u, (int32_t)f0});
-    if (utt_group) max_group = std::max(max_group, utt_group[u]);
-  }
-  b->total_frames = b->frame_offsets_host[n_utts];
-  b->total_samples = n_utts ? so[n_utts] - so[0] : 0;
-  b->wave_len = n_utts ? so[n_utts] : 0;
-  b->n_tiles = (int32_t)tiles.size();
-  b->n_groups = utt_group ? max_group + 1 : std::max(n_utts, 1);
-  cudaStream_t st = ctx->stream;
-  auto fail = [&](cudaError_t e) {
-    set_error("mafe_batch_create: %s", cudaGetErrorString(e));
-    mafe_batch_destroy(b);
-    return e == cudaErrorMemoryAllocation ? MAFE_E_OOM : MAFE_E_CUDA;
-  };
-  cudaError_t e;
-  size_t no = (size_t)n_utts + 1;
-  if ((e = cudaMalloc((void**)&b->sample_offsets_dev, no * 8)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void**)&b->frame_offsets_dev, no * 8)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void**)&b->tiles_dev, std::max<size_t>(tiles.size(), 1) * sizeof(Tile))) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void**)&b->utt_sum_dev, std::max<size_t>(n_utts, 1) * 8)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void**)&b->group_max_dev, (size_t)std::max(b->n_groups, 1) * 4)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc((void**)&b->work_counter_dev, 64)) != cudaSuccess) return fail(e);
-  // offsets relative to so[0] are NOT rebased: wave_dev must point at sample 0 of the flat array
-  if (n_utts) {
-    if ((e = cudaMemcpyAsync(b->sample_offsets_dev, so, no * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
-  } else {
-    int64_t z = 0;
-    if ((e = cudaMemcpyAsync(b->sample_offsets_dev, &z, 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
-  }
-  if ((e = cudaMemcpyAsync(b->frame_offsets_dev, b->frame_offsets_host.data(), no * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
-  if (!tiles.empty())
-    if ((e = cudaMemcpyAsync(b->tiles_dev, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
-  if (utt_group && n_utts) {
-    if ((e = cudaMalloc((void**)&b->utt_group_dev, (size_t)n_utts * 4)) != cudaSuccess) return fail(e);
-    if ((e = cudaMemcpyAsync(b->utt_group_dev, utt_group, (size_t)n_utts * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
-  }
-  if ((plan->d.utt_cmvn_mean || plan->d.utt_cmvn_std) && n_utts > 0) {
-    if ((e = cudaMalloc((void**)&b->utt_stats_dev, (size_t)n_utts * 2 * plan->out_dim * sizeof(double))) != cudaSuccess) return fail(e);
-  }
-  if (plan->d.out_kind == MAFE_OUT_MFCC && b->total_frames > 0) {
-    b->scratch_bytes = (size_t)b->total_frames * plan->d.n_mels * sizeof(float);
-    if ((e = cudaMalloc((void**)&b->scratch_dev, b->scratch_bytes)) != cudaSuccess) return fail(e);
-  }
-  // the tile vector is pageable host memory: make sure the copies have consumed it before returning
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e);
+  // offsets are NOT rebased: wave_dev must point at sample 0 of the flat array
+  int rc = batch_fill(ctx, plan, b, so, n_utts, utt_group, 0);
+  if (rc != MAFE_OK) { mafe_batch_destroy(b); return rc; }
   *out = b;
   return MAFE_OK;
 }
@@ -323,7 +346,6 @@ int mafe_batch_destroy(mafe_batch* b) {
   cudaFree(b->utt_sum_dev);
   cudaFree(b->group_max_dev);
   cudaFree(b->scratch_dev);
-  cudaFree(b->work_counter_dev);
   cudaFree(b->utt_stats_dev);
   delete b;
   return MAFE_OK;
@@ -368,6 +390,65 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   if (cmvn)
     return mafe_cmvn_utt(ctx, out_dev, batch->frame_offsets_dev, batch->n_utts, plan->out_dim, d.utt_cmvn_mean, d.utt_cmvn_std);
   return MAFE_OK;
+}
+
+// ---------------------------------------------------------------- host-to-host hot path
+int mafe_frontend_run_host(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, int32_t n_utts, const void* wave_host,
+                           int32_t wave_dtype, float wave_scale, float* out_host, int64_t* frame_offsets_out,
+                           int32_t chunk_utts, int32_t db_group) {
+  MAFE_REQUIRE(ctx && plan && (so || n_utts == 0), "mafe_frontend_run_host: NULL argument");
+  MAFE_REQUIRE(wave_dtype == MAFE_WAVE_F32 || wave_dtype == MAFE_WAVE_I16, "bad wave_dtype %d", wave_dtype);
+  MAFE_REQUIRE(db_group == MAFE_DBGROUP_NONE || db_group == MAFE_DBGROUP_UTT,
+               "the chunked host path supports per-utterance dB groups only (a batch-wide floor couples chunks)");
+  DeviceGuard g(ctx->device);
+  const size_t es = wave_dtype == MAFE_WAVE_I16 ? 2 : 4;
+  if (chunk_utts <= 0) chunk_utts = 512;
+  if (ctx->lanes.empty()) {
+    ctx->lanes.resize(3);
+    for (auto& l : ctx->lanes) MAFE_CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+  }
+  std::vector<int64_t> fo((size_t)n_utts + 1, 0);
+  for (int32_t u = 0; u < n_utts; ++u) fo[u + 1] = fo[u] + mafe_plan_num_frames(plan, so[u + 1] - so[u]);
+  if (frame_offsets_out) memcpy(frame_offsets_out, fo.data(), fo.size() * sizeof(int64_t));
+  cudaStream_t saved = ctx->stream;
+  int rc = MAFE_OK;
+  int c = 0;
+  for (int32_t u0 = 0; u0 < n_utts && rc == MAFE_OK; u0 += chunk_utts, ++c) {
+    const int32_t u1 = std::min(n_utts, u0 + chunk_utts);
+    mafe_lane& l = ctx->lanes[c % ctx->lanes.size()];
+    ctx->stream = l.stream;
+    const int64_t s_begin = so[u0], n_samp = so[u1] - so[u0];
+    const int64_t n_frames = fo[u1] - fo[u0];
+    if (n_frames == 0) continue;
+    // stream order protects the lane's buffers: the previous chunk of this lane has been enqueued before
+    if (!l.batch) { l.batch = new (std::nothrow) mafe_batch(); l.batch->device = ctx->device; }
+    cudaError_t e;
+    if ((size_t)n_samp * es + 64 > l.wave_cap) {
+      cudaStreamSynchronize(l.stream);
+      cudaFree(l.wave_dev);
+      l.wave_cap = ((size_t)n_samp * es + 64) * 5 / 4;
+      if ((e = cudaMalloc(&l.wave_dev, l.wave_cap)) != cudaSuccess) { set_error("cudaMalloc: %s", cudaGetErrorString(e)); rc = MAFE_E_OOM; break; }
+    }
+    const size_t out_bytes = (size_t)n_frames * plan->out_dim * sizeof(float);
+    if (out_bytes > l.out_cap) {
+      cudaStreamSynchronize(l.stream);
+      cudaFree(l.out_dev);
+      l.out_cap = out_bytes * 5 / 4;
+      if ((e = cudaMalloc((void**)&l.out_dev, l.out_cap)) != cudaSuccess) { set_error("cudaMalloc: %s", cudaGetErrorString(e)); rc = MAFE_E_OOM; break; }
+    }
+    if ((rc = batch_fill(ctx, plan, l.batch, so + u0, u1 - u0, nullptr, s_begin)) != MAFE_OK) break;
+    e = cudaMemcpyAsync(l.wave_dev, (const char*)wave_host + (size_t)s_begin * es, (size_t)n_samp * es, cudaMemcpyHostToDevice, l.stream);
+    if (e != cudaSuccess) { set_error("H2D: %s", cudaGetErrorString(e)); rc = MAFE_E_CUDA; break; }
+    if ((rc = mafe_frontend_run(ctx, plan, l.batch, l.wave_dev, wave_dtype, wave_scale, l.out_dev, db_group)) != MAFE_OK) break;
+    e = cudaMemcpyAsync(out_host + (size_t)fo[u0] * plan->out_dim, l.out_dev, out_bytes, cudaMemcpyDeviceToHost, l.stream);
+    if (e != cudaSuccess) { set_error("D2H: %s", cudaGetErrorString(e)); rc = MAFE_E_CUDA; break; }
+  }
+  ctx->stream = saved;
+  for (auto& l : ctx->lanes) {
+    cudaError_t e = cudaStreamSynchronize(l.stream);
+    if (e != cudaSuccess && rc == MAFE_OK) { set_error("lane sync: %s", cudaGetErrorString(e)); rc = MAFE_E_CUDA; }
+  }
+  return rc;
 }
 
 }  // extern "C"

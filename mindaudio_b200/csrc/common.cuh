@@ -56,6 +56,16 @@ struct mafe_prof_pending {
   cudaEvent_t e0, e1;
 };
 
+struct mafe_batch;
+struct mafe_lane {  // one lane of the pipelined host path: stream + grow-only device buffers
+  cudaStream_t stream = nullptr;
+  void* wave_dev = nullptr;
+  size_t wave_cap = 0;
+  float* out_dev = nullptr;
+  size_t out_cap = 0;
+  mafe_batch* batch = nullptr;
+};
+
 struct mafe_ctx {
   int device = 0;
   int sm_count = 0;
@@ -66,6 +76,7 @@ struct mafe_ctx {
   double prof_ms[MAFE_PROF_COUNT] = {0, 0, 0, 0};
   int64_t prof_n[MAFE_PROF_COUNT] = {0, 0, 0, 0};
   std::vector<mafe_prof_pending> prof_pending;
+  std::vector<mafe_lane> lanes;
 };
 
 namespace mafe {
@@ -119,6 +130,10 @@ struct mafe_batch {
   int32_t n_tiles = 0;
   int32_t n_groups = 0;
   std::vector<int64_t> frame_offsets_host;
+  std::vector<int64_t> so_host;
+  std::vector<mafe::Tile> tiles_host;
+  size_t cap_offsets = 0, cap_foffsets = 0, cap_tiles = 0, cap_utt_sum = 0, cap_groups = 0, cap_utt_group = 0,
+         cap_utt_stats = 0, cap_scratch = 0;
   int64_t* sample_offsets_dev = nullptr;  // [n_utts+1]
   int64_t* frame_offsets_dev = nullptr;   // [n_utts+1]
   mafe::Tile* tiles_dev = nullptr;        // [n_tiles]
@@ -127,7 +142,6 @@ struct mafe_batch {
   int32_t* group_max_dev = nullptr;       // [max(n_utts,1)] ordered-int keys of the dB maxima
   float* scratch_dev = nullptr;           // MFCC intermediate [total_frames][n_mels]
   size_t scratch_bytes = 0;
-  int32_t* work_counter_dev = nullptr;    // persistent-kernel tile counter
   double* utt_stats_dev = nullptr;        // [n_utts][2][dim] fused utterance-CMVN statistics
 };
 

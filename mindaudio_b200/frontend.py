@@ -114,11 +114,28 @@ class FbankPipeline:
                 batch.close()
 
     # ---- host to host (the end-to-end path) ----
-    def run_host(self, wave_host_ptr, wave_nbytes, batch, out_host_ptr, dev_wave_ptr, dev_out_ptr,
-                 wave_dtype=L.WAVE_F32, wave_scale=1.0):
-        """Pinned host waveform -> H2D -> kernels -> D2H of the features, all on the engine stream."""
-        eng, lib = self.eng, self.eng.lib
-        L.check(lib.mafe_memcpy_h2d(eng.ctx, C.c_void_p(dev_wave_ptr), C.c_void_p(wave_host_ptr), wave_nbytes))
-        self.run(dev_wave_ptr, batch, dev_out_ptr, wave_dtype, wave_scale)
-        L.check(lib.mafe_memcpy_d2h(eng.ctx, C.c_void_p(out_host_ptr), C.c_void_p(dev_out_ptr),
-                                    4 * batch.total_frames * self.mel_bin))
+    def run_host(self, wave_host_ptr, sample_offsets, out_host_ptr, wave_dtype=L.WAVE_F32, wave_scale=1.0, chunk_utts=512):
+        """Waveforms in (pinned) host memory -> features in host memory through ``mafe_frontend_run_host``:
+        chunks of ``chunk_utts`` utterances on three streams, so H2D, kernels and D2H overlap.  Synchronous.
+        ``sample_offsets``: int64 ``[n_utts + 1]`` into the flat host waveform.  Returns the frame offsets."""
+        so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+        fo = np.empty(len(so), dtype=np.int64)
+        eng = self.eng
+        L.check(eng.lib.mafe_frontend_run_host(eng.ctx, self.plan.h, so.ctypes.data_as(C.c_void_p), len(so) - 1,
+                                               C.c_void_p(wave_host_ptr), wave_dtype, float(wave_scale),
+                                               C.c_void_p(out_host_ptr), fo.ctypes.data_as(C.c_void_p), int(chunk_utts),
+                                               L.DBGROUP_NONE))
+        return fo
+
+    def features(self, waves, wave_scale=1.0, chunk_utts=512):
+        """numpy front door: list of 1-D waveforms (float32 or int16) -> (flat features, frame offsets)."""
+        lens = [len(w) for w in waves]
+        dt = np.int16 if all(np.asarray(w).dtype == np.int16 for w in waves) else np.float32
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=dt) for w in waves])) if waves else np.zeros(0, dt)
+        so = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=so[1:])
+        total = sum(self.plan.num_frames(n) for n in lens)
+        out = np.empty((total, self.mel_bin), dtype=np.float32)
+        fo = self.run_host(flat.ctypes.data, so, out.ctypes.data, L.WAVE_I16 if dt == np.int16 else L.WAVE_F32,
+                           wave_scale, chunk_utts)
+        return out, fo

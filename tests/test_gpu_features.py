@@ -174,6 +174,34 @@ def test_pipeline_with_utt_cmvn_matches_reference_chain(ma):
     out = out.cpu().numpy()
     fo = batch.frame_offsets
     for u, w in enumerate(waves):
-        ref = R.utt_cmvn(R.conformer_fbank(w.astype(np.float64)))
-        assert mixed_err(out[fo[u]:fo[u + 1]], ref) <= 2e-4
+        raw = R.conformer_fbank(w.astype(np.float64))
+        assert logmel_err(out[fo[u]:fo[u + 1]] * raw.std(axis=0) + raw.mean(axis=0), raw) <= 2.0
+        assert mixed_err(out[fo[u]:fo[u + 1]], R.utt_cmvn(raw)) <= 1e-3
     batch.close()
+
+
+def test_host_pipeline_chunked_matches_oracle(ma):
+    """mafe_frontend_run_host: chunked H2D / kernels / D2H on three streams (ragged, chunk boundaries, int16)."""
+    rng = np.random.default_rng(9)
+    lens = [int(v) for v in rng.integers(400, 60000, size=23)] + [399, 0, 400]
+    waves = [np.round(synth(300 + i, (n,)) * 32768).astype(np.float32) for i, n in enumerate(lens)]
+    for cmvn in (None, "utt"):
+        pipe = ma.FbankPipeline(cmvn=cmvn)
+        out, fo = pipe.features(waves, chunk_utts=4)
+        assert fo[-1] == out.shape[0]
+        for u, w in enumerate(waves):
+            ref = R.conformer_fbank(w.astype(np.float64)) if len(w) else np.zeros((0, 80))
+            got = out[fo[u]:fo[u + 1]]
+            assert got.shape == ref.shape
+            if cmvn and ref.shape[0] > 1:
+                # CMVN divides by the per-bin std: judge the DE-normalised features with the log-mel criterion
+                # (factor 2: the statistics carry the same FP32 rounding as the features)
+                assert logmel_err(got * ref.std(axis=0) + ref.mean(axis=0), ref) <= 2.0, u
+            elif not cmvn:
+                assert logmel_err(got, ref) <= 1.0, u
+        out16, fo16 = pipe.features([w.astype(np.int16) for w in waves], chunk_utts=7)
+        assert np.array_equal(fo16, fo)
+        if cmvn is None:
+            assert np.array_equal(out16, out)                     # PCM16 staging is lossless for integer samples
+        else:
+            assert np.allclose(out16, out, atol=1e-5, equal_nan=True)   # chunking changes the atomic summation order
