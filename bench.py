@@ -248,13 +248,15 @@ def main():
     achieved_tflops = FLOP_PER_FRAME * n_frames / k_avg_s / 1e12
     # roofline = the slower of bytes at the measured HBM bandwidth and flops at the FP32 peak
     t_hbm = BYTES_PER_FRAME * n_frames / (hbm_peak * 1e9)
-    t_fp32 = FLOP_PER_FRAME * n_frames / (FP32_PEAK_NOMINAL_TFLOPS * 1e12)
+    fp32_peak = eng.fp32_fma_peak()          # measured on this box, this run (FFMA microbenchmark in libmafe)
+    t_fp32 = FLOP_PER_FRAME * n_frames / (fp32_peak * 1e12)
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "fbank512_baked_kernel",
                 "kernel_ms": k_avg_s * 1e3, "frames_per_launch": int(n_frames),
-                "fp32": {"achieved_tflops": achieved_tflops, "nominal_peak_tflops": FP32_PEAK_NOMINAL_TFLOPS,
-                         "frac_of_nominal": achieved_tflops / FP32_PEAK_NOMINAL_TFLOPS,
-                         "note": "FP32 FMA peak is nominal (148 SM x 128 lanes x 2 x 1.965 GHz), not in MEASURED_PEAKS.json"},
+                "fp32": {"achieved_tflops": achieved_tflops, "measured_peak_tflops": fp32_peak,
+                         "nominal_peak_tflops": FP32_PEAK_NOMINAL_TFLOPS, "frac_of_measured": achieved_tflops / fp32_peak,
+                         "note": "FP32 FMA peak measured in this run by mafe_fp32_fma_peak (not in MEASURED_PEAKS.json); "
+                                 "algorithmic flops = 14 253 per frame (SURVEY.md 8d)"},
                 "frac_of_min_roofline": max(t_hbm, t_fp32) / k_avg_s,
                 "step_share": {"fbank512_baked_kernel_ms": k_ms / max(k_n, 1), "frame_mean_prepass_ms": p_ms / max(p_n, 1),
                                "cmvn_ms": c_ms / max(c_n, 1), "step_ms": ms / args.steps}}

@@ -142,6 +142,10 @@ int mafe_ctx_profile_enable(mafe_ctx* ctx, int32_t enable);
 int mafe_ctx_profile_read(mafe_ctx* ctx, int32_t which, double* ms_out, int64_t* launches_out);
 int mafe_ctx_profile_reset(mafe_ctx* ctx);
 
+/* FP32 FMA peak of the device (TFLOP/s) from a register-resident FFMA microbenchmark: the denominator of the
+ * compute roofline of the fbank path (SURVEY.md section 8d asks for it to be measured, not assumed). */
+int mafe_fp32_fma_peak(mafe_ctx* ctx, double* tflops_out);
+
 /* ---- memory plumbing for numpy callers (no torch needed) ---- */
 int mafe_device_malloc(mafe_ctx* ctx, size_t bytes, void** out_dev);
 int mafe_device_free(mafe_ctx* ctx, void* dev);

@@ -73,6 +73,12 @@ class Engine:
         L.check(self.lib.mafe_ctx_profile_read(self.ctx, which, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def fp32_fma_peak(self):
+        """Measured FP32 FMA peak of this GPU in TFLOP/s (register-resident FFMA microbenchmark)."""
+        v = C.c_double()
+        L.check(self.lib.mafe_fp32_fma_peak(self.ctx, C.byref(v)))
+        return v.value
+
     def buf(self, name, nbytes):
         """Grow-only named device buffer (numpy API calls are synchronous, so reuse is safe)."""
         cur = self._bufs.get(name)

@@ -56,6 +56,7 @@ _PROTOS = {
     "mafe_ctx_profile_enable": (C.c_int, [_P, _I32]),
     "mafe_ctx_profile_read": (C.c_int, [_P, _I32, C.POINTER(C.c_double), C.POINTER(_I64)]),
     "mafe_ctx_profile_reset": (C.c_int, [_P]),
+    "mafe_fp32_fma_peak": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "mafe_device_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "mafe_device_free": (C.c_int, [_P, _P]),
     "mafe_pinned_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),

@@ -272,6 +272,22 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------ FP32 FMA peak microbenchmark
+// 16 independent FFMA chains per thread: the roofline denominator SURVEY.md section 8d asks to measure.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
+}
+
 }  // namespace mafe
 
 using namespace mafe;
@@ -410,6 +426,35 @@ int mafe_transpose(mafe_ctx* ctx, const float* in, float* out, int32_t n_mats, i
   MAFE_REQUIRE(out_mat_stride >= (int64_t)rows * cols, "out_mat_stride too small");
   transpose_kernel<<<grid, block, 0, ctx->stream>>>(in, out, rows, cols, out_mat_stride);
   MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_fp32_fma_peak(mafe_ctx* ctx, double* tflops_out) {
+  MAFE_REQUIRE(ctx && tflops_out, "mafe_fp32_fma_peak: NULL argument");
+  cudaSetDevice(ctx->device);
+  float* d = nullptr;
+  MAFE_CUDA_CHECK(cudaMalloc((void**)&d, 16));
+  const int iters = 4096, blocks = ctx->sm_count * 16;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    fma_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 16.0 * iters * 256.0 * blocks;
+    if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  ctx->launches += 5;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  MAFE_CUDA_CHECK(cudaGetLastError());
+  *tflops_out = best;
   return MAFE_OK;
 }
 
