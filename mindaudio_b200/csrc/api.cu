@@ -301,6 +301,7 @@ static int batch_fill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* b, const
   MAFE_CUDA_CHECK(ensure_cap(&b->tiles_dev, &b->cap_tiles, b->tiles_host.size()));
   MAFE_CUDA_CHECK(ensure_cap(&b->utt_sum_dev, &b->cap_utt_sum, (size_t)std::max(n_utts, 1)));
   MAFE_CUDA_CHECK(ensure_cap(&b->group_max_dev, &b->cap_groups, (size_t)std::max(b->n_groups, 1)));
+  if (!b->queue_dev) MAFE_CUDA_CHECK(cudaMalloc((void**)&b->queue_dev, 64));
   MAFE_CUDA_CHECK(cudaMemcpyAsync(b->sample_offsets_dev, b->so_host.data(), no * 8, cudaMemcpyHostToDevice, st));
   MAFE_CUDA_CHECK(cudaMemcpyAsync(b->frame_offsets_dev, b->frame_offsets_host.data(), no * 8, cudaMemcpyHostToDevice, st));
   if (!b->tiles_host.empty())
@@ -347,6 +348,7 @@ int mafe_batch_destroy(mafe_batch* b) {
   cudaFree(b->group_max_dev);
   cudaFree(b->scratch_dev);
   cudaFree(b->utt_stats_dev);
+  cudaFree(b->queue_dev);
   delete b;
   return MAFE_OK;
 }

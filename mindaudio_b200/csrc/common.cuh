@@ -143,6 +143,7 @@ struct mafe_batch {
   float* scratch_dev = nullptr;           // MFCC intermediate [total_frames][n_mels]
   size_t scratch_bytes = 0;
   double* utt_stats_dev = nullptr;        // [n_utts][2][dim] fused utterance-CMVN statistics
+  int32_t* queue_dev = nullptr;           // persistent-kernel work queue head (1 int)
 };
 
 namespace mafe {

@@ -516,10 +516,12 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     // A/B switch (measured on B200, 8192-utterance chunk: straight-line 9.21 ms, table-driven 9.98 ms)
     static const bool straight = getenv("MAFE_SWEEP_TABLE") == nullptr;
     Q.out = out;
+    Q.queue_head = b->queue_dev;
+    MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
     if (d.remove_frame_mean) {
       MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
       ProfScope ps(ctx, MAFE_PROF_FRAME_MEAN);
-      const int pgrid = std::min(b->n_tiles, 16 * ctx->sm_count);
+      const int pgrid = b->n_tiles;  // one CTA per tile: the hardware keeps 8 CTAs per SM in flight (more loads in flight)
       if (wave_dtype == MAFE_WAVE_I16)
         frame_sum_baked_kernel<true><<<pgrid, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
       else

@@ -53,6 +53,7 @@ struct V2Params {
   const SweepStep* sweep_steps;  // [2][8][kMaxSteps]
   const SweepHdr* sweep_hdr;     // [8]
   float* out;
+  int* queue_head;               // dynamic work queue: next unclaimed tile index
 };
 
 // table-driven sweep: one step per FFT bin of a (half, warp) range
@@ -90,7 +91,7 @@ struct V2Smem {
   static constexpr size_t kW512 = kWin + sizeof(float) * 400;            // float2[256]
   static constexpr size_t kW256 = kW512 + sizeof(float2) * 256;          // float2[256]
   static constexpr size_t kBar = kW256 + sizeof(float2) * 256;           // 2 mbarriers
-  static constexpr size_t kInfo = kBar + 16;                             // 2 x TileInfo
+  static constexpr size_t kInfo = kBar + 32;                             // (2 mbarriers + 2 claimed indices), 2 x TileInfo
   static constexpr size_t kSteps = kInfo + 2 * 64;                       // SweepStep[2][8][kMaxSteps]
   static constexpr size_t kHdr = kSteps + sizeof(SweepStep) * 2 * kFastWarps * kMaxSteps;  // SweepHdr[8]
   static constexpr size_t kTotal = kHdr + sizeof(SweepHdr) * kFastWarps;
@@ -316,15 +317,18 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
   }
   __syncthreads();
 
-  // Thread 0 prepares every work item ONE ITERATION AHEAD: it walks the tile -> utterance -> offsets
-  // chain in global memory, launches the TMA copy of the waveform bytes and leaves the geometry in shared
-  // memory, so the other threads never wait on a global load at the top of the loop.
-  auto prepare = [&](int tile_index, int slot) {
-    const Tile tile = P.tiles[tile_index];
-    const int64_t off = P.sample_offsets[tile.utt];
-    const int64_t fo = P.frame_offsets[tile.utt];
-    const int T = (int)(P.frame_offsets[tile.utt + 1] - fo);
-    const TileSrc<I16> src = tile_src<I16>(P, tile, off, T);
+  // Thread 0 prepares every work item ONE ITERATION AHEAD, and it does so in STAGES spread over the
+  // iteration: each stage only issues loads whose results are consumed after a later barrier, so the chain
+  // claim (atomicAdd) -> tile -> offsets/mean -> TMA never stalls warp 0 (and with it the whole CTA).
+  // Tiles are claimed from a global counter: uneven tiles (utterance tails) balance by themselves.
+  int* s_work = reinterpret_cast<int*>(smem + V2Smem::kBar) + 4;  // [2] claimed tile index per buffer
+  int nx_w = P.n_tiles;          // stage registers: only meaningful in thread 0
+  Tile nx_tile = {0, 0};
+  int64_t nx_off = 0, nx_fo0 = 0, nx_fo1 = 0;
+  double nx_sum = 0.0;
+  auto issue_tile = [&](int slot) {   // final stage: geometry + TMA for the tile claimed as nx_w
+    const int T = (int)(nx_fo1 - nx_fo0);
+    const TileSrc<I16> src = tile_src<I16>(P, nx_tile, nx_off, T);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (src.bytes) {
       mbar_expect_tx(&bars[slot], src.bytes);
@@ -333,27 +337,36 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
       mbar_arrive(&bars[slot]);
     }
     TileInfo ti_;
-    ti_.out_row = fo + tile.frame0;
-    ti_.s0 = (int64_t)tile.frame0 * kV2Hop;
+    ti_.out_row = nx_fo0 + nx_tile.frame0;
+    ti_.s0 = (int64_t)nx_tile.frame0 * kV2Hop;
     ti_.cov_end = src.cov_end;
     ti_.end_elem = src.end_elem;
     ti_.base_elem = src.ga_byte / ES;
-    ti_.utt = tile.utt;
-    ti_.nf = min(kTileFrames, T - tile.frame0);
+    ti_.utt = nx_tile.utt;
+    ti_.nf = min(kTileFrames, T - nx_tile.frame0);
     ti_.shift = src.shift;
-    ti_.neg_mu = P.remove_mean ? -(float)(P.utt_sum[tile.utt] / ((double)T * (double)kV2Flen)) : 0.f;
+    ti_.neg_mu = P.remove_mean ? -(float)(nx_sum / ((double)T * (double)kV2Flen)) : 0.f;
     info[slot] = ti_;
   };
+  auto load_offsets = [&]() {
+    nx_off = P.sample_offsets[nx_tile.utt];
+    nx_fo0 = P.frame_offsets[nx_tile.utt];
+    nx_fo1 = P.frame_offsets[nx_tile.utt + 1];
+    if (P.remove_mean) nx_sum = P.utt_sum[nx_tile.utt];
+  };
 
-  int ti = blockIdx.x;
-  if (ti < P.n_tiles && tid == 0) prepare(ti, 0);
+  if (tid == 0) {   // prologue: the first tile, all stages back to back
+    nx_w = atomicAdd(P.queue_head, 1);
+    s_work[0] = nx_w;
+    if (nx_w < P.n_tiles) { nx_tile = P.tiles[nx_w]; load_offsets(); issue_tile(0); }
+  }
   __syncthreads();
 
   uint32_t phase0 = 0, phase1 = 0;
   int buf = 0;
-  for (; ti < P.n_tiles; ti += gridDim.x, buf ^= 1) {
-    // the other buffer is free since the previous iteration's pass P: prefetch the next tile into it
-    if (ti + (int)gridDim.x < P.n_tiles && tid == 0) prepare(ti + gridDim.x, buf ^ 1);
+  for (;; buf ^= 1) {
+    if (s_work[buf] >= P.n_tiles) break;
+    if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1 (issue): claim the next tile
     const TileInfo cur = info[buf];
     const uint32_t utt = (uint32_t)cur.utt;
     const int nf = cur.nf;
@@ -418,6 +431,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     }
     const float neg_mu = cur.neg_mu;
     __syncthreads();
+    if (tid == 0) {   // stage 2: the claim has arrived during pass P -> publish it, fetch the tile record
+      s_work[buf ^ 1] = nx_w;
+      if (nx_w < P.n_tiles) nx_tile = P.tiles[nx_w];
+    }
 
     // ---- phase F: frame pair -> registers, window, mean removal, radix-2 fold ----
     const int t = lane & 15;
@@ -445,6 +462,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
       }
     }
     __syncthreads();  // ybuf is dead: it becomes the mel planes
+    if (tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3: offsets + frame-mean sum of the next tile's utterance
 
     const float2* zp = Zs + (lane >> 1) * kSlotStride;
     const float sgn = (lane & 1) ? -1.f : 1.f;
@@ -452,6 +470,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     float* plane_dst = planes + (warp & 1) * (kPlaneRows * kPlaneStride) + (hdr.lo + 1) * kPlaneStride + lane;
     fft256_group(v0, slot, s_w256, t);
     __syncthreads();
+    // stage 4: everything has arrived during the FFT -> geometry into shared memory, TMA into the other raw
+    // buffer (free since the previous tile's pass P); it lands while the rest of this tile is computed
+    if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
     if (TABLE) sweep_table<0>(s_steps + warp * kMaxSteps, hdr.nsteps[0], hdr.tail[0], (const unsigned char*)zp, sgn, plane_dst);
     else sweep_dispatch<0>(warp, zp, sgn, planes + kPlaneStride, lane, W);
     __syncthreads();
