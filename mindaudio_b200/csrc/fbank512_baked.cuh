@@ -83,8 +83,8 @@ static_assert(sizeof(TileInfo) <= 64, "TileInfo slot");
 struct V2Smem {
   static constexpr size_t kRaw0 = 0;
   static constexpr size_t kRaw1 = kV2RawBytes;
-  static constexpr size_t kY = 2 * kV2RawBytes;                          // float[5440]: pre-emphasised tile, then the mel planes
-  static constexpr size_t kYBytes = sizeof(float) * 5440;
+  static constexpr size_t kY = 2 * kV2RawBytes;                          // float[5472]: pre-emphasised tile, then the mel planes + zero row
+  static constexpr size_t kYBytes = sizeof(float) * 5472;
   static constexpr size_t kZ = kY + kYBytes;                             // float2[16][273], then the output staging
   static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
   static constexpr size_t kWin = kZ + kZBytes;                           // float[400]
@@ -97,7 +97,7 @@ struct V2Smem {
   static constexpr size_t kTotal = kHdr + sizeof(SweepHdr) * kFastWarps;
 };
 static_assert(V2Smem::kZ % 16 == 0 && V2Smem::kBar % 8 == 0, "smem alignment");
-static_assert(2 * kPlaneRows * kPlaneStride <= 5440, "mel planes must fit in the y buffer");
+static_assert(2 * kPlaneRows * kPlaneStride + kPlaneStride <= 5472, "mel planes + zero row must fit in the y buffer");
 static_assert((kTileFrames * kV2StageStride + 6 * kV2Mels) * 4 <= (int)V2Smem::kZBytes, "staging must fit in the Z buffer");
 
 // ---------------------------------------------------------------------------------------------
@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
       const int need = (nf - 1) * kV2Hop + kV2Flen;
       const int sh = cur.shift + 1;  // raw index of sample s0
       if (nf == kTileFrames && s0 > 0 && P.dither == 0.f && P.preemph_on) {
-        // interior tile: every sample and its predecessor exist -- no bounds logic
+        // interior tile: every sample and its predecessor exist -- no bounds logic (unrolled: all loads in flight)
+#pragma unroll
         for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
           const float x0 = raw_elem<I16>(rb, sh + i0 - 1, P.wave_scale);
           const float x1 = raw_elem<I16>(rb, sh + i0, P.wave_scale);
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     }
     __syncthreads();  // ybuf is dead: it becomes the mel planes
     if (tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3: offsets + frame-mean sum of the next tile's utterance
+    if (tid >= kFastThreads - 32) planes[2 * kPlaneRows * kPlaneStride + lane] = 0.f;   // the all-zero row (see phase C1)
 
     const float2* zp = Zs + (lane >> 1) * kSlotStride;
     const float sgn = (lane & 1) ? -1.f : 1.f;
@@ -483,25 +485,31 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     __syncthreads();
 
     // ---- phase C1: combine the (<= 2) partial sums, log, stage [frame][80]; thread = (frame group g, filter m) ----
+    // Branch-free: a filter with fewer than 2 contributing warps reads the all-zero row instead of a plane row.
     float* part = stage + kTileFrames * kV2StageStride;  // [3][2][80] per-group CMVN partial sums
     if (tid < 3 * kV2Mels) {
       const int g = tid / kV2Mels, m = tid - g * kV2Mels;
       const int c = P.combine[m];
       const int n = c & 3, p0 = (c >> 2) & 1;
-      const float* pa = planes + p0 * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride;
-      const float* pb = planes + (p0 ^ 1) * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride;
+      const float* zero_row = planes + 2 * kPlaneRows * kPlaneStride;
+      const float* pa = n >= 1 ? planes + p0 * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
+      const float* pb = n == 2 ? planes + (p0 ^ 1) * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
       float s1 = 0.f, s2 = 0.f;
+      auto body = [&](auto log_fn) {
 #pragma unroll
-      for (int f = g; f < kTileFrames; f += 3) {
-        float acc = n >= 1 ? pa[f] : 0.f;
-        if (n == 2) acc += pb[f];
-        float o;
-        if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) o = __logf(acc == 0.f ? 2.220446049250313e-16f : acc);
-        else if (P.log_kind == MAFE_LOG_LN_PLUS) o = __logf(acc + P.log_arg);
-        else o = acc;
-        stage[f * kV2StageStride + m] = o;
-        if (f < nf) { s1 += o; s2 = fmaf(o, o, s2); }
-      }
+        for (int f = g; f < kTileFrames; f += 3) {
+          const float o = log_fn(pa[f] + pb[f]);
+          stage[f * kV2StageStride + m] = o;
+          const float ov = f < nf ? o : 0.f;
+          s1 += ov;
+          s2 = fmaf(ov, ov, s2);
+        }
+      };
+      // ln x = lg2 x * ln 2 with the raw MUFU (mel energies are never subnormal: 0 is replaced by DBL_EPSILON)
+      auto fast_ln = [](float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.69314718055994530942f; };
+      if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) body([&](float a) { return fast_ln(a == 0.f ? 2.220446049250313e-16f : a); });
+      else if (P.log_kind == MAFE_LOG_LN_PLUS) body([&](float a) { return fast_ln(a + P.log_arg); });
+      else body([](float a) { return a; });
       part[(g * 2) * kV2Mels + m] = s1;
       part[(g * 2 + 1) * kV2Mels + m] = s2;
     }
