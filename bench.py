@@ -250,8 +250,17 @@ def main():
     t_hbm = BYTES_PER_FRAME * n_frames / (hbm_peak * 1e9)
     fp32_peak = eng.fp32_fma_peak()          # measured on this box, this run (FFMA microbenchmark in libmafe)
     t_fp32 = FLOP_PER_FRAME * n_frames / (fp32_peak * 1e12)
+    # DRAM traffic of one launch from the committed `ncu --set full` capture of this very workload (profiles/)
+    traffic, traffic_src = None, None
+    tp = os.path.join(REPO, "profiles", "r01_fbank512_traffic.json")
+    if os.path.isfile(tp):
+        with open(tp) as fh:
+            td = json.load(fh)
+        if int(td.get("frames_per_launch", -1)) == int(n_frames):
+            traffic, traffic_src = td["traffic_bytes_per_launch"], "profiles/r01_fbank512_traffic.json (dram__bytes_read+write)"
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "fbank512_baked_kernel",
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_FRAME * n_frames,
+                "peak_source": peak_src, "kernel": "fbank512_baked_kernel",
                 "kernel_ms": k_avg_s * 1e3, "frames_per_launch": int(n_frames),
                 "fp32": {"achieved_tflops": achieved_tflops, "measured_peak_tflops": fp32_peak,
                          "nominal_peak_tflops": FP32_PEAK_NOMINAL_TFLOPS, "frac_of_measured": achieved_tflops / fp32_peak,
