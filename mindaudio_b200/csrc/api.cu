@@ -216,7 +216,7 @@ int mafe_plan_create(mafe_ctx* ctx, const mafe_frontend_desc* d, mafe_plan** out
     rc = fast_plan_init(ctx, p, d);
     if (rc == MAFE_OK) {
       p->fast = true;
-      p->tile_frames = fast_tile_frames();
+      p->tile_frames = fast_tile_frames();   // a multiple of the generic kernel's tile: it sub-tiles via gridDim.y
     }
   }
   // host table pointers are not retained
@@ -376,8 +376,11 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   const mafe_frontend_desc& d = plan->d;
   const bool cmvn = d.utt_cmvn_mean || d.utt_cmvn_std;
   MAFE_REQUIRE(!(cmvn && d.out_kind == MAFE_OUT_COMPLEX), "utterance CMVN needs a real-valued output kind");
-  if (plan->fast) return fast_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev);  // CMVN fused inside
   int rc;
+  if (plan->fast) {
+    rc = fast_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev);  // CMVN fused inside
+    if (rc != MAFE_E_UNSUPPORTED) return rc;   // e.g. int16 / unaligned input to the STFT kernel: generic route below
+  }
   if (d.out_kind == MAFE_OUT_MFCC) {
     rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, batch->scratch_dev, MAFE_OUT_LOGMEL, db_group);
     if (rc) return rc;

@@ -161,6 +161,7 @@ bool fast_plan_supported(const mafe_frontend_desc* desc);
 int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* desc);
 void fast_plan_free(mafe_plan* p);
 int fast_tile_frames();
+// returns MAFE_E_UNSUPPORTED (without setting an error) when this call must take the generic route instead
 int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale,
              float* out);
 }  // namespace mafe

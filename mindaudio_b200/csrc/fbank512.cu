@@ -319,9 +319,14 @@ __global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, doubl
 #include "fbank512_baked.cuh"
 namespace mafe {
 
+}  // namespace mafe
+#include "stft512.cuh"
+namespace mafe {
+
 struct FastTablesHost {
   FastTablesDev dev;
   int ylen;
+  bool stft = false;      // n_fft = 512 complex STFT plan (stft512_kernel)
   bool baked = false;     // the plan is exactly the conformer configuration the baked kernel was generated for
   BakedWeights weights;   // (w0, w1) per bin for the baked kernel's parameter bank
   SweepStep* steps_dev = nullptr;
@@ -379,7 +384,13 @@ static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector
   return true;
 }
 
+static bool stft_plan_supported(const mafe_frontend_desc* d) {
+  return d->n_fft == kNfft && d->frame_len == kNfft && d->out_kind == MAFE_OUT_COMPLEX && d->hop >= 1 && d->hop <= kStftMaxHop &&
+         d->preemph == 0.0 && !d->remove_frame_mean && d->dither == 0.f && d->spec_scale == 1.0f;
+}
+
 bool fast_plan_supported(const mafe_frontend_desc* d) {
+  if (stft_plan_supported(d)) return true;
   if (d->n_fft != kNfft || d->center || d->out_kind != MAFE_OUT_LOGMEL || d->power != 2.0f || d->spec_scale != 1.0f)
     return false;
   if (!(d->log_kind == MAFE_LOG_LN_EPS_IF_ZERO || d->log_kind == MAFE_LOG_LN_PLUS || d->log_kind == MAFE_LOG_NONE)) return false;
@@ -406,8 +417,9 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
   memset(&th->dev, 0, sizeof(th->dev));
   th->ylen = (kTileFrames - 1) * d->hop + d->frame_len;
   p->fast_tables = th;
+  th->stft = stft_plan_supported(d);
   std::vector<float> win(kNfft, 0.f);
-  for (int i = 0; i < d->frame_len; ++i) win[i] = d->window[i];
+  for (int i = 0; i < d->frame_len; ++i) win[i] = th->stft ? 0.5f * d->window[i] : d->window[i];
   std::vector<float2> w512(256), w256(256);
   for (int n = 0; n < 256; ++n) {
     double a = -2.0 * M_PI * n / 512.0;
@@ -418,6 +430,14 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       double a = -2.0 * M_PI * (double)(t * kj) / 256.0;
       w256[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
     }
+  int rc;
+  if (th->stft) {
+    if ((rc = up(&th->dev.window, win))) return rc;
+    if ((rc = up(&th->dev.w512, w512))) return rc;
+    if ((rc = up(&th->dev.w256t, w256))) return rc;
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftSmem::kTotal));
+    return MAFE_OK;
+  }
   std::vector<BinEntry> bins;
   std::vector<int2> ranges;
   std::vector<int> comb;
@@ -425,7 +445,6 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     set_error("filterbank is not in per-bin form");
     return MAFE_E_UNSUPPORTED;
   }
-  int rc;
   if ((rc = up(&th->dev.window, win))) return rc;
   if ((rc = up(&th->dev.w512, w512))) return rc;
   if ((rc = up(&th->dev.w256t, w256))) return rc;
@@ -492,6 +511,20 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
   if (b->n_tiles == 0) return MAFE_OK;
   const FastTablesHost* th = static_cast<const FastTablesHost*>(p->fast_tables);
   const mafe_frontend_desc& d = p->d;
+  if (th->stft) {
+    if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
+    StftParams S;
+    S.wave = (const float*)wave; S.total_samples = b->wave_len;
+    S.sample_offsets = b->sample_offsets_dev; S.frame_offsets = b->frame_offsets_dev; S.tiles = b->tiles_dev;
+    S.n_tiles = b->n_tiles; S.hop = d.hop; S.center = d.center; S.pad_mode = d.pad_mode;
+    S.window = th->dev.window; S.w512 = th->dev.w512; S.w256t = th->dev.w256t;
+    S.out = out; S.queue_head = b->queue_dev;
+    MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
+    ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+    stft512_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, StftSmem::kTotal, ctx->stream>>>(S);
+    MAFE_LAUNCH_CHECK(ctx);
+    return MAFE_OK;
+  }
   FastParams P;
   P.wave = wave; P.wave_dtype = wave_dtype; P.wave_scale = wave_scale;
   P.sample_offsets = b->sample_offsets_dev; P.frame_offsets = b->frame_offsets_dev; P.tiles = b->tiles_dev;

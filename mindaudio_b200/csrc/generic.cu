@@ -116,12 +116,14 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   float2* cur = smem;
   float2* nxt = smem + (size_t)pairs * N;
 
-  const Tile tile = P.tiles[blockIdx.x];
+  Tile tile = P.tiles[blockIdx.x];
+  tile.frame0 += blockIdx.y * 2 * pairs;   // batch tiles may be larger than this kernel's 2*pairs frames (gridDim.y sub-tiles)
   const uint32_t utt = (uint32_t)tile.utt;
   const int64_t off = P.sample_offsets[utt];
   const int64_t L = P.sample_offsets[utt + 1] - off;
   const int64_t fo = P.frame_offsets[utt];
   const int64_t T = P.frame_offsets[utt + 1] - fo;
+  if (tile.frame0 >= T) return;
   float mu = 0.0f;
   if (P.remove_mean) mu = (float)(P.utt_sum[utt] / ((double)T * (double)P.frame_len));
 
@@ -387,7 +389,8 @@ int generic_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wa
     MAFE_LAUNCH_CHECK(ctx);
   }
   ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-  generic_frontend_kernel<<<b->n_tiles, kGenericThreads, p->smem_bytes, ctx->stream>>>(P);
+  const int sub = (p->tile_frames + 2 * p->pairs_per_tile - 1) / (2 * p->pairs_per_tile);
+  generic_frontend_kernel<<<dim3(b->n_tiles, sub), kGenericThreads, p->smem_bytes, ctx->stream>>>(P);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }
