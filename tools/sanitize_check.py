@@ -1,0 +1,19 @@
+import numpy as np, sys
+sys.path.insert(0, '.')
+import mindaudio_b200 as ma
+from oracle import restated as R
+from tests.util import synth
+rng = np.random.default_rng(1)
+lens = [16000, 5361, 400, 399, 0, 561, 30000, 5120 + 400]
+waves = [np.round(synth(50 + i, (n,)) * 32768).astype(np.float32) for i, n in enumerate(lens)]
+for cmvn in (None, "utt"):
+    pipe = ma.FbankPipeline(cmvn=cmvn)
+    out, fo = pipe.features(waves, chunk_utts=3)
+    out16, _ = pipe.features([w.astype(np.int16) for w in waves], chunk_utts=5)
+x = synth(2, (3, 9000))
+for kw in (dict(n_fft=512, hop_length=256), dict(n_fft=512, hop_length=128, pad_mode="reflect"), dict(n_fft=512, hop_length=200, center=False)):
+    s = ma.stft(x, **kw); r = R.stft(x, **kw)
+    assert np.abs(s - r).max() / np.abs(r).max() < 1e-5
+f = ma.fbank(x[0], n_mels=80, n_fft=400, hop_length=160)
+m = ma.mfcc(x)
+print("sanitize script ok")
