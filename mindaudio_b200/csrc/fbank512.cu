@@ -554,11 +554,19 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     if (d.remove_frame_mean) {
       MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
       ProfScope ps(ctx, MAFE_PROF_FRAME_MEAN);
-      const int pgrid = b->n_tiles;  // one CTA per tile: the hardware keeps 8 CTAs per SM in flight (more loads in flight)
-      if (wave_dtype == MAFE_WAVE_I16)
-        frame_sum_baked_kernel<true><<<pgrid, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
-      else
-        frame_sum_baked_kernel<false><<<pgrid, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
+      if (b->n_utts >= 4 * ctx->sm_count) {
+        // enough utterances to fill the machine: one CTA streams one utterance (no per-tile latency chain)
+        if (wave_dtype == MAFE_WAVE_I16)
+          frame_sum_utt_kernel<true><<<b->n_utts, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
+        else
+          frame_sum_utt_kernel<false><<<b->n_utts, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
+      } else {
+        const int pgrid = b->n_tiles;  // one CTA per tile
+        if (wave_dtype == MAFE_WAVE_I16)
+          frame_sum_baked_kernel<true><<<pgrid, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
+        else
+          frame_sum_baked_kernel<false><<<pgrid, 256, 0, ctx->stream>>>(Q, th->dev.cover, b->utt_sum_dev);
+      }
       MAFE_LAUNCH_CHECK(ctx);
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));

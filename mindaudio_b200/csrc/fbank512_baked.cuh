@@ -608,6 +608,68 @@ __global__ void __launch_bounds__(256) frame_sum_baked_kernel(const V2Params P, 
   }
 }
 
+// Same sum with ONE CTA PER UTTERANCE (used when the batch has enough utterances to fill the machine): each CTA
+// streams its whole utterance with deep load pipelining and issues a single atomic-free store.
+template <bool I16>
+__global__ void __launch_bounds__(256) frame_sum_utt_kernel(const V2Params P, const float* __restrict__ cw, double* utt_sum) {
+  __shared__ float s_cw[kV2Hop];
+  __shared__ double ws[8];
+  const int tid = threadIdx.x;
+  if (tid < kV2Hop) s_cw[tid] = cw[tid];
+  __syncthreads();
+  const uint32_t utt = blockIdx.x;
+  const int64_t off = P.sample_offsets[utt];
+  const int T = (int)(P.frame_offsets[utt + 1] - P.frame_offsets[utt]);
+  if (T <= 0) { if (tid == 0) utt_sum[utt] = 0.0; return; }
+  const int64_t framed_end = (int64_t)(T - 1) * kV2Hop + kV2Flen;
+  // interior [320, T*160): every sample is covered by frames q, q-1, (q-2) that all exist -> c = cw[s mod 160]
+  const int64_t in_lo = 2 * kV2Hop, in_hi = (int64_t)T * kV2Hop;
+  float acc = 0.f;
+  auto general = [&](int64_t s) {
+    float v = gload<I16>(P.wave, off + s, P.wave_scale);
+    if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)s, utt, P.seed), v);
+    if (P.preemph_on && s > 0) {
+      float vp = gload<I16>(P.wave, off + s - 1, P.wave_scale);
+      if (P.dither != 0.f) vp = fmaf(P.dither, dither_normal((uint64_t)(s - 1), utt, P.seed), vp);
+      v = fmaf(-P.pre_lo, vp, fmaf(-P.pre_hi, vp, v));
+    }
+    const int t_hi = (int)min((int64_t)T - 1, s / kV2Hop);
+    float c = 0.f;
+    for (int tt = t_hi; tt >= 0; --tt) {
+      const int64_t n = s - (int64_t)tt * kV2Hop;
+      if (n >= kV2Flen) break;
+      c += __ldg(&P.window[n]);
+    }
+    acc = fmaf(v, c, acc);
+  };
+  if (P.dither == 0.f && P.preemph_on && in_hi > in_lo) {
+    for (int64_t s = tid; s < in_lo; s += 256) general(s);
+    for (int64_t s = in_hi + tid; s < framed_end; s += 256) general(s);
+    int r = (int)((in_lo + tid) % kV2Hop);
+    const int64_t g = off;
+#pragma unroll 8
+    for (int64_t s = in_lo + tid; s < in_hi; s += 256) {
+      const float x = gload<I16>(P.wave, g + s, P.wave_scale);
+      float xp = __shfl_up_sync(0xffffffffu, x, 1);
+      if ((tid & 31) == 0) xp = gload<I16>(P.wave, g + s - 1, P.wave_scale);
+      acc = fmaf(fmaf(-P.pre_lo, xp, fmaf(-P.pre_hi, xp, x)), s_cw[r], acc);
+      r += 256 - kV2Hop;
+      if (r >= kV2Hop) r -= kV2Hop;
+    }
+  } else {
+    for (int64_t s = tid; s < framed_end; s += 256) general(s);
+  }
+  double d = (double)acc;
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if ((tid & 31) == 0) ws[tid >> 5] = d;
+  __syncthreads();
+  if (tid == 0) {
+    double t8 = 0.0;
+    for (int w = 0; w < 8; ++w) t8 += ws[w];
+    utt_sum[utt] = t8;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // utterance CMVN from the fused statistics: x = (x - mean) / std, tile-parallel, float4
 // ---------------------------------------------------------------------------------------------

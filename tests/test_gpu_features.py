@@ -205,3 +205,20 @@ def test_host_pipeline_chunked_matches_oracle(ma):
             assert np.array_equal(out16, out)                     # PCM16 staging is lossless for integer samples
         else:
             assert np.allclose(out16, out, atol=1e-5, equal_nan=True)   # chunking changes the atomic summation order
+
+
+def test_many_utterances_take_the_per_utterance_prepass(ma):
+    """>= 4 x SM-count utterances: the frame-mean pre-pass runs one CTA per utterance (frame_sum_utt_kernel)."""
+    rng = np.random.default_rng(21)
+    n = 640
+    lens = [int(v) for v in rng.integers(400, 6000, size=n)]
+    lens[5], lens[17], lens[100] = 399, 0, 52000
+    waves = [np.round(synth(1000 + i, (m,)) * 32768).astype(np.float32) for i, m in enumerate(lens)]
+    pipe = ma.FbankPipeline(cmvn=None)
+    out, fo = pipe.features(waves, chunk_utts=n)      # one chunk: all utterances in one batch
+    for u in list(range(0, n, 37)) + [5, 17, 100, n - 1]:
+        w = waves[u]
+        ref = R.conformer_fbank(w.astype(np.float64)) if len(w) else np.zeros((0, 80))
+        got = out[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        assert logmel_err(got, ref) <= 1.0, u
