@@ -490,6 +490,8 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     }
     if ((rc = up(&th->steps_dev, steps))) return rc;
     if ((rc = up(&th->hdr_dev, hdr))) return rc;
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_occ3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2SmemT<true>::kTotal));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_occ3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2SmemT<true>::kTotal));
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
@@ -570,6 +572,16 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
+    static const bool occ2 = getenv("MAFE_OCC2") != nullptr;   // A/B switch: 2 CTAs/SM variant with two raw buffers
+    if (!occ2 && straight) {
+      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      if (wave_dtype == MAFE_WAVE_I16)
+        fbank512_baked_occ3_kernel<true><<<grid3, kFastThreads, V2SmemT<true>::kTotal, ctx->stream>>>(Q, th->weights);
+      else
+        fbank512_baked_occ3_kernel<false><<<grid3, kFastThreads, V2SmemT<true>::kTotal, ctx->stream>>>(Q, th->weights);
+      MAFE_LAUNCH_CHECK(ctx);
+    } else {
     const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
     {
       ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
@@ -580,6 +592,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       else
         fbank512_baked_kernel<false, true><<<grid, kFastThreads, V2Smem::kTotal, ctx->stream>>>(Q, th->weights);
       MAFE_LAUNCH_CHECK(ctx);
+    }
     }
     if (cmvn) {
       ProfScope ps(ctx, MAFE_PROF_CMVN);

@@ -80,24 +80,31 @@ struct TileInfo {  // geometry of one work item, prepared by thread 0 one iterat
 };
 static_assert(sizeof(TileInfo) <= 64, "TileInfo slot");
 
-struct V2Smem {
-  static constexpr size_t kRaw0 = 0;
-  static constexpr size_t kRaw1 = kV2RawBytes;
-  static constexpr size_t kY = 2 * kV2RawBytes;                          // float[5472]: pre-emphasised tile, then the mel planes + zero row
-  static constexpr size_t kYBytes = sizeof(float) * 5472;
+// Shared-memory layout.  OCC3 = false: two raw (TMA landing) buffers, 2 CTAs/SM.  OCC3 = true: no dedicated raw
+// buffer -- the next tile's waveform lands in the upper part of the Z region once the last sweep has read it
+// (the lower part is the output staging), 62.8 KB per CTA -> 3 CTAs/SM.
+template <bool OCC3>
+struct V2SmemT {
+  static constexpr size_t kRawBase = 0;
+  static constexpr size_t kY = OCC3 ? 0 : 2 * kV2RawBytes;              // float[5472]: pre-emphasised tile, then the mel planes + zero row
+  static constexpr size_t kYBytes = sizeof(float) * 5632;                // 5360 samples padded 16 per 320 (5616), planes + zero row (5445)
   static constexpr size_t kZ = kY + kYBytes;                             // float2[16][273], then the output staging
   static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
+  static constexpr size_t kRawInZ = kZBytes - kV2RawBytes;               // OCC3: raw landing zone = last 21 504 B of the Z region
   static constexpr size_t kWin = kZ + kZBytes;                           // float[400]
   static constexpr size_t kW512 = kWin + sizeof(float) * 400;            // float2[256]
   static constexpr size_t kW256 = kW512 + sizeof(float2) * 256;          // float2[256]
-  static constexpr size_t kBar = kW256 + sizeof(float2) * 256;           // 2 mbarriers
-  static constexpr size_t kInfo = kBar + 32;                             // (2 mbarriers + 2 claimed indices), 2 x TileInfo
-  static constexpr size_t kSteps = kInfo + 2 * 64;                       // SweepStep[2][8][kMaxSteps]
-  static constexpr size_t kHdr = kSteps + sizeof(SweepStep) * 2 * kFastWarps * kMaxSteps;  // SweepHdr[8]
+  static constexpr size_t kBar = kW256 + sizeof(float2) * 256;           // 2 mbarriers + 2 claimed indices
+  static constexpr size_t kInfo = kBar + 32;                             // 2 x TileInfo
+  static constexpr size_t kSteps = kInfo + 2 * 64;                       // SweepStep[2][8][kMaxSteps] (table sweep only)
+  static constexpr size_t kHdr = kSteps + (OCC3 ? 0 : sizeof(SweepStep) * 2 * kFastWarps * kMaxSteps);  // SweepHdr[8]
   static constexpr size_t kTotal = kHdr + sizeof(SweepHdr) * kFastWarps;
 };
+typedef V2SmemT<false> V2Smem;
+static_assert(V2SmemT<true>::kRawInZ % 128 == 0 && V2SmemT<true>::kRawInZ >= (kTileFrames * kV2StageStride + 6 * kV2Mels) * 4,
+              "raw landing zone must not overlap the staging area");
 static_assert(V2Smem::kZ % 16 == 0 && V2Smem::kBar % 8 == 0, "smem alignment");
-static_assert(2 * kPlaneRows * kPlaneStride + kPlaneStride <= 5472, "mel planes + zero row must fit in the y buffer");
+static_assert(2 * kPlaneRows * kPlaneStride + kPlaneStride <= 5632 && kV2Ylen + 16 * (kV2Ylen / 320) <= 5632, "y buffer size");
 static_assert((kTileFrames * kV2StageStride + 6 * kV2Mels) * 4 <= (int)V2Smem::kZBytes, "staging must fit in the Z buffer");
 
 // ---------------------------------------------------------------------------------------------
@@ -288,10 +295,13 @@ __device__ __forceinline__ float raw_elem(const unsigned char* raw, int idx, flo
   return reinterpret_cast<const float*>(raw)[idx] * scale;
 }
 
-template <bool I16, bool TABLE>
-__global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V2Params P, const BakedWeights W) {
+template <bool I16, bool TABLE, bool OCC3>
+__device__ __forceinline__ void fbank512_baked_body(const V2Params& P, const BakedWeights& W) {
+  typedef V2SmemT<OCC3> V2Smem;
   extern __shared__ __align__(128) unsigned char smem[];
-  auto raw_buf = [&](int b) -> unsigned char* { return smem + (size_t)b * kV2RawBytes; };
+  auto raw_buf = [&](int b) -> unsigned char* {
+    return OCC3 ? smem + V2Smem::kZ + V2Smem::kRawInZ : smem + (size_t)b * kV2RawBytes;
+  };
   float* ybuf = reinterpret_cast<float*>(smem + V2Smem::kY);
   float* planes = ybuf;
   float2* Zs = reinterpret_cast<float2*>(smem + V2Smem::kZ);
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kV2Flen; i += kFastThreads) s_win[i] = P.window[i];
   for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
-  for (int i = tid; i < 2 * kFastWarps * kMaxSteps; i += kFastThreads) s_steps[i] = P.sweep_steps[i];
+  if (TABLE) for (int i = tid; i < 2 * kFastWarps * kMaxSteps; i += kFastThreads) s_steps[i] = P.sweep_steps[i];
   if (tid < kFastWarps) s_hdr[tid] = P.sweep_hdr[tid];
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -384,49 +394,40 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     }
 
     // ---- pass P: [dither] + pre-emphasis, raw -> ybuf (y[0] = x[0] at the start of an utterance) ----
+    // Lanes touch consecutive words (one shared-memory wavefront per 32 samples); ybuf is PADDED by 16 floats per
+    // 320 samples (pidx) so that the two frame pairs a warp folds sit 16 banks apart.
     {
       const int64_t s0 = cur.s0;
       const int need = (nf - 1) * kV2Hop + kV2Flen;
       const int sh = cur.shift + 1;  // raw index of sample s0
+      int rem = tid, pad = 0;        // i mod 320, 16 * (i / 320)  (tid < 256 < 320)
       if (nf == kTileFrames && s0 > 0 && P.dither == 0.f && P.preemph_on) {
-        // interior tile: every sample and its predecessor exist -- no bounds logic (unrolled: all loads in flight)
+        // interior tile: every sample and its predecessor exist -- no bounds logic
 #pragma unroll
-        for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
-          const float x0 = raw_elem<I16>(rb, sh + i0 - 1, P.wave_scale);
-          const float x1 = raw_elem<I16>(rb, sh + i0, P.wave_scale);
-          const float x2 = raw_elem<I16>(rb, sh + i0 + 1, P.wave_scale);
-          const float x3 = raw_elem<I16>(rb, sh + i0 + 2, P.wave_scale);
-          const float x4 = raw_elem<I16>(rb, sh + i0 + 3, P.wave_scale);
-          float4 y;
-          y.x = fmaf(-P.pre_lo, x0, fmaf(-P.pre_hi, x0, x1));
-          y.y = fmaf(-P.pre_lo, x1, fmaf(-P.pre_hi, x1, x2));
-          y.z = fmaf(-P.pre_lo, x2, fmaf(-P.pre_hi, x2, x3));
-          y.w = fmaf(-P.pre_lo, x3, fmaf(-P.pre_hi, x3, x4));
-          *reinterpret_cast<float4*>(ybuf + i0) = y;
+        for (int k = 0; k < (kV2Ylen + kFastThreads - 1) / kFastThreads; ++k) {   // fixed trip count: the shuffle stays convergent
+          const int i = tid + k * kFastThreads;
+          const bool ok = i < kV2Ylen;
+          const float x = ok ? raw_elem<I16>(rb, sh + i, P.wave_scale) : 0.f;
+          float xp = __shfl_up_sync(0xffffffffu, x, 1);
+          if (lane == 0 && ok) xp = raw_elem<I16>(rb, sh + i - 1, P.wave_scale);
+          if (ok) ybuf[i + pad] = fmaf(-P.pre_lo, xp, fmaf(-P.pre_hi, xp, x));
+          rem += kFastThreads;
+          if (rem >= 320) { rem -= 320; pad += 16; }
         }
       } else {
-        for (int i0 = tid * 4; i0 < kV2Ylen; i0 += kFastThreads * 4) {
-          float x[5];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int i = i0 - 1 + j;
-            float v = 0.f;
-            if (i < need && (i >= 0 || s0 > 0)) {
-              v = raw_elem<I16>(rb, sh + i, P.wave_scale);
-              if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)(s0 + i), utt, P.seed), v);
+        for (int i = tid; i < kV2Ylen; i += kFastThreads) {
+          float v = 0.f, vp = 0.f;
+          if (i < need) {
+            v = raw_elem<I16>(rb, sh + i, P.wave_scale);
+            if (P.dither != 0.f) v = fmaf(P.dither, dither_normal((uint64_t)(s0 + i), utt, P.seed), v);
+            if (i > 0 || s0 > 0) {
+              vp = raw_elem<I16>(rb, sh + i - 1, P.wave_scale);
+              if (P.dither != 0.f) vp = fmaf(P.dither, dither_normal((uint64_t)(s0 + i - 1), utt, P.seed), vp);
             }
-            x[j] = v;
           }
-          float4 y;
-          if (P.preemph_on) {
-            y.x = fmaf(-P.pre_lo, x[0], fmaf(-P.pre_hi, x[0], x[1]));
-            y.y = fmaf(-P.pre_lo, x[1], fmaf(-P.pre_hi, x[1], x[2]));
-            y.z = fmaf(-P.pre_lo, x[2], fmaf(-P.pre_hi, x[2], x[3]));
-            y.w = fmaf(-P.pre_lo, x[3], fmaf(-P.pre_hi, x[3], x[4]));
-          } else {
-            y = make_float4(x[1], x[2], x[3], x[4]);
-          }
-          *reinterpret_cast<float4*>(ybuf + i0) = y;
+          ybuf[i + pad] = P.preemph_on ? fmaf(-P.pre_lo, vp, fmaf(-P.pre_hi, vp, v)) : v;
+          rem += kFastThreads;
+          if (rem >= 320) { rem -= 320; pad += 16; }
         }
       }
     }
@@ -443,17 +444,21 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     float2* slot = Zs + pair * kSlotStride;
     cpx v0[16], v1[16];
     {
-      const float* ya = ybuf + (2 * pair) * kV2Hop;
+      // pair p starts at padded index 336 p; sample n of frame a sits at n + 16 (n >= 320), of frame b (= a + 160)
+      // at 160 + n + 16 (n >= 160): with n = t + 16 j these shifts depend on j only (compile time)
+      const float* ya = ybuf + pair * 336;
       const float* yb = ya + kV2Hop;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int n = t + 16 * j;
         const float w = s_win[n];
-        const cpx lo = cx(fmaf(ya[n], w, neg_mu), fmaf(yb[n], w, neg_mu));
+        const int sb = j >= 10 ? 16 : 0;                       // frame b, index n
+        const cpx lo = cx(fmaf(ya[n], w, neg_mu), fmaf(yb[n + sb], w, neg_mu));
         const float2 tw = s_w512[n];
         if (j < 9) {  // n + 256 < 400 for every lane exactly when j <= 8
           const float w2 = s_win[n + 256];
-          const cpx hi = cx(fmaf(ya[n + 256], w2, neg_mu), fmaf(yb[n + 256], w2, neg_mu));
+          const int sa2 = j >= 4 ? 16 : 0;                     // frame a, index n + 256 >= 320  <=>  j >= 4
+          const cpx hi = cx(fmaf(ya[n + 256 + sa2], w2, neg_mu), fmaf(yb[n + 256 + 16], w2, neg_mu));   // frame b: 160 + n + 256 >= 320 always
           v0[j] = lo + hi;
           v1[j] = cmulf(lo - hi, cx(tw.x, tw.y));
         } else {
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     __syncthreads();
     // stage 4: everything has arrived during the FFT -> geometry into shared memory, TMA into the other raw
     // buffer (free since the previous tile's pass P); it lands while the rest of this tile is computed
-    if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
+    if (!OCC3 && tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
     if (TABLE) sweep_table<0>(s_steps + warp * kMaxSteps, hdr.nsteps[0], hdr.tail[0], (const unsigned char*)zp, sgn, plane_dst);
     else sweep_dispatch<0>(warp, zp, sgn, planes + kPlaneStride, lane, W);
     __syncthreads();
@@ -483,6 +488,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     if (TABLE) sweep_table<1>(s_steps + (kFastWarps + warp) * kMaxSteps, hdr.nsteps[1], hdr.tail[1], (const unsigned char*)zp, sgn, plane_dst);
     else sweep_dispatch<1>(warp, zp, sgn, planes + kPlaneStride, lane, W);
     __syncthreads();
+    // OCC3: the Z region has been read for the last time -> the next tile's waveform may land in its upper part
+    if (OCC3 && tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
 
     // ---- phase C1: combine the (<= 2) partial sums, log, stage [frame][80]; thread = (frame group g, filter m) ----
     // Branch-free: a filter with fewer than 2 contributing warps reads the all-zero row instead of a plane row.
@@ -532,6 +539,17 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V
     }
     __syncthreads();  // stage (Z) and planes (y) are rewritten by the next iteration
   }
+}
+
+template <bool I16, bool TABLE>
+__global__ void __launch_bounds__(kFastThreads, 2) fbank512_baked_kernel(const V2Params P, const BakedWeights W) {
+  fbank512_baked_body<I16, TABLE, false>(P, W);
+}
+
+// 3 CTAs per SM: 80 registers/thread (a few dozen spills), 62.8 KB of shared memory per CTA
+template <bool I16>
+__global__ void __launch_bounds__(kFastThreads, 3) fbank512_baked_occ3_kernel(const V2Params P, const BakedWeights W) {
+  fbank512_baked_body<I16, false, true>(P, W);
 }
 
 // ---------------------------------------------------------------------------------------------
