@@ -166,6 +166,16 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.cpu_utts)
 
+    if world > 1:
+        # one contiguous slice of the allowed CPUs per rank: pinned buffers are then first-touched on the memory of
+        # the socket that (on HGX boards) also hosts this rank's GPU, instead of all ranks sharing one NUMA node
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, cpus[local * per:(local + 1) * per] or cpus)
+        except (AttributeError, OSError):
+            pass
+
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
