@@ -376,21 +376,21 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   const mafe_frontend_desc& d = plan->d;
   const bool cmvn = d.utt_cmvn_mean || d.utt_cmvn_std;
   MAFE_REQUIRE(!(cmvn && d.out_kind == MAFE_OUT_COMPLEX), "utterance CMVN needs a real-valued output kind");
-  int rc;
+  int rc = MAFE_E_UNSUPPORTED;
+  float* const feat_target = d.out_kind == MAFE_OUT_MFCC ? batch->scratch_dev : out_dev;
   if (plan->fast) {
-    rc = fast_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev);  // CMVN fused inside
-    if (rc != MAFE_E_UNSUPPORTED) return rc;   // e.g. int16 / unaligned input to the STFT kernel: generic route below
+    rc = fast_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, feat_target, db_group);
+    if (rc == MAFE_OK) return rc;                                // conformer fbank (CMVN fused inside) / STFT: done
+    if (rc != kFastNeedsPost && rc != MAFE_E_UNSUPPORTED) return rc;
   }
-  if (d.out_kind == MAFE_OUT_MFCC) {
-    rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, batch->scratch_dev, MAFE_OUT_LOGMEL, db_group);
+  if (rc == MAFE_E_UNSUPPORTED) {   // generic route (also for int16 / unaligned input to a specialised kernel)
+    rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, feat_target,
+                     d.out_kind == MAFE_OUT_MFCC ? MAFE_OUT_LOGMEL : -1, db_group);
     if (rc) return rc;
-    rc = dct_run(ctx, plan, batch, batch->scratch_dev, out_dev, db_group);
-  } else {
-    rc = generic_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev, -1, db_group);
-    if (rc) return rc;
-    if (d.out_kind == MAFE_OUT_LOGMEL && d.log_kind == MAFE_LOG_DB)
-      rc = db_clamp_run(ctx, plan, batch, out_dev, plan->out_dim, db_group);
   }
+  if (d.out_kind == MAFE_OUT_MFCC) rc = dct_run(ctx, plan, batch, batch->scratch_dev, out_dev, db_group);
+  else if (d.out_kind == MAFE_OUT_LOGMEL && d.log_kind == MAFE_LOG_DB) rc = db_clamp_run(ctx, plan, batch, out_dev, plan->out_dim, db_group);
+  else rc = MAFE_OK;
   if (rc) return rc;
   if (cmvn)
     return mafe_cmvn_utt(ctx, out_dev, batch->frame_offsets_dev, batch->n_utts, plan->out_dim, d.utt_cmvn_mean, d.utt_cmvn_std);

@@ -161,9 +161,11 @@ bool fast_plan_supported(const mafe_frontend_desc* desc);
 int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* desc);
 void fast_plan_free(mafe_plan* p);
 int fast_tile_frames();
-// returns MAFE_E_UNSUPPORTED (without setting an error) when this call must take the generic route instead
+// returns MAFE_E_UNSUPPORTED (without setting an error) when this call must take the generic route instead, and
+// kFastNeedsPost when the features were produced but the generic post-processing (top_db clamp / DCT / CMVN) remains
+constexpr int kFastNeedsPost = 1;
 int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale,
-             float* out);
+             float* out, int db_group);
 }  // namespace mafe
 
 // ---- device helpers ----
@@ -190,6 +192,19 @@ __device__ __forceinline__ int64_t pad_index(int64_t s, int64_t L, int mode) {
     default:
       return -1;
   }
+}
+
+// same map, cheap path first: one reflection / clamp in plain compares; the general (multiply reflected) case falls back
+__device__ __forceinline__ int64_t pad_index_fast(int64_t s, int64_t L, int mode) {
+  if (s >= 0 && s < L) return s;
+  int64_t u;
+  switch (mode) {
+    case MAFE_PAD_REFLECT: u = s < 0 ? -s : 2 * (L - 1) - s; break;
+    case MAFE_PAD_SYMMETRIC: u = s < 0 ? -s - 1 : 2 * L - 1 - s; break;
+    case MAFE_PAD_EDGE: return s < 0 ? 0 : L - 1;
+    default: return -1;
+  }
+  return (u >= 0 && u < L) ? u : pad_index(s, L, mode);
 }
 
 // Philox4x32-10 (Salmon et al. 2011), same constants as oracle/restated.py

@@ -1,0 +1,336 @@
+// fbank400.cuh -- specialised kernel for n_fft = 400 mel front-ends: spectrum.melspectrogram (spectrum.py:609-698),
+// features.fbank (features.py:196-270), features.mfcc (:273-373) with their defaults (hann 400, reflect centre
+// padding, hop 160/200, HTK triangles) -- the ECAPA-TDNN / fastspeech2-style front-end of BASELINE.json configs[0],[3].
+// Included by fbank512.cu.
+//
+// Same machinery as the 512-point kernel (persistent CTAs, dynamic tile queue, staged next-tile preparation, TMA
+// bulk load of the waveform tile, frame pairs packed a + i*b, lanes = frames for the sparse mel sweep), with a
+// 400 = 25 x 16 FFT: every lane of a 16-lane group transforms 25 points in registers (5 x 5), the 16-point stage
+// runs as 50 independent 16-point DFTs per warp (two rounds of 32 lanes), and the mel sweep is table driven
+// (any filterbank with <= 2 adjacent filters per bin).  Output: mel energies or log-mel (dB / ln); the top_db clamp
+// and the DCT of MFCC run in the existing follow-up kernels (db_clamp_kernel, dct_kernel).
+#pragma once
+#include "fft400.cuh"
+
+namespace mafe {
+
+constexpr int kN400 = 400;
+constexpr int kBins400 = 201;
+constexpr int kSlot400 = 425;                     // 25 rows x 17 (transpose) >= 400 outputs; 425*8 B = 18 banks mod 32
+constexpr int kRaw400Bytes = 26496;               // (31 * 200 + 400) * 4 + slack, 128 B multiple
+constexpr int kZ400Bytes = kPairs * kSlot400 * 8; // 54 400
+constexpr int kRaw400InZ = kZ400Bytes - kRaw400Bytes;   // 27 904: the waveform tile lands in the upper part of Z
+constexpr int kMaxHop400 = 200;
+constexpr int kMaxMels400 = 128;
+constexpr int kBinsPerWarp400 = 26;               // 8 warps x 26 >= 201 bins
+static_assert(kRaw400InZ % 128 == 0, "raw landing zone alignment");
+
+struct Step400 {
+  float w0, w1;      // weights of filters cur / cur + 1 (pre-scaled: the pair separation leaves 2X, window carries 1/2)
+  uint32_t offs;     // byte offsets of Z[k] (low 16) and Z[400 - k] (high 16) inside the pair's slot
+  int nflush;        // filters to retire before this bin is accumulated
+};
+struct Hdr400 {
+  int lo, nsteps, tail, pad;
+};
+
+struct F400Params {
+  const float* wave;
+  int64_t total_samples;
+  const int64_t* sample_offsets;
+  const int64_t* frame_offsets;
+  const Tile* tiles;
+  int n_tiles;
+  int hop, center, pad_mode, n_mels;
+  int log_kind;
+  float log_arg, log_mult, log_offset;
+  const float* window;     // [400], pre-scaled by spec_scale * wave_scale * 1/2
+  const float2* tw400;     // [25][16]  W400^(t kj)
+  const Step400* steps;    // [8][32]
+  const Hdr400* hdr;       // [8]
+  const int* combine;      // [n_mels]
+  float* out;              // [total_frames][n_mels]
+  int* queue_head;
+  int* group_max;          // dB maxima (ordered-int keys) or null
+  const int* utt_group;
+  int db_group;
+  float2 tw25[16];         // W25^(j1 k1), j1,k1 = 1..4: kernel-parameter constant bank
+};
+
+struct F400TileInfo {
+  int64_t out_row, p_lo, u_lo, off, L, cov_end, end_elem, base_elem;
+  int nf, shift, n_loaded, edge, utt, pad;
+};
+static_assert(sizeof(F400TileInfo) <= 96, "F400TileInfo slot");
+
+// dynamic shared memory: [Z 54400][planes (2*(nm+2)*33+33)*4][window 1600][tw400 3200][steps 4096][hdr 128][bars 32][info 192]
+__host__ __device__ inline size_t f400_planes_bytes(int nm) { return (size_t)(2 * (nm + 2) * kPlaneStride + kPlaneStride) * 4; }
+__host__ __device__ inline size_t f400_smem_bytes(int nm) {
+  return kZ400Bytes + ((f400_planes_bytes(nm) + 15) & ~(size_t)15) + 1600 + 3200 + 4096 + 128 + 32 + 192;
+}
+
+template <int HALFDUMMY = 0>
+__device__ __forceinline__ void sweep400(const Step400* steps, int nsteps, int tail, const unsigned char* zp, float sgn, float* dst) {
+  float acc_lo = 0.f, acc_hi = 0.f;
+  for (int s = 0; s < nsteps; ++s) {
+    const Step400 st = steps[s];
+    int nf = st.nflush;
+    while (__any_sync(0xffffffffu, nf > 0)) {   // table-driven => warp-uniform; the vote tells the compiler
+      *dst = acc_lo;
+      acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride; --nf;
+    }
+    const float2 zk = *reinterpret_cast<const float2*>(zp + (st.offs & 0xffffu));
+    const float2 zn = *reinterpret_cast<const float2*>(zp + (st.offs >> 16));
+    const float re = fmaf(sgn, zn.x, zk.x);
+    const float im = fmaf(-sgn, zn.y, zk.y);
+    const float pw = fmaf(re, re, im * im);
+    acc_lo = fmaf(st.w0, pw, acc_lo);
+    acc_hi = fmaf(st.w1, pw, acc_hi);
+  }
+  while (__any_sync(0xffffffffu, tail > 0)) {
+    *dst = acc_lo;
+    acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride; --tail;
+  }
+}
+
+__global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nm = P.n_mels;
+  float2* Zs = reinterpret_cast<float2*>(smem);
+  float* rawz = reinterpret_cast<float*>(smem + kRaw400InZ);
+  float* stage = reinterpret_cast<float*>(smem);
+  float* planes = reinterpret_cast<float*>(smem + kZ400Bytes);
+  unsigned char* tail_base = smem + kZ400Bytes + ((f400_planes_bytes(nm) + 15) & ~(size_t)15);
+  float* s_win = reinterpret_cast<float*>(tail_base);
+  float2* s_tw = reinterpret_cast<float2*>(tail_base + 1600);
+  Step400* s_steps = reinterpret_cast<Step400*>(tail_base + 1600 + 3200);
+  Hdr400* s_hdr = reinterpret_cast<Hdr400*>(tail_base + 1600 + 3200 + 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail_base + 1600 + 3200 + 4096 + 128);
+  int* s_work = reinterpret_cast<int*>(bars) + 4;
+  F400TileInfo* info = reinterpret_cast<F400TileInfo*>(tail_base + 1600 + 3200 + 4096 + 128 + 32);
+  const int stage_stride = (nm + 4) & ~3;   // floats per staged frame row (16 B multiple)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hop = P.hop;
+  for (int i = tid; i < kN400; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.tw400[i]; }
+  for (int i = tid; i < kFastWarps * 32; i += kFastThreads) s_steps[i] = P.steps[i];
+  if (tid < kFastWarps) s_hdr[tid] = P.hdr[tid];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- staged preparation of the next tile by thread 0 (see fbank512_baked.cuh) ----
+  int nx_w = P.n_tiles;
+  Tile nx_tile = {0, 0};
+  int64_t nx_off = 0, nx_off1 = 0, nx_fo0 = 0, nx_fo1 = 0;
+  auto load_offsets = [&]() {
+    nx_off = P.sample_offsets[nx_tile.utt];
+    nx_off1 = P.sample_offsets[nx_tile.utt + 1];
+    nx_fo0 = P.frame_offsets[nx_tile.utt];
+    nx_fo1 = P.frame_offsets[nx_tile.utt + 1];
+  };
+  auto issue_tile = [&](int slot) {
+    const int T = (int)(nx_fo1 - nx_fo0);
+    const int64_t L = nx_off1 - nx_off;
+    const int nf = min(kTileFrames, T - nx_tile.frame0);
+    const int pad = P.center ? kN400 / 2 : 0;
+    const int64_t p_lo = (int64_t)nx_tile.frame0 * hop - pad;
+    const int64_t p_hi = p_lo + (int64_t)(nf - 1) * hop + kN400;
+    const int64_t u_lo = p_lo < 0 ? 0 : p_lo, u_hi = p_hi > L ? L : p_hi;
+    const int64_t g_lo = nx_off + u_lo, g_hi = nx_off + u_hi;
+    const int64_t ga = (g_lo * 4) & ~(int64_t)15;
+    const int64_t total16 = (P.total_samples * 4) & ~(int64_t)15;
+    int64_t gb = (g_hi * 4 + 15) & ~(int64_t)15;
+    if (gb > total16) gb = total16;
+    const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (bytes) {
+      mbar_expect_tx(&bars[slot], bytes);
+      tma_bulk_g2s(rawz, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+    } else {
+      mbar_arrive(&bars[slot]);
+    }
+    F400TileInfo ti_;
+    ti_.out_row = nx_fo0 + nx_tile.frame0;
+    ti_.p_lo = p_lo; ti_.u_lo = u_lo; ti_.off = nx_off; ti_.L = L;
+    ti_.base_elem = ga / 4;
+    ti_.cov_end = bytes ? gb / 4 : g_lo;
+    ti_.end_elem = g_hi;
+    ti_.nf = nf;
+    ti_.shift = (int)(g_lo - ga / 4);
+    ti_.n_loaded = (int)(u_hi - u_lo);
+    ti_.edge = (p_lo < 0 || p_hi > L) ? 1 : 0;
+    ti_.utt = nx_tile.utt; ti_.pad = 0;
+    info[slot] = ti_;
+  };
+  if (tid == 0) {
+    nx_w = atomicAdd(P.queue_head, 1);
+    s_work[0] = nx_w;
+    if (nx_w < P.n_tiles) { nx_tile = P.tiles[nx_w]; load_offsets(); issue_tile(0); }
+  }
+  __syncthreads();
+
+  uint32_t phase0 = 0, phase1 = 0;
+  int buf = 0;
+  const int t = lane & 15;
+  const int pair = warp * 2 + (lane >> 4);
+  const int planes_rows = nm + 2;
+  for (;; buf ^= 1) {
+    if (s_work[buf] >= P.n_tiles) break;
+    if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1: claim
+    const F400TileInfo cur = info[buf];
+    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    if (cur.cov_end < cur.end_elem) {
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rawz[e - cur.base_elem] = P.wave[e];
+      __syncthreads();
+    }
+
+    // ---- load: frame pair -> 25 windowed complex points per lane ----
+    cpx v[25];
+    {
+      const int ia = (2 * pair) * hop, ib = ia + hop;
+      const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
+      const float* xr = rawz + cur.shift;   // xr[i] = utterance sample u_lo + i
+      auto sample = [&](int i) -> float {   // padded sample at tile-relative index i (edge tiles only)
+        const int64_t u = pad_index_fast(cur.p_lo + i, cur.L, P.pad_mode);
+        if (u < 0) return 0.f;
+        const int64_t r = u - cur.u_lo;
+        return (r >= 0 && r < cur.n_loaded) ? xr[r] : __ldg(P.wave + cur.off + u);
+      };
+#pragma unroll
+      for (int j = 0; j < 25; ++j) {
+        const int n = t + 16 * j;
+        float a, b;
+        if (!cur.edge) {
+          a = fa_ok ? xr[ia + n] : 0.f;
+          b = fb_ok ? xr[ib + n] : 0.f;
+        } else {
+          a = fa_ok ? sample(ia + n) : 0.f;
+          b = fb_ok ? sample(ib + n) : 0.f;
+        }
+        const float w = s_win[n];
+        v[j] = cx(a * w, b * w);
+      }
+    }
+    __syncthreads();   // the waveform has been consumed: the Z region may be written
+    if (tid == 0) {    // stage 2: publish the claim, fetch the tile record
+      s_work[buf ^ 1] = nx_w;
+      if (nx_w < P.n_tiles) nx_tile = P.tiles[nx_w];
+    }
+
+    // ---- stage 1: 25-point DFT in registers, twiddle W400^(t kj), rows [kj][t] of the pair's slot ----
+    fft25(v, P.tw25);
+    {
+      float2* slot = Zs + pair * kSlot400;
+#pragma unroll
+      for (int kj = 0; kj < 25; ++kj) {
+        cpx x = v[fft25_pos(kj)];
+        if (kj > 0) {
+          const float2 tw = s_tw[kj * 16 + t];
+          x = cmulf(x, cx(tw.x, tw.y));
+        }
+        slot[kj * kRowStride + t] = make_float2(x.x, x.y);
+      }
+    }
+    __syncwarp();
+    if (tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3
+
+    // ---- stage 2: the warp's 2 x 25 sixteen-point DFTs over t, two rounds of 32 lanes ----
+    {
+      cpx u0[16], u1[16];
+      const int q0 = lane / 25, kj0 = lane - 25 * q0;                 // task = lane        (0..31)
+      const int task1 = 32 + lane, q1 = task1 / 25, kj1 = task1 - 25 * q1;   // task = 32 + lane (valid for lane < 18)
+      const float2* s0 = Zs + (warp * 2 + q0) * kSlot400;
+      const float2* s1 = Zs + (warp * 2 + (lane < 18 ? q1 : 0)) * kSlot400;
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) {
+        const float2 x = s0[kj0 * kRowStride + tt];
+        u0[tt] = cx(x.x, x.y);
+        const float2 y = s1[(lane < 18 ? kj1 : 0) * kRowStride + tt];
+        u1[tt] = cx(y.x, y.y);
+      }
+      __syncwarp();
+      fft16(u0);
+      fft16(u1);
+      float2* d0 = Zs + (warp * 2 + q0) * kSlot400;
+      float2* d1 = Zs + (warp * 2 + q1) * kSlot400;
+#pragma unroll
+      for (int kt = 0; kt < 16; ++kt) {
+        const cpx x = u0[fft16_pos(kt)];
+        d0[kj0 + 25 * kt] = make_float2(x.x, x.y);
+        if (lane < 18) {
+          const cpx y = u1[fft16_pos(kt)];
+          d1[kj1 + 25 * kt] = make_float2(y.x, y.y);
+        }
+      }
+    }
+    __syncthreads();   // every pair's spectrum is in its slot
+
+    // ---- sweep: lanes = frames, this warp's 26 bins ----
+    {
+      const Hdr400 hdr = s_hdr[warp];
+      const unsigned char* zp = reinterpret_cast<const unsigned char*>(Zs + (lane >> 1) * kSlot400);
+      const float sgn = (lane & 1) ? -1.f : 1.f;
+      float* dst = planes + (warp & 1) * (planes_rows * kPlaneStride) + (hdr.lo + 1) * kPlaneStride + lane;
+      sweep400(s_steps + warp * 32, hdr.nsteps, hdr.tail, zp, sgn, dst);
+      if (tid >= kFastThreads - 32) planes[2 * planes_rows * kPlaneStride + lane] = 0.f;   // the all-zero row
+    }
+    __syncthreads();   // Z has been read for the last time
+    if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4: next tile's waveform into the upper Z region
+
+    // ---- combine, log, stage [frame][nm], track the dB maximum ----
+    {
+      const int G = kFastThreads / nm;              // frame groups (nm <= 128 -> G >= 2)
+      const int g = tid / nm, m = tid - g * nm;
+      float vmax = -INFINITY;
+      if (g < G) {
+        const int c = P.combine[m];
+        const int n = c & 3, p0 = (c >> 2) & 1;
+        const float* zero_row = planes + 2 * planes_rows * kPlaneStride;
+        const float* pa = n >= 1 ? planes + p0 * (planes_rows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
+        const float* pb = n == 2 ? planes + (p0 ^ 1) * (planes_rows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
+        for (int f = g; f < kTileFrames; f += G) {
+          const float e = pa[f] + pb[f];
+          float o = e;
+          if (P.log_kind == MAFE_LOG_DB) {
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(e, P.log_arg)));
+            o = fmaf(P.log_mult * 0.30102999566398119521f, l2, -P.log_offset);
+            if (f < cur.nf) vmax = fmaxf(vmax, o);
+          } else if (P.log_kind == MAFE_LOG_LN_PLUS) {
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e + P.log_arg));
+            o = l2 * 0.69314718055994530942f;
+          } else if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) {
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e == 0.f ? 2.220446049250313e-16f : e));
+            o = l2 * 0.69314718055994530942f;
+          }
+          stage[f * stage_stride + m] = o;
+        }
+      }
+      if (P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE) {
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0 && vmax > -INFINITY) {
+          const int grp = P.db_group == MAFE_DBGROUP_UTT ? cur.utt : (P.db_group == MAFE_DBGROUP_BATCH ? 0 : P.utt_group[cur.utt]);
+          atomicMax(&P.group_max[grp], ordered_key(vmax));
+        }
+      }
+    }
+    __syncthreads();
+    {
+      float* dst = P.out + cur.out_row * (int64_t)nm;
+      const int total = cur.nf * nm;
+      for (int e = tid; e < total; e += kFastThreads) {
+        const int f = e / nm, m = e - f * nm;
+        dst[e] = stage[f * stage_stride + m];
+      }
+    }
+    __syncthreads();   // staging (lower Z) and planes are free again; s_work / info of the next tile are visible
+  }
+}
+
+}  // namespace mafe

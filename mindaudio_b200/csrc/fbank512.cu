@@ -321,12 +321,18 @@ namespace mafe {
 
 }  // namespace mafe
 #include "stft512.cuh"
+#include "fbank400.cuh"
 namespace mafe {
 
 struct FastTablesHost {
   FastTablesDev dev;
   int ylen;
   bool stft = false;      // n_fft = 512 complex STFT plan (stft512_kernel)
+  bool f400 = false;      // n_fft = 400 mel front-end plan (fbank400_kernel)
+  float2* tw400_dev = nullptr;
+  Step400* steps400_dev = nullptr;
+  Hdr400* hdr400_dev = nullptr;
+  float2 tw25[16];
   bool baked = false;     // the plan is exactly the conformer configuration the baked kernel was generated for
   BakedWeights weights;   // (w0, w1) per bin for the baked kernel's parameter bank
   SweepStep* steps_dev = nullptr;
@@ -336,8 +342,8 @@ struct FastTablesHost {
 int fast_tile_frames() { return kTileFrames; }
 
 // per-bin form of the filterbank: <= 2 ADJACENT filters per bin, non-decreasing in k
-static bool build_bins(const mafe_frontend_desc* d, std::vector<BinEntry>& bins) {
-  const int nb = kBins, nm = d->n_mels;
+static bool build_bins_n(const mafe_frontend_desc* d, int nb, float scale, std::vector<BinEntry>& bins) {
+  const int nm = d->n_mels;
   bins.assign(nb, BinEntry{0, 0.f, 0.f, 0});
   int prev = -1;
   for (int k = 0; k < nb; ++k) {
@@ -357,18 +363,22 @@ static bool build_bins(const mafe_frontend_desc* d, std::vector<BinEntry>& bins)
     }
     if (e.f0 < prev) return false;
     prev = e.f0;
-    e.w0 *= 0.25f; e.w1 *= 0.25f;  // the pair separation leaves 2*X: |2X|^2 / 4
+    e.w0 *= scale; e.w1 *= scale;
     bins[k] = e;
   }
   return true;
 }
+// 512-point kernels: the pair separation leaves 2*X, so |2X|^2 / 4
+static bool build_bins(const mafe_frontend_desc* d, std::vector<BinEntry>& bins) { return build_bins_n(d, kBins, 0.25f, bins); }
 
 // the kernel's emit pattern, replayed on the host (it does not depend on data)
-static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector<int2>& ranges, std::vector<int>& comb) {
+static bool build_combine_n(const std::vector<BinEntry>& bins, int nm, int nb, int bins_per_warp, std::vector<int2>& ranges,
+                            std::vector<int>& comb) {
   ranges.assign(kFastWarps, int2{0, -1});
   std::vector<std::vector<int>> who(nm);
   for (int w = 0; w < kFastWarps; ++w) {
-    const int k_lo = 32 * w, k_hi = (w == kFastWarps - 1) ? kBins : 32 * w + 32;
+    const int k_lo = std::min(bins_per_warp * w, nb - 1);
+    const int k_hi = (w == kFastWarps - 1) ? nb : std::min(bins_per_warp * w + bins_per_warp, nb);
     int lo = bins[k_lo].f0, hi = bins[k_hi - 1].f0 + 1;
     ranges[w] = int2{lo, hi};
     for (int m = std::max(lo, 0); m <= std::min(hi, nm - 1); ++m) who[m].push_back(w);
@@ -383,14 +393,29 @@ static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector
   }
   return true;
 }
+static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector<int2>& ranges, std::vector<int>& comb) {
+  return build_combine_n(bins, nm, kBins, 32, ranges, comb);
+}
 
 static bool stft_plan_supported(const mafe_frontend_desc* d) {
   return d->n_fft == kNfft && d->frame_len == kNfft && d->out_kind == MAFE_OUT_COMPLEX && d->hop >= 1 && d->hop <= kStftMaxHop &&
          d->preemph == 0.0 && !d->remove_frame_mean && d->dither == 0.f && d->spec_scale == 1.0f;
 }
 
+static bool f400_plan_supported(const mafe_frontend_desc* d) {
+  if (!(d->n_fft == kN400 && d->frame_len == kN400 && d->hop >= 1 && d->hop <= kMaxHop400)) return false;
+  if (!(d->out_kind == MAFE_OUT_MEL || d->out_kind == MAFE_OUT_LOGMEL || d->out_kind == MAFE_OUT_MFCC)) return false;
+  if (d->power != 2.0f || d->preemph != 0.0 || d->remove_frame_mean || d->dither != 0.f) return false;
+  if (d->n_mels < 2 || d->n_mels > kMaxMels400) return false;
+  std::vector<BinEntry> bins;
+  std::vector<int2> ranges;
+  std::vector<int> comb;
+  return build_bins_n(d, kBins400, 1.0f, bins) && build_combine_n(bins, d->n_mels, kBins400, kBinsPerWarp400, ranges, comb);
+}
+
 bool fast_plan_supported(const mafe_frontend_desc* d) {
   if (stft_plan_supported(d)) return true;
+  if (f400_plan_supported(d)) return true;
   if (d->n_fft != kNfft || d->center || d->out_kind != MAFE_OUT_LOGMEL || d->power != 2.0f || d->spec_scale != 1.0f)
     return false;
   if (!(d->log_kind == MAFE_LOG_LN_EPS_IF_ZERO || d->log_kind == MAFE_LOG_LN_PLUS || d->log_kind == MAFE_LOG_NONE)) return false;
@@ -431,6 +456,51 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       w256[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
     }
   int rc;
+  th->f400 = !th->stft && f400_plan_supported(d);
+  if (th->f400) {
+    std::vector<float> w400(kN400);
+    for (int i = 0; i < kN400; ++i) w400[i] = 0.5f * d->spec_scale * d->window[i];   // 1/2: the pair separation leaves 2X
+    std::vector<float2> tw400(kN400);
+    for (int kj = 0; kj < 25; ++kj)
+      for (int t = 0; t < 16; ++t) {
+        double a = -2.0 * M_PI * (double)(t * kj) / 400.0;
+        tw400[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
+      }
+    for (int j1 = 1; j1 < 5; ++j1)
+      for (int k1 = 1; k1 < 5; ++k1) {
+        double a = -2.0 * M_PI * (double)(j1 * k1) / 25.0;
+        th->tw25[(j1 - 1) * 4 + (k1 - 1)] = make_float2((float)cos(a), (float)sin(a));
+      }
+    std::vector<BinEntry> bins;
+    std::vector<int2> ranges;
+    std::vector<int> comb;
+    if (!build_bins_n(d, kBins400, 1.0f, bins) || !build_combine_n(bins, d->n_mels, kBins400, kBinsPerWarp400, ranges, comb)) {
+      set_error("filterbank is not in per-bin form");
+      return MAFE_E_UNSUPPORTED;
+    }
+    std::vector<Step400> steps(kFastWarps * 32, Step400{0.f, 0.f, 0u, 0});
+    std::vector<Hdr400> hdr(kFastWarps);
+    for (int w = 0; w < kFastWarps; ++w) {
+      const int k_lo = kBinsPerWarp400 * w, k_hi = (w == kFastWarps - 1) ? kBins400 : std::min(k_lo + kBinsPerWarp400, kBins400);
+      int cur = ranges[w].x, n = 0;
+      for (int k = k_lo; k < k_hi; ++k, ++n) {
+        Step400 st;
+        st.w0 = bins[k].w0; st.w1 = bins[k].w1;
+        st.offs = (uint32_t)(k * 8) | ((uint32_t)(((kN400 - k) % kN400) * 8) << 16);
+        st.nflush = bins[k].f0 - cur;
+        cur = bins[k].f0;
+        steps[w * 32 + n] = st;
+      }
+      hdr[w] = Hdr400{ranges[w].x, n, n ? ranges[w].y - cur + 1 : 0, 0};
+    }
+    if ((rc = up(&th->dev.window, w400))) return rc;
+    if ((rc = up(&th->tw400_dev, tw400))) return rc;
+    if ((rc = up(&th->steps400_dev, steps))) return rc;
+    if ((rc = up(&th->hdr400_dev, hdr))) return rc;
+    if ((rc = up(&th->dev.combine, comb))) return rc;
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f400_smem_bytes(kMaxMels400)));
+    return MAFE_OK;
+  }
   if (th->stft) {
     if ((rc = up(&th->dev.window, win))) return rc;
     if ((rc = up(&th->dev.w512, w512))) return rc;
@@ -505,14 +575,45 @@ void fast_plan_free(mafe_plan* p) {
   cudaFree(th->dev.window); cudaFree(th->dev.w512); cudaFree(th->dev.w256t);
   cudaFree(th->dev.bins); cudaFree(th->dev.warp_range); cudaFree(th->dev.combine); cudaFree(th->dev.cover);
   cudaFree(th->steps_dev); cudaFree(th->hdr_dev);
+  cudaFree(th->tw400_dev); cudaFree(th->steps400_dev); cudaFree(th->hdr400_dev);
   delete th;
   p->fast_tables = nullptr;
 }
 
-int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale, float* out) {
+__global__ void fill_keys_kernel(int* p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale, float* out,
+             int db_group) {
   if (b->n_tiles == 0) return MAFE_OK;
   const FastTablesHost* th = static_cast<const FastTablesHost*>(p->fast_tables);
   const mafe_frontend_desc& d = p->d;
+  if (th->f400) {
+    if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
+    F400Params F;
+    F.wave = (const float*)wave; F.total_samples = b->wave_len;
+    F.sample_offsets = b->sample_offsets_dev; F.frame_offsets = b->frame_offsets_dev; F.tiles = b->tiles_dev;
+    F.n_tiles = b->n_tiles; F.hop = d.hop; F.center = d.center; F.pad_mode = d.pad_mode; F.n_mels = d.n_mels;
+    F.log_kind = d.out_kind == MAFE_OUT_MEL ? MAFE_LOG_NONE : d.log_kind;
+    F.log_arg = d.log_arg; F.log_mult = d.log_mult; F.log_offset = d.log_offset;
+    F.window = th->dev.window; F.tw400 = th->tw400_dev; F.steps = th->steps400_dev; F.hdr = th->hdr400_dev;
+    F.combine = th->dev.combine; F.out = out; F.queue_head = b->queue_dev;
+    F.db_group = (d.log_kind == MAFE_LOG_DB && d.top_db >= 0.f && d.out_kind != MAFE_OUT_MEL) ? db_group : MAFE_DBGROUP_NONE;
+    F.group_max = b->group_max_dev; F.utt_group = b->utt_group_dev;
+    for (int i = 0; i < 16; ++i) F.tw25[i] = th->tw25[i];
+    MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
+    if (F.db_group != MAFE_DBGROUP_NONE) {
+      const int n = std::max(b->n_groups, 1);
+      fill_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->group_max_dev, n, (int)0x80000000);
+      MAFE_LAUNCH_CHECK(ctx);
+    }
+    ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+    fbank400_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, f400_smem_bytes(d.n_mels), ctx->stream>>>(F);
+    MAFE_LAUNCH_CHECK(ctx);
+    return kFastNeedsPost;
+  }
   if (th->stft) {
     if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
     StftParams S;

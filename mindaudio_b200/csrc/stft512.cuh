@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftPara
       const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
       const float* xr = rb + cur.shift;   // xr[i] = utterance sample u_lo + i
       auto sample = [&](int i) -> float {   // padded sample at tile-relative index i (edge tiles only)
-        const int64_t u = pad_index(cur.p_lo + i, cur.L, P.pad_mode);
+        const int64_t u = pad_index_fast(cur.p_lo + i, cur.L, P.pad_mode);
         if (u < 0) return 0.f;
         const int64_t r = u - cur.u_lo;
         return (r >= 0 && r < cur.n_loaded) ? xr[r] : __ldg(P.wave + cur.off + u);
