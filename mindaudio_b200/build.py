@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmafe.so")
 SOURCES = ["api.cu", "generic.cu", "fbank512.cu", "ops.cu", "istft.cu"]
-HEADERS = ["common.cuh", "fft_generic.cuh", os.path.join("..", "..", "include", "mafe.h")]
+HEADERS = [os.path.join("..", "..", "include", "mafe.h")]   # + every *.cuh / *.inc next to the sources (see _digest)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -28,7 +28,8 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    for name in SOURCES + HEADERS:
+    included = sorted(n for n in os.listdir(CSRC) if n.endswith((".cuh", ".inc", ".h")))
+    for name in SOURCES + HEADERS + included:
         with open(os.path.join(CSRC, name), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

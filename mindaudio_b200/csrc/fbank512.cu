@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, doubl
 // ---------------------------------------------------------------------------------------------
 }  // namespace mafe
 #include "fbank512_baked.cuh"
+#include "fbank512_v3.cuh"
 namespace mafe {
 
 }  // namespace mafe
@@ -335,6 +336,9 @@ struct FastTablesHost {
   float2 tw25[16];
   bool baked = false;     // the plan is exactly the conformer configuration the baked kernel was generated for
   BakedWeights weights;   // (w0, w1) per bin for the baked kernel's parameter bank
+  V3Sweep sweep;          // sweep program of the v3 kernel (kernel-parameter bank)
+  bool v3 = false;        // the v3 kernel's compact planes can hold this filterbank
+  int* comb3_dev = nullptr;   // v3: plane rows (A | B << 8) of every filter
   SweepStep* steps_dev = nullptr;
   SweepHdr* hdr_dev = nullptr;
 };
@@ -393,6 +397,79 @@ static bool build_combine_n(const std::vector<BinEntry>& bins, int nm, int nb, i
   }
   return true;
 }
+// Sweep program of the v3 kernel.  The 128 sub-transform outputs kk (FFT bins 2kk, 2kk+1; the Nyquist bin rides with the
+// last warp) are split into 8 contiguous warp ranges that BALANCE the sweep cost (bins x c_bin + retired filters x
+// c_ret per half): the mel triangles are narrower than an FFT bin at the low end and ~16 bins wide at the top, so equal
+// bin counts would leave the first warp with 4x the retires of the last.  Exact min-max partition by dynamic programming.
+static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std::vector<int>& comb3) {
+  memset(&S, 0, sizeof(S));
+  comb3.assign(kV2Mels, 0);
+  constexpr int NK = 128, W = kFastWarps;
+  constexpr int c_bin = 14, c_ret = 21;   // measured instruction counts per bin / per retire (SASS)
+  auto lo_of = [&](int a) { return bins[2 * a].f0; };
+  auto hi_of = [&](int b) { return bins[b == NK ? kBins - 1 : 2 * b - 1].f0 + 1; };   // last warp takes bin 256 too
+  auto cost = [&](int a, int b) -> long {
+    const int nret = hi_of(b) - lo_of(a) + 1;
+    if (nret > kV3Runs) return -1;
+    // a filter may be emitted by at most two (adjacent) warps: the range must advance the filter index by >= 2
+    if (a > 0 && b < NK && bins[2 * b].f0 - bins[2 * a - 1].f0 < 2) return -1;
+    return (long)c_bin * (2 * (b - a) + (b == NK ? 1 : 0)) + (long)c_ret * 2 * nret;
+  };
+  const long INF = 1L << 60;
+  std::vector<std::vector<long>> best(W + 1, std::vector<long>(NK + 1, INF));
+  std::vector<std::vector<int>> from(W + 1, std::vector<int>(NK + 1, -1));
+  best[0][0] = 0;
+  for (int w = 1; w <= W; ++w)
+    for (int b = w; b <= NK; ++b)
+      for (int a = w - 1; a < b; ++a) {
+        if (best[w - 1][a] == INF) continue;
+        const long c = cost(a, b);
+        if (c < 0) continue;
+        const long v = std::max(best[w - 1][a], c);
+        if (v < best[w][b]) { best[w][b] = v; from[w][b] = a; }
+      }
+  if (best[W][NK] == INF) return false;
+  int edge[W + 1];
+  edge[W] = NK;
+  for (int w = W; w > 0; --w) edge[w - 1] = from[w][edge[w]];
+
+  int rows = 0;
+  std::vector<int> nrow(kV2Mels, 0);
+  for (int w = 0; w < W; ++w) {
+    const int a = edge[w], b = edge[w + 1];
+    const int lo = lo_of(a), hi = hi_of(b);
+    S.kk0[w] = (unsigned char)a;
+    S.row0[w] = (unsigned char)rows;
+    for (int m = lo; m <= hi; ++m, ++rows)
+      if (m >= 0 && m < kV2Mels) {
+        if (nrow[m] >= 2) return false;
+        comb3[m] |= rows << (8 * nrow[m]);
+        ++nrow[m];
+      }
+    for (int h = 0; h < 2; ++h) {
+      // runs: bins accumulated before each retire; exactly hi - lo + 1 retires, the last one after the last bin
+      const int gw = h * W + w;
+      const int kk_end = b + ((h == 0 && b == NK) ? 1 : 0);
+      int cur = lo, r = 0, len = 0;
+      for (int kk = a; kk < kk_end; ++kk) {
+        const BinEntry& e = bins[2 * kk + h];
+        for (; cur < e.f0; ++cur) { if (r >= kV3Runs) return false; S.len[gw][r++] = (unsigned char)len; len = 0; }
+        S.w[h * kV3HalfStride + kk] = make_float2(e.w0, e.w1);
+        ++len;
+      }
+      for (; cur <= hi; ++cur) { if (r >= kV3Runs) return false; S.len[gw][r++] = (unsigned char)len; len = 0; }
+      S.nrun[gw] = (unsigned char)r;
+    }
+  }
+  if (rows >= kV3PlaneRows) return false;
+  S.zero_row = rows;
+  for (int m = 0; m < kV2Mels; ++m) {
+    if (nrow[m] == 0) comb3[m] = rows | (rows << 8);
+    else if (nrow[m] == 1) comb3[m] |= rows << 8;
+  }
+  return true;
+}
+
 static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector<int2>& ranges, std::vector<int>& comb) {
   return build_combine_n(bins, nm, kBins, 32, ranges, comb);
 }
@@ -558,6 +635,13 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
         hdr[w].tail[h] = hi - cur + 1;
       }
     }
+    {
+      std::vector<int> comb3;
+      th->v3 = build_v3_program(bins, th->sweep, comb3);
+      if ((rc = up(&th->comb3_dev, comb3))) return rc;
+    }
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem::kTotal));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem::kTotal));
     if ((rc = up(&th->steps_dev, steps))) return rc;
     if ((rc = up(&th->hdr_dev, hdr))) return rc;
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_occ3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2SmemT<true>::kTotal));
@@ -574,7 +658,7 @@ void fast_plan_free(mafe_plan* p) {
   if (!th) return;
   cudaFree(th->dev.window); cudaFree(th->dev.w512); cudaFree(th->dev.w256t);
   cudaFree(th->dev.bins); cudaFree(th->dev.warp_range); cudaFree(th->dev.combine); cudaFree(th->dev.cover);
-  cudaFree(th->steps_dev); cudaFree(th->hdr_dev);
+  cudaFree(th->steps_dev); cudaFree(th->hdr_dev); cudaFree(th->comb3_dev);
   cudaFree(th->tw400_dev); cudaFree(th->steps400_dev); cudaFree(th->hdr400_dev);
   delete th;
   p->fast_tables = nullptr;
@@ -674,7 +758,17 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
     static const bool occ2 = getenv("MAFE_OCC2") != nullptr;   // A/B switch: 2 CTAs/SM variant with two raw buffers
-    if (!occ2 && straight) {
+    static const bool use_v2 = getenv("MAFE_V2") != nullptr;   // A/B switch: previous kernel generation
+    if (!use_v2 && th->v3) {
+      Q.combine = th->comb3_dev;
+      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      if (wave_dtype == MAFE_WAVE_I16)
+        fbank512_v3_kernel<true><<<grid3, kFastThreads, V3Smem::kTotal, ctx->stream>>>(Q, th->sweep);
+      else
+        fbank512_v3_kernel<false><<<grid3, kFastThreads, V3Smem::kTotal, ctx->stream>>>(Q, th->sweep);
+      MAFE_LAUNCH_CHECK(ctx);
+    } else if (!occ2 && straight) {
       const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
       ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
       if (wave_dtype == MAFE_WAVE_I16)

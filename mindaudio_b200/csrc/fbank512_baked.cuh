@@ -287,6 +287,7 @@ __device__ __forceinline__ void fft256_group(cpx (&v)[16], float2* slot, const f
     const cpx x = u[fft16_pos(kt)];
     slot[t + 16 * kt] = make_float2(x.x, x.y);
   }
+  if (t == 0) slot[256] = make_float2(u[fft16_pos(0)].x, u[fft16_pos(0)].y);   // output 0 again: partner of itself (v3 sweep)
 }
 
 template <bool I16>
@@ -531,11 +532,17 @@ __device__ __forceinline__ void fbank512_baked_body(const V2Params& P, const Bak
       const float* pb = n == 2 ? planes + (p0 ^ 1) * (kPlaneRows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
       float s1 = 0.f, s2 = 0.f;
       auto body = [&](auto log_fn) {
+        // frames g, g + 3, ..., g + 30: fixed trip count, immediate offsets; only the last step can leave the tile
+        // (f = 32 reads the pad column of the plane row and is discarded)
+        const float* qa = pa + g;
+        const float* qb = pb + g;
+        float* sd = stage + g * kV2StageStride + m;
+        const int left = nf - g;
 #pragma unroll
-        for (int f = g; f < kTileFrames; f += 3) {
-          const float o = log_fn(pa[f] + pb[f]);
-          stage[f * kV2StageStride + m] = o;
-          const float ov = f < nf ? o : 0.f;
+        for (int i = 0; i < 11; ++i) {
+          const float o = log_fn(qa[3 * i] + qb[3 * i]);
+          if (i < 10 || g < 2) sd[3 * i * kV2StageStride] = o;
+          const float ov = 3 * i < left ? o : 0.f;
           s1 += ov;
           s2 = fmaf(ov, ov, s2);
         }
