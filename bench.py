@@ -270,15 +270,15 @@ def main():
             traffic, traffic_src = td["traffic_bytes_per_launch"], "profiles/r01_fbank512_traffic.json (dram__bytes_read+write)"
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_FRAME * n_frames,
-                "peak_source": peak_src, "kernel": "fbank512_baked_kernel",
+                "peak_source": peak_src, "kernel": "fbank512_v3_kernel",
                 "kernel_ms": k_avg_s * 1e3, "frames_per_launch": int(n_frames),
                 "fp32": {"achieved_tflops": achieved_tflops, "measured_peak_tflops": fp32_peak,
                          "nominal_peak_tflops": FP32_PEAK_NOMINAL_TFLOPS, "frac_of_measured": achieved_tflops / fp32_peak,
                          "note": "FP32 FMA peak measured in this run by mafe_fp32_fma_peak (not in MEASURED_PEAKS.json); "
                                  "algorithmic flops = 14 253 per frame (SURVEY.md 8d)"},
                 "frac_of_min_roofline": max(t_hbm, t_fp32) / k_avg_s,
-                "step_share": {"fbank512_baked_kernel_ms": k_ms / max(k_n, 1), "frame_mean_prepass_ms": p_ms / max(p_n, 1),
-                               "cmvn_ms": c_ms / max(c_n, 1), "step_ms": ms / args.steps}}
+                "step_share": {"fbank512_v3_kernel_ms": k_ms / max(k_n, 1), "frame_mean_prepass_ms": p_ms / max(p_n, 1),
+                               "cmvn_apply_ms": c_ms / max(c_n, 1), "step_ms": ms / args.steps}}
 
     # ---- end to end through the host-facing call: pinned host buffers, copies inside the timed region ----
     e2e = None

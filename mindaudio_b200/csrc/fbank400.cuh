@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
   }
   __syncthreads();
 
-  // ---- staged preparation of the next tile by thread 0 (see fbank512_baked.cuh) ----
+  // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh) ----
   int nx_w = P.n_tiles;
   Tile nx_tile = {0, 0};
   int64_t nx_off = 0, nx_off1 = 0, nx_fo0 = 0, nx_fo1 = 0;

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, doubl
 // host side
 // ---------------------------------------------------------------------------------------------
 }  // namespace mafe
-#include "fbank512_baked.cuh"
+#include "fbank512_tile.cuh"
 #include "fbank512_v3.cuh"
 namespace mafe {
 
@@ -334,13 +334,10 @@ struct FastTablesHost {
   Step400* steps400_dev = nullptr;
   Hdr400* hdr400_dev = nullptr;
   float2 tw25[16];
-  bool baked = false;     // the plan is exactly the conformer configuration the baked kernel was generated for
-  BakedWeights weights;   // (w0, w1) per bin for the baked kernel's parameter bank
+  bool tile_geom = false; // conformer geometry (400 / 160 / 512 / 80 filters): the v3 kernel and its pre-pass apply
   V3Sweep sweep;          // sweep program of the v3 kernel (kernel-parameter bank)
   bool v3 = false;        // the v3 kernel's compact planes can hold this filterbank
   int* comb3_dev = nullptr;   // v3: plane rows (A | B << 8) of every filter
-  SweepStep* steps_dev = nullptr;
-  SweepHdr* hdr_dev = nullptr;
 };
 
 int fast_tile_frames() { return kTileFrames; }
@@ -405,7 +402,7 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
   memset(&S, 0, sizeof(S));
   comb3.assign(kV2Mels, 0);
   constexpr int NK = 128, W = kFastWarps;
-  constexpr int c_bin = 14, c_ret = 21;   // measured instruction counts per bin / per retire (SASS)
+  constexpr int c_bin = 17, c_ret = 8;   // instruction counts per bin / per retire (SASS)
   auto lo_of = [&](int a) { return bins[2 * a].f0; };
   auto hi_of = [&](int b) { return bins[b == NK ? kBins - 1 : 2 * b - 1].f0 + 1; };   // last warp takes bin 256 too
   auto cost = [&](int a, int b) -> long {
@@ -439,6 +436,7 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
     const int a = edge[w], b = edge[w + 1];
     const int lo = lo_of(a), hi = hi_of(b);
     S.kk0[w] = (unsigned char)a;
+    S.kk0[w + 1] = (unsigned char)b;
     S.row0[w] = (unsigned char)rows;
     for (int m = lo; m <= hi; ++m, ++rows)
       if (m >= 0 && m < kV2Mels) {
@@ -447,18 +445,14 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
         ++nrow[m];
       }
     for (int h = 0; h < 2; ++h) {
-      // runs: bins accumulated before each retire; exactly hi - lo + 1 retires, the last one after the last bin
-      const int gw = h * W + w;
       const int kk_end = b + ((h == 0 && b == NK) ? 1 : 0);
-      int cur = lo, r = 0, len = 0;
+      int cur = lo;
       for (int kk = a; kk < kk_end; ++kk) {
         const BinEntry& e = bins[2 * kk + h];
-        for (; cur < e.f0; ++cur) { if (r >= kV3Runs) return false; S.len[gw][r++] = (unsigned char)len; len = 0; }
-        S.w[h * kV3HalfStride + kk] = make_float2(e.w0, e.w1);
-        ++len;
+        S.step[h * kV3HalfStride + kk] = V3Step{e.w0, e.w1, e.f0 - cur, 0};
+        cur = e.f0;
       }
-      for (; cur <= hi; ++cur) { if (r >= kV3Runs) return false; S.len[gw][r++] = (unsigned char)len; len = 0; }
-      S.nrun[gw] = (unsigned char)r;
+      S.tail[h][w] = (unsigned char)(hi - cur + 1);
     }
   }
   if (rows >= kV3PlaneRows) return false;
@@ -608,47 +602,13 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     if ((rc = up(&th->dev.cover, cover))) return rc;
   }
   MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastSmem::kTotal));
-  th->baked = d->frame_len == kV2Flen && d->hop == kV2Hop && d->n_mels == kV2Mels;
-  for (int k = 0; k < kBins && th->baked; ++k) th->baked = bins[k].f0 == kF0[k];
-  if (th->baked) {
-    for (int k = 0; k < kBins; ++k) th->weights.w[k] = make_float2(bins[k].w0, bins[k].w1);
-    // sweep program of every (half, warp): the data-independent emit pattern, replayed on the host
-    std::vector<SweepStep> steps(2 * kFastWarps * kMaxSteps, SweepStep{0.f, 0.f, 0u, 0});
-    std::vector<SweepHdr> hdr(kFastWarps);
-    for (int w = 0; w < kFastWarps; ++w) {
-      const int lo = ranges[w].x, hi = ranges[w].y;
-      hdr[w].lo = lo;
-      for (int h = 0; h < 2; ++h) {
-        int cur = lo, n = 0;
-        const int kk_end = 16 * w + 16 + ((h == 0 && w == kFastWarps - 1) ? 1 : 0);
-        for (int kk = 16 * w; kk < kk_end; ++kk, ++n) {
-          const int k = 2 * kk + h;
-          const int kr = h == 0 ? ((256 - kk) & 255) : (255 - kk);
-          SweepStep st;
-          st.w0 = bins[k].w0; st.w1 = bins[k].w1;
-          st.offs = (uint32_t)((kk & 255) * 8) | ((uint32_t)(kr * 8) << 16);
-          st.nflush = bins[k].f0 - cur;
-          cur = bins[k].f0;
-          steps[(h * kFastWarps + w) * kMaxSteps + n] = st;
-        }
-        hdr[w].nsteps[h] = n;
-        hdr[w].tail[h] = hi - cur + 1;
-      }
-    }
-    {
-      std::vector<int> comb3;
-      th->v3 = build_v3_program(bins, th->sweep, comb3);
-      if ((rc = up(&th->comb3_dev, comb3))) return rc;
-    }
+  th->tile_geom = d->frame_len == kV2Flen && d->hop == kV2Hop && d->n_mels == kV2Mels;
+  if (th->tile_geom) {
+    std::vector<int> comb3;
+    th->v3 = build_v3_program(bins, th->sweep, comb3);
+    if ((rc = up(&th->comb3_dev, comb3))) return rc;
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem::kTotal));
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem::kTotal));
-    if ((rc = up(&th->steps_dev, steps))) return rc;
-    if ((rc = up(&th->hdr_dev, hdr))) return rc;
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_occ3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2SmemT<true>::kTotal));
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_occ3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2SmemT<true>::kTotal));
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_baked_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2Smem::kTotal));
   }
   return MAFE_OK;
 }
@@ -658,7 +618,7 @@ void fast_plan_free(mafe_plan* p) {
   if (!th) return;
   cudaFree(th->dev.window); cudaFree(th->dev.w512); cudaFree(th->dev.w256t);
   cudaFree(th->dev.bins); cudaFree(th->dev.warp_range); cudaFree(th->dev.combine); cudaFree(th->dev.cover);
-  cudaFree(th->steps_dev); cudaFree(th->hdr_dev); cudaFree(th->comb3_dev);
+  cudaFree(th->comb3_dev);
   cudaFree(th->tw400_dev); cudaFree(th->steps400_dev); cudaFree(th->hdr400_dev);
   delete th;
   p->fast_tables = nullptr;
@@ -724,17 +684,15 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
   P.tab = th->dev;
   P.out = out;
   const bool cmvn = d.utt_cmvn_mean || d.utt_cmvn_std;
-  if (th->baked && ((uintptr_t)wave & 15) == 0) {
+  if (th->tile_geom && th->v3 && ((uintptr_t)wave & 15) == 0) {
     V2Params Q;
     Q.wave = wave; Q.total_samples = b->wave_len; Q.wave_scale = wave_scale;
     Q.sample_offsets = b->sample_offsets_dev; Q.frame_offsets = b->frame_offsets_dev; Q.tiles = b->tiles_dev;
     Q.n_tiles = b->n_tiles; Q.utt_sum = b->utt_sum_dev; Q.utt_stats = cmvn ? b->utt_stats_dev : nullptr;
+
     Q.pre_hi = P.pre_hi; Q.pre_lo = P.pre_lo; Q.preemph_on = P.preemph_on; Q.remove_mean = P.remove_mean;
     Q.dither = P.dither; Q.seed = P.seed; Q.log_kind = P.log_kind; Q.log_arg = P.log_arg;
-    Q.window = th->dev.window; Q.w512 = th->dev.w512; Q.w256t = th->dev.w256t; Q.combine = th->dev.combine;
-    Q.sweep_steps = th->steps_dev; Q.sweep_hdr = th->hdr_dev;
-    // A/B switch (measured on B200, 8192-utterance chunk: straight-line 9.21 ms, table-driven 9.98 ms)
-    static const bool straight = getenv("MAFE_SWEEP_TABLE") == nullptr;
+    Q.window = th->dev.window; Q.w512 = th->dev.w512; Q.w256t = th->dev.w256t; Q.combine = th->comb3_dev;
     Q.out = out;
     Q.queue_head = b->queue_dev;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
@@ -757,37 +715,14 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
-    static const bool occ2 = getenv("MAFE_OCC2") != nullptr;   // A/B switch: 2 CTAs/SM variant with two raw buffers
-    static const bool use_v2 = getenv("MAFE_V2") != nullptr;   // A/B switch: previous kernel generation
-    if (!use_v2 && th->v3) {
-      Q.combine = th->comb3_dev;
-      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
+    {
+      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);   // persistent: 3 CTAs per SM, dynamic tile queue
       ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
       if (wave_dtype == MAFE_WAVE_I16)
         fbank512_v3_kernel<true><<<grid3, kFastThreads, V3Smem::kTotal, ctx->stream>>>(Q, th->sweep);
       else
         fbank512_v3_kernel<false><<<grid3, kFastThreads, V3Smem::kTotal, ctx->stream>>>(Q, th->sweep);
       MAFE_LAUNCH_CHECK(ctx);
-    } else if (!occ2 && straight) {
-      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
-      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-      if (wave_dtype == MAFE_WAVE_I16)
-        fbank512_baked_occ3_kernel<true><<<grid3, kFastThreads, V2SmemT<true>::kTotal, ctx->stream>>>(Q, th->weights);
-      else
-        fbank512_baked_occ3_kernel<false><<<grid3, kFastThreads, V2SmemT<true>::kTotal, ctx->stream>>>(Q, th->weights);
-      MAFE_LAUNCH_CHECK(ctx);
-    } else {
-    const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
-    {
-      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-      if (wave_dtype == MAFE_WAVE_I16)
-        fbank512_baked_kernel<true, true><<<grid, kFastThreads, V2Smem::kTotal, ctx->stream>>>(Q, th->weights);
-      else if (straight)
-        fbank512_baked_kernel<false, false><<<grid, kFastThreads, V2Smem::kTotal, ctx->stream>>>(Q, th->weights);
-      else
-        fbank512_baked_kernel<false, true><<<grid, kFastThreads, V2Smem::kTotal, ctx->stream>>>(Q, th->weights);
-      MAFE_LAUNCH_CHECK(ctx);
-    }
     }
     if (cmvn) {
       ProfScope ps(ctx, MAFE_PROF_CMVN);

@@ -1,8 +1,8 @@
 // fbank512_v3.cuh -- version 3 of the headline kernel (conformer front-end: 400-sample frames, hop 160, 512-point
-// FFT, 80 mel triangles; examples/conformer/dataset.py:117-168).  Included by fbank512.cu after fbank512_baked.cuh,
+// FFT, 80 mel triangles; examples/conformer/dataset.py:117-168).  Included by fbank512.cu after fbank512_tile.cuh,
 // whose tile geometry / TMA / FFT helpers it shares.
 //
-// Why a third version: ncu's source view of v2 (profiles/r01_occ3_segments.txt) charged 28 % of all stall samples to
+// Why a third version: ncu's source view of v2 (profiles/r01_fbank512_v2occ3_segments.txt) charged 28 % of all stall samples to
 // `no_instruction`: v2's code is 93 KB (every warp ran its own straight-line mel sweep, both 256-point transforms and
 // five unrolled copies of pass P were inlined) against a 32 KB L1.5 instruction cache, and the 80-register cap of
 // 3 CTAs/SM spilled the second transform's inputs.  v3 is the same algorithm with ONE copy of each phase:
@@ -21,23 +21,28 @@ namespace mafe {
 constexpr int kV3HalfStride = 130;   // >= 129 sub-transform outputs (bins 2kk + g) of one half
 constexpr int kV3Runs = 32;          // >= filters one warp emits
 // Sweep program: warp w owns the sub-transform outputs kk0[w] .. kk0[w+1]-1 of both halves (g = 0: FFT bins 2kk incl.
-// the Nyquist bin for the last warp; g = 1: bins 2kk+1).  Per (half, warp): nrun runs; run r = len[r] consecutive bins
-// accumulated into filters (cur, cur + 1), then filter cur is retired (stored to its plane row) and cur advances.
-// The split is cost balanced on the host (build_v3_program); everything is data independent.
+// the Nyquist bin for the last warp; g = 1: bins 2kk+1).  A lane keeps two accumulators, filters (cur, cur + 1); step
+// (g, kk) first RETIRES nret filters (stores acc of filter cur to its plane row, cur advances), then accumulates the
+// bin with weights (w0, w1); after the warp's last bin tail[g][w] more filters are retired.  The split is cost balanced
+// on the host (build_v3_program); everything is data independent.
+struct __align__(16) V3Step {
+  float w0, w1;   // weights of filters cur / cur + 1, pre-scaled by 1/4 (the pair separation leaves 2 X)
+  int nret;
+  int pad;
+};
 struct V3Sweep {  // kernel-parameter resident (constant bank 0)
-  float2 w[2 * kV3HalfStride];                   // (w0, w1) per bin: weights of filters cur / cur + 1, pre-scaled by 1/4
-  unsigned char len[2 * kFastWarps][kV3Runs];
-  unsigned char nrun[2 * kFastWarps];
-  unsigned char kk0[kFastWarps];
+  V3Step step[2 * kV3HalfStride];
+  unsigned char tail[2][kFastWarps];
+  unsigned char kk0[kFastWarps + 1];
   unsigned char row0[kFastWarps];      // first plane row of a warp: it emits filters lo .. hi into consecutive rows
   int zero_row;                        // an all-zero plane row (filters with < 2 contributing warps read it)
 };
-static_assert(sizeof(V3Sweep) + sizeof(V2Params) < 4000, "kernel parameters must stay below 4 KB");
+static_assert(sizeof(V3Sweep) + sizeof(V2Params) < 8000, "kernel parameters (large-parameter ABI, <= 32764 B)");
 
 constexpr int kV3PlaneRows = 98;       // sum over warps of emitted filters (80 + 2 guards + <= 2 shared per boundary) + zero row
 struct V3Smem {
   static constexpr size_t kY = 0;                                         // float[5632]: pre-emphasised tile (padded 16 per 320)
-  static constexpr size_t kZ = kY + sizeof(float) * 5632;                 // float2[16][273]; upper part = TMA landing zone, lower = output staging
+  static constexpr size_t kZ = kY + sizeof(float) * 5632;                 // float2[16][273]; upper part = TMA landing zone
   static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
   static constexpr size_t kRawInZ = kZBytes - kV2RawBytes;
   static constexpr size_t kPlanes = kZ + kZBytes;                         // float[98][33]
@@ -49,7 +54,7 @@ struct V3Smem {
   static constexpr size_t kTotal = kInfo + 2 * 64;
 };
 static_assert(3 * (V3Smem::kTotal + 1024) <= 228 * 1024, "3 CTAs per SM");
-static_assert(V3Smem::kRawInZ % 128 == 0 && V3Smem::kRawInZ >= (kTileFrames * kV2StageStride + 6 * kV2Mels) * 4, "landing zone vs staging");
+static_assert(V3Smem::kRawInZ % 128 == 0 && V3Smem::kRawInZ >= 6 * kV2Mels * 4, "landing zone vs the CMVN partial sums");
 static_assert(V3Smem::kZ % 16 == 0 && V3Smem::kBar % 8 == 0 && V3Smem::kWin % 16 == 0, "smem alignment");
 
 // One copy for every warp and both halves.  FFT bin k = 2 kk + g sits at sub-index kk of the group's slot, its conjugate
@@ -68,39 +73,35 @@ __device__ __forceinline__ void bump(int& a) { asm volatile("add.s32 %0, %0, %1;
 
 __device__ __forceinline__ void sweep_v3(const V3Sweep& S, int g, int warp, const float2* __restrict__ zp, float sgn,
                                          float* __restrict__ dst) {
-  const int gw = g * kFastWarps + warp;
   const int kk0 = S.kk0[warp];
   uint32_t ak = smem_u32(zp + kk0);
   uint32_t an = smem_u32(zp + (256 - g) - kk0);
   int si = g * kV3HalfStride + kk0;
-  int r = gw * kV3Runs;
-  const int r_end = r + S.nrun[gw];
+  const int si_end = g * kV3HalfStride + S.kk0[warp + 1] + ((g == 0 && warp == kFastWarps - 1) ? 1 : 0);
   float acc_lo = 0.f, acc_hi = 0.f;
-  if (r != r_end) {
+  auto retire = [&](int n) {
 #pragma unroll 1
     do {
-      const uint32_t ae = ak + 8u * S.len[0][r];
-      bump<1>(r);
-      if (ak != ae) {
-#pragma unroll 1
-        do {
-          const float2 w = S.w[si];
-          const float2 zk = lds_f2(ak);
-          const float2 zn = lds_f2(an);
-          bump<1>(si); bump<8>(ak); bump<-8>(an);
-          const float re = fmaf(sgn, zn.x, zk.x);
-          const float im = fmaf(-sgn, zn.y, zk.y);
-          const float pw = fmaf(re, re, im * im);
-          acc_lo = fmaf(w.x, pw, acc_lo);
-          acc_hi = fmaf(w.y, pw, acc_hi);
-        } while (ak != ae);
-      }
       float v = acc_lo;
       if (g) v += *dst;
       *dst = v;
       acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride;
-    } while (r != r_end);
-  }
+    } while (--n);
+  };
+#pragma unroll 1
+  do {
+    const V3Step st = S.step[si];
+    if (st.nret) retire(st.nret);
+    const float2 zk = lds_f2(ak);
+    const float2 zn = lds_f2(an);
+    bump<1>(si); bump<8>(ak); bump<-8>(an);
+    const float re = fmaf(sgn, zn.x, zk.x);
+    const float im = fmaf(-sgn, zn.y, zk.y);
+    const float pw = fmaf(re, re, im * im);
+    acc_lo = fmaf(st.w0, pw, acc_lo);
+    acc_hi = fmaf(st.w1, pw, acc_hi);
+  } while (si != si_end);
+  retire(S.tail[g][warp]);   // >= 1: the last filter is always retired after the last bin
 }
 
 // frame pair -> registers for group g: window, mean removal, radix-2 fold.  g = 0: even bins (lo + hi);
@@ -333,22 +334,22 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v3_kernel(const __gr
     // the Z region has been read for the last time -> the next tile's waveform may land in its upper part
     if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
 
-    // ---- phase C1: combine the (<= 2) partial sums, log, stage [frame][80]; thread = (frame group g, filter m) ----
+    // ---- phase C: combine the (<= 2) partial sums, log, store; thread = (frame group g, filter m) ----
     // Branch-free: a filter with fewer than 2 contributing warps reads the all-zero row for the missing ones.
-    float* part = stage + kTileFrames * kV2StageStride;  // [3][2][80] per-group CMVN partial sums
+    // The stores go straight to global memory: for one frame the 80 threads of a group write 320 contiguous bytes.
+    float* part = stage;  // [3][2][80] per-group CMVN partial sums (lower part of the Z region, free after the sweeps)
     if (tid < 3 * kV2Mels) {
       const int g = cg, m = cm;
       const float* qa = planes + (crow & 0xff) * kPlaneStride + g;
       const float* qb = planes + (crow >> 8) * kPlaneStride + g;
-      float* sd = stage + g * kV2StageStride + m;
+      float* od = P.out + (cur.out_row + g) * (int64_t)kV2Mels + m;
       const int left = nf - g;
       // one code path for the three log kinds: ln(a == 0 ? eps : a), ln(a + c), a
       const bool use_log = P.log_kind != MAFE_LOG_NONE;
       const float add = P.log_kind == MAFE_LOG_LN_PLUS ? P.log_arg : 0.f;
       const float zero_sub = P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO ? 2.220446049250313e-16f : 0.f;
       float s1 = 0.f, s2 = 0.f;
-      // frames g, g + 3, ..., g + 30: fixed trip count, immediate offsets; only the last step can leave the tile
-      // (f = 32 reads the pad column of the plane row and is discarded)
+      // frames g, g + 3, ..., g + 30: fixed trip count, immediate offsets (f = 32 reads the pad column and is discarded)
 #pragma unroll
       for (int i = 0; i < 11; ++i) {
         const float a = qa[3 * i] + qb[3 * i];
@@ -358,32 +359,25 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v3_kernel(const __gr
         float l;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
         const float o = use_log ? l * 0.69314718055994530942f : a;
-        if (i < 10 || g < 2) sd[3 * i * kV2StageStride] = o;
-        const float ov = 3 * i < left ? o : 0.f;
+        const bool in = 3 * i < left;
+        if (in) od[3 * i * kV2Mels] = o;
+        const float ov = in ? o : 0.f;
         s1 += ov;
         s2 = fmaf(ov, ov, s2);
       }
-      part[(g * 2) * kV2Mels + m] = s1;
-      part[(g * 2 + 1) * kV2Mels + m] = s2;
-    }
-    __syncthreads();
-
-    // ---- phase C2: coalesced float4 stores + per-utterance CMVN statistics ----
-    {
-      float4* dst = reinterpret_cast<float4*>(P.out + cur.out_row * (int64_t)kV2Mels);
-      const int total4 = nf * (kV2Mels / 4);
-      for (int q = tid; q < total4; q += kFastThreads) {
-        const int f = q / (kV2Mels / 4), m4 = q - f * (kV2Mels / 4);
-        dst[q] = *reinterpret_cast<const float4*>(stage + f * kV2StageStride + 4 * m4);
+      if (P.utt_stats != nullptr) {
+        part[(g * 2) * kV2Mels + m] = s1;
+        part[(g * 2 + 1) * kV2Mels + m] = s2;
       }
-      if (P.utt_stats != nullptr && tid < 2 * kV2Mels) {
-        const int m = tid % kV2Mels, which = tid / kV2Mels;
-        const double s = (double)part[which * kV2Mels + m] + (double)part[(2 + which) * kV2Mels + m] +
+    }
+    __syncthreads();   // the next tile's geometry (thread 0, above) and the partial sums are visible
+    // per-utterance CMVN statistics: one double atomic per (filter, moment)
+    if (P.utt_stats != nullptr && tid < 2 * kV2Mels) {
+      const int m = tid % kV2Mels, which = tid / kV2Mels;
+      const double sum = (double)part[which * kV2Mels + m] + (double)part[(2 + which) * kV2Mels + m] +
                          (double)part[(4 + which) * kV2Mels + m];
-        atomicAdd(&P.utt_stats[((size_t)utt * 2 + which) * kV2Mels + m], s);
-      }
+      atomicAdd(&P.utt_stats[((size_t)utt * 2 + which) * kV2Mels + m], sum);
     }
-    __syncthreads();  // stage (Z), planes and ybuf are rewritten by the next iteration
   }
 }
 
