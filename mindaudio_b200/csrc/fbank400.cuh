@@ -6,9 +6,11 @@
 // Same machinery as the 512-point kernel (persistent CTAs, dynamic tile queue, staged next-tile preparation, TMA
 // bulk load of the waveform tile, frame pairs packed a + i*b, lanes = frames for the sparse mel sweep), with a
 // 400 = 25 x 16 FFT: every lane of a 16-lane group transforms 25 points in registers (5 x 5), the 16-point stage
-// runs as 50 independent 16-point DFTs per warp (two rounds of 32 lanes), and the mel sweep is table driven
-// (any filterbank with <= 2 adjacent filters per bin).  Output: mel energies or log-mel (dB / ln); the top_db clamp
-// and the DCT of MFCC run in the existing follow-up kernels (db_clamp_kernel, dct_kernel).
+// runs as 50 independent 16-point DFTs per warp (two rounds of 32 lanes), and the mel sweep is the table-driven,
+// cost-balanced rolled loop of fbank512_v3.cuh (any filterbank with <= 2 adjacent filters per bin).  Centre padding
+// is written in place by a short pad pass in the first / last tile of an utterance, so the frame loads are one code
+// path.  Output: mel energies or log-mel (dB / ln), stored straight from the combine phase; the top_db clamp and
+// the DCT of MFCC run in the existing follow-up kernels (db_clamp_kernel, dct_kernel).
 #pragma once
 #include "fft400.cuh"
 
@@ -16,22 +18,23 @@ namespace mafe {
 
 constexpr int kN400 = 400;
 constexpr int kBins400 = 201;
-constexpr int kSlot400 = 425;                     // 25 rows x 17 (transpose) >= 400 outputs; 425*8 B = 18 banks mod 32
+constexpr int kSlot400 = 425;                     // 25 rows x 17 (transpose) >= 401 outputs; 425*8 B = 18 banks mod 32
 constexpr int kRaw400Bytes = 26496;               // (31 * 200 + 400) * 4 + slack, 128 B multiple
 constexpr int kZ400Bytes = kPairs * kSlot400 * 8; // 54 400
 constexpr int kRaw400InZ = kZ400Bytes - kRaw400Bytes;   // 27 904: the waveform tile lands in the upper part of Z
 constexpr int kMaxHop400 = 200;
 constexpr int kMaxMels400 = 128;
-constexpr int kBinsPerWarp400 = 26;               // 8 warps x 26 >= 201 bins
+constexpr int kMaxRows400 = kMaxMels400 + 2 + 2 * (kFastWarps - 1) + 1;   // compact planes: emitted filters + zero row
 static_assert(kRaw400InZ % 128 == 0, "raw landing zone alignment");
 
-struct Step400 {
-  float w0, w1;      // weights of filters cur / cur + 1 (pre-scaled: the pair separation leaves 2X, window carries 1/2)
-  uint32_t offs;     // byte offsets of Z[k] (low 16) and Z[400 - k] (high 16) inside the pair's slot
-  int nflush;        // filters to retire before this bin is accumulated
-};
-struct Hdr400 {
-  int lo, nsteps, tail, pad;
+// Sweep program (see V3Sweep in fbank512_v3.cuh): warp w owns bins kk0[w] .. kk0[w+1]-1; step k first retires nret
+// filters, then accumulates bin k into filters (cur, cur + 1) with weights (w0, w1).  Cost balanced on the host.
+struct F400Sweep {
+  V3Step step[kBins400 + 3];
+  unsigned char tail[kFastWarps];
+  unsigned char kk0[kFastWarps + 1];
+  unsigned char row0[kFastWarps];
+  int zero_row;
 };
 
 struct F400Params {
@@ -46,75 +49,44 @@ struct F400Params {
   float log_arg, log_mult, log_offset;
   const float* window;     // [400], pre-scaled by spec_scale * wave_scale * 1/2
   const float2* tw400;     // [25][16]  W400^(t kj)
-  const Step400* steps;    // [8][32]
-  const Hdr400* hdr;       // [8]
-  const int* combine;      // [n_mels]
+  const int* combine;      // [n_mels]: plane rows A | B << 8 holding the filter's partial sums
   float* out;              // [total_frames][n_mels]
   int* queue_head;
   int* group_max;          // dB maxima (ordered-int keys) or null
   const int* utt_group;
   int db_group;
+  int plane_rows;          // rows of the compact mel planes incl. the zero row
   float2 tw25[16];         // W25^(j1 k1), j1,k1 = 1..4: kernel-parameter constant bank
 };
 
 struct F400TileInfo {
   int64_t out_row, p_lo, u_lo, off, L, cov_end, end_elem, base_elem;
-  int nf, shift, n_loaded, edge, utt, pad;
+  int nf, shift, n_loaded, lpad, utt, tile_len;
 };
 static_assert(sizeof(F400TileInfo) <= 96, "F400TileInfo slot");
 
-// dynamic shared memory: [Z 54400][planes (2*(nm+2)*33+33)*4][window 1600][tw400 3200][steps 4096][hdr 128][bars 32][info 192]
-__host__ __device__ inline size_t f400_planes_bytes(int nm) { return (size_t)(2 * (nm + 2) * kPlaneStride + kPlaneStride) * 4; }
-__host__ __device__ inline size_t f400_smem_bytes(int nm) {
-  return kZ400Bytes + ((f400_planes_bytes(nm) + 15) & ~(size_t)15) + 1600 + 3200 + 4096 + 128 + 32 + 192;
-}
+// dynamic shared memory: [Z 54400][planes rows*33*4][window 1600][tw400 3200][bars 32][info 192]
+__host__ __device__ inline size_t f400_planes_bytes(int rows) { return ((size_t)rows * kPlaneStride * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t f400_smem_bytes(int rows) { return kZ400Bytes + f400_planes_bytes(rows) + 1600 + 3200 + 32 + 192; }
 
-template <int HALFDUMMY = 0>
-__device__ __forceinline__ void sweep400(const Step400* steps, int nsteps, int tail, const unsigned char* zp, float sgn, float* dst) {
-  float acc_lo = 0.f, acc_hi = 0.f;
-  for (int s = 0; s < nsteps; ++s) {
-    const Step400 st = steps[s];
-    int nf = st.nflush;
-    while (__any_sync(0xffffffffu, nf > 0)) {   // table-driven => warp-uniform; the vote tells the compiler
-      *dst = acc_lo;
-      acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride; --nf;
-    }
-    const float2 zk = *reinterpret_cast<const float2*>(zp + (st.offs & 0xffffu));
-    const float2 zn = *reinterpret_cast<const float2*>(zp + (st.offs >> 16));
-    const float re = fmaf(sgn, zn.x, zk.x);
-    const float im = fmaf(-sgn, zn.y, zk.y);
-    const float pw = fmaf(re, re, im * im);
-    acc_lo = fmaf(st.w0, pw, acc_lo);
-    acc_hi = fmaf(st.w1, pw, acc_hi);
-  }
-  while (__any_sync(0xffffffffu, tail > 0)) {
-    *dst = acc_lo;
-    acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride; --tail;
-  }
-}
-
-__global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Params P) {
+__global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_constant__ F400Params P,
+                                                                   const __grid_constant__ F400Sweep S) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int nm = P.n_mels;
   float2* Zs = reinterpret_cast<float2*>(smem);
   float* rawz = reinterpret_cast<float*>(smem + kRaw400InZ);
-  float* stage = reinterpret_cast<float*>(smem);
   float* planes = reinterpret_cast<float*>(smem + kZ400Bytes);
-  unsigned char* tail_base = smem + kZ400Bytes + ((f400_planes_bytes(nm) + 15) & ~(size_t)15);
+  unsigned char* tail_base = smem + kZ400Bytes + f400_planes_bytes(P.plane_rows);
   float* s_win = reinterpret_cast<float*>(tail_base);
   float2* s_tw = reinterpret_cast<float2*>(tail_base + 1600);
-  Step400* s_steps = reinterpret_cast<Step400*>(tail_base + 1600 + 3200);
-  Hdr400* s_hdr = reinterpret_cast<Hdr400*>(tail_base + 1600 + 3200 + 4096);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail_base + 1600 + 3200 + 4096 + 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail_base + 1600 + 3200);
   int* s_work = reinterpret_cast<int*>(bars) + 4;
-  F400TileInfo* info = reinterpret_cast<F400TileInfo*>(tail_base + 1600 + 3200 + 4096 + 128 + 32);
-  const int stage_stride = (nm + 4) & ~3;   // floats per staged frame row (16 B multiple)
+  F400TileInfo* info = reinterpret_cast<F400TileInfo*>(tail_base + 1600 + 3200 + 32);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
   for (int i = tid; i < kN400; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.tw400[i]; }
-  for (int i = tid; i < kFastWarps * 32; i += kFastThreads) s_steps[i] = P.steps[i];
-  if (tid < kFastWarps) s_hdr[tid] = P.hdr[tid];
+  if (tid < kPlaneStride) planes[S.zero_row * kPlaneStride + tid] = 0.f;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -123,6 +95,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
   __syncthreads();
 
   // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh) ----
+  // Centre padding: the first tile of an utterance lands `pad` floats into the buffer and the last one leaves room
+  // behind the data, so that a short "pad pass" can write the reflected / replicated / zero samples in place and the
+  // frame loads are the same code for every tile.
   int nx_w = P.n_tiles;
   Tile nx_tile = {0, 0};
   int64_t nx_off = 0, nx_off1 = 0, nx_fo0 = 0, nx_fo1 = 0;
@@ -140,7 +115,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
     const int64_t p_lo = (int64_t)nx_tile.frame0 * hop - pad;
     const int64_t p_hi = p_lo + (int64_t)(nf - 1) * hop + kN400;
     const int64_t u_lo = p_lo < 0 ? 0 : p_lo, u_hi = p_hi > L ? L : p_hi;
-    const int64_t g_lo = nx_off + u_lo, g_hi = nx_off + u_hi;
+    const int lpad = (int)(u_lo - p_lo);   // 0 or pad (200 floats = 800 B: keeps the 16 B alignment of the bulk copy)
+    const int64_t g_lo = nx_off + u_lo, g_hi = nx_off + (u_hi > u_lo ? u_hi : u_lo);
     const int64_t ga = (g_lo * 4) & ~(int64_t)15;
     const int64_t total16 = (P.total_samples * 4) & ~(int64_t)15;
     int64_t gb = (g_hi * 4 + 15) & ~(int64_t)15;
@@ -149,7 +125,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
       mbar_expect_tx(&bars[slot], bytes);
-      tma_bulk_g2s(rawz, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+      tma_bulk_g2s(rawz + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
     } else {
       mbar_arrive(&bars[slot]);
     }
@@ -161,9 +137,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
     ti_.end_elem = g_hi;
     ti_.nf = nf;
     ti_.shift = (int)(g_lo - ga / 4);
-    ti_.n_loaded = (int)(u_hi - u_lo);
-    ti_.edge = (p_lo < 0 || p_hi > L) ? 1 : 0;
-    ti_.utt = nx_tile.utt; ti_.pad = 0;
+    ti_.n_loaded = (int)(g_hi - g_lo);
+    ti_.lpad = lpad;
+    ti_.utt = nx_tile.utt;
+    ti_.tile_len = (nf - 1) * hop + kN400;
     info[slot] = ti_;
   };
   if (tid == 0) {
@@ -177,41 +154,49 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
   int buf = 0;
   const int t = lane & 15;
   const int pair = warp * 2 + (lane >> 4);
-  const int planes_rows = nm + 2;
+  // combine role of this thread: (frame group cg, filter cm)
+  const int G = kFastThreads / nm;                  // frame groups (nm <= 128 -> G >= 2)
+  const int cg = tid / nm, cm = tid - cg * nm;
+  const int crow = cg < G ? P.combine[cm] : 0;
   for (;; buf ^= 1) {
     if (s_work[buf] >= P.n_tiles) break;
     if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1: claim
     const F400TileInfo cur = info[buf];
     if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
-    if (cur.cov_end < cur.end_elem) {
-      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rawz[e - cur.base_elem] = P.wave[e];
+    float* xr = rawz + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
+    if (cur.cov_end < cur.end_elem) {   // bytes the 16 B-granular bulk copy could not cover (end of the flat array)
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rawz[cur.lpad + (e - cur.base_elem)] = P.wave[e];
+      __syncthreads();
+    }
+    if (cur.lpad > 0 || cur.lpad + cur.n_loaded < cur.tile_len) {
+      // ---- pad pass (first / last tile of an utterance): padded samples outside the loaded range, in place ----
+      const int d_end = cur.lpad + cur.n_loaded;
+      const int n_fill = cur.lpad + (cur.tile_len - d_end);
+#pragma unroll 1
+      for (int e = tid; e < n_fill; e += kFastThreads) {
+        const int i = e < cur.lpad ? e : d_end + (e - cur.lpad);
+        const int64_t u = pad_index_fast(cur.p_lo + i, cur.L, P.pad_mode);
+        float x = 0.f;
+        if (u >= 0) {
+          const int64_t r = u - cur.u_lo;
+          x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
+        }
+        xr[i] = x;
+      }
       __syncthreads();
     }
 
     // ---- load: frame pair -> 25 windowed complex points per lane ----
     cpx v[25];
     {
-      const int ia = (2 * pair) * hop, ib = ia + hop;
+      const float* xa = xr + (2 * pair) * hop + t;
+      const float* xb = xa + hop;
       const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
-      const float* xr = rawz + cur.shift;   // xr[i] = utterance sample u_lo + i
-      auto sample = [&](int i) -> float {   // padded sample at tile-relative index i (edge tiles only)
-        const int64_t u = pad_index_fast(cur.p_lo + i, cur.L, P.pad_mode);
-        if (u < 0) return 0.f;
-        const int64_t r = u - cur.u_lo;
-        return (r >= 0 && r < cur.n_loaded) ? xr[r] : __ldg(P.wave + cur.off + u);
-      };
 #pragma unroll
       for (int j = 0; j < 25; ++j) {
-        const int n = t + 16 * j;
-        float a, b;
-        if (!cur.edge) {
-          a = fa_ok ? xr[ia + n] : 0.f;
-          b = fb_ok ? xr[ib + n] : 0.f;
-        } else {
-          a = fa_ok ? sample(ia + n) : 0.f;
-          b = fb_ok ? sample(ib + n) : 0.f;
-        }
-        const float w = s_win[n];
+        const float a = fa_ok ? xa[16 * j] : 0.f;
+        const float b = fb_ok ? xb[16 * j] : 0.f;
+        const float w = s_win[t + 16 * j];
         v[j] = cx(a * w, b * w);
       }
     }
@@ -266,40 +251,63 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
           d1[kj1 + 25 * kt] = make_float2(y.x, y.y);
         }
       }
+      if (kj0 == 0) d0[kN400] = make_float2(u0[fft16_pos(0)].x, u0[fft16_pos(0)].y);   // bin 0 again: its own partner
     }
     __syncthreads();   // every pair's spectrum is in its slot
 
-    // ---- sweep: lanes = frames, this warp's 26 bins ----
+    // ---- sweep: lanes = frames, this warp's bin range (one rolled loop, program in the parameter bank) ----
     {
-      const Hdr400 hdr = s_hdr[warp];
-      const unsigned char* zp = reinterpret_cast<const unsigned char*>(Zs + (lane >> 1) * kSlot400);
+      const float2* zp = Zs + (lane >> 1) * kSlot400;
       const float sgn = (lane & 1) ? -1.f : 1.f;
-      float* dst = planes + (warp & 1) * (planes_rows * kPlaneStride) + (hdr.lo + 1) * kPlaneStride + lane;
-      sweep400(s_steps + warp * 32, hdr.nsteps, hdr.tail, zp, sgn, dst);
-      if (tid >= kFastThreads - 32) planes[2 * planes_rows * kPlaneStride + lane] = 0.f;   // the all-zero row
+      float* dst = planes + (int)S.row0[warp] * kPlaneStride + lane;
+      const int k0 = S.kk0[warp];
+      uint32_t ak = smem_u32(zp + k0);
+      uint32_t an = smem_u32(zp + kN400 - k0);
+      int si = k0;
+      const int si_end = S.kk0[warp + 1];
+      float acc_lo = 0.f, acc_hi = 0.f;
+      auto retire = [&](int n) {
+#pragma unroll 1
+        do {
+          *dst = acc_lo;
+          acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride;
+        } while (--n);
+      };
+#pragma unroll 1
+      do {
+        const V3Step st = S.step[si];
+        if (st.nret) retire(st.nret);
+        const float2 zk = lds_f2(ak);
+        const float2 zn = lds_f2(an);
+        bump<1>(si); bump<8>(ak); bump<-8>(an);
+        const float re = fmaf(sgn, zn.x, zk.x);
+        const float im = fmaf(-sgn, zn.y, zk.y);
+        const float pw = fmaf(re, re, im * im);
+        acc_lo = fmaf(st.w0, pw, acc_lo);
+        acc_hi = fmaf(st.w1, pw, acc_hi);
+      } while (si != si_end);
+      retire(S.tail[warp]);
     }
     __syncthreads();   // Z has been read for the last time
     if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4: next tile's waveform into the upper Z region
 
-    // ---- combine, log, stage [frame][nm], track the dB maximum ----
+    // ---- combine, log, store straight to global memory (a frame group writes nm contiguous floats per frame),
+    //      track the dB maximum ----
     {
-      const int G = kFastThreads / nm;              // frame groups (nm <= 128 -> G >= 2)
-      const int g = tid / nm, m = tid - g * nm;
       float vmax = -INFINITY;
-      if (g < G) {
-        const int c = P.combine[m];
-        const int n = c & 3, p0 = (c >> 2) & 1;
-        const float* zero_row = planes + 2 * planes_rows * kPlaneStride;
-        const float* pa = n >= 1 ? planes + p0 * (planes_rows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
-        const float* pb = n == 2 ? planes + (p0 ^ 1) * (planes_rows * kPlaneStride) + (m + 1) * kPlaneStride : zero_row;
-        for (int f = g; f < kTileFrames; f += G) {
+      if (cg < G) {
+        const float* pa = planes + (crow & 0xff) * kPlaneStride;
+        const float* pb = planes + (crow >> 8) * kPlaneStride;
+        float* od = P.out + cur.out_row * (int64_t)nm + cm;
+#pragma unroll 2
+        for (int f = cg; f < cur.nf; f += G) {
           const float e = pa[f] + pb[f];
           float o = e;
           if (P.log_kind == MAFE_LOG_DB) {
             float l2;
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(e, P.log_arg)));
             o = fmaf(P.log_mult * 0.30102999566398119521f, l2, -P.log_offset);
-            if (f < cur.nf) vmax = fmaxf(vmax, o);
+            vmax = fmaxf(vmax, o);
           } else if (P.log_kind == MAFE_LOG_LN_PLUS) {
             float l2;
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e + P.log_arg));
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e == 0.f ? 2.220446049250313e-16f : e));
             o = l2 * 0.69314718055994530942f;
           }
-          stage[f * stage_stride + m] = o;
+          od[(int64_t)f * nm] = o;
         }
       }
       if (P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE) {
@@ -320,16 +328,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const F400Par
         }
       }
     }
-    __syncthreads();
-    {
-      float* dst = P.out + cur.out_row * (int64_t)nm;
-      const int total = cur.nf * nm;
-      for (int e = tid; e < total; e += kFastThreads) {
-        const int f = e / nm, m = e - f * nm;
-        dst[e] = stage[f * stage_stride + m];
-      }
-    }
-    __syncthreads();   // staging (lower Z) and planes are free again; s_work / info of the next tile are visible
+    __syncthreads();   // planes are free again; s_work / info of the next tile are visible
   }
 }
 

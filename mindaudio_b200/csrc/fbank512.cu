@@ -331,8 +331,7 @@ struct FastTablesHost {
   bool stft = false;      // n_fft = 512 complex STFT plan (stft512_kernel)
   bool f400 = false;      // n_fft = 400 mel front-end plan (fbank400_kernel)
   float2* tw400_dev = nullptr;
-  Step400* steps400_dev = nullptr;
-  Hdr400* hdr400_dev = nullptr;
+  F400Sweep sweep400;     // sweep program of fbank400_kernel (kernel-parameter bank)
   float2 tw25[16];
   bool tile_geom = false; // conformer geometry (400 / 160 / 512 / 80 filters): the v3 kernel and its pre-pass apply
   V3Sweep sweep;          // sweep program of the v3 kernel (kernel-parameter bank)
@@ -464,6 +463,65 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
   return true;
 }
 
+// Same for the one-pass sweep of fbank400_kernel: bins 0 .. 200 split into 8 cost-balanced contiguous warp ranges.
+static bool build_f400_program(const std::vector<BinEntry>& bins, int nm, F400Sweep& S, std::vector<int>& comb) {
+  memset(&S, 0, sizeof(S));
+  comb.assign(nm, 0);
+  constexpr int NK = kBins400, W = kFastWarps;
+  constexpr int c_bin = 17, c_ret = 7;
+  auto lo_of = [&](int a) { return bins[a].f0; };
+  auto hi_of = [&](int b) { return bins[b - 1].f0 + 1; };
+  auto cost = [&](int a, int b) -> long {
+    if (a > 0 && b < NK && bins[b].f0 - bins[a - 1].f0 < 2) return -1;   // a filter is emitted by <= 2 adjacent warps
+    return (long)c_bin * (b - a) + (long)c_ret * (hi_of(b) - lo_of(a) + 1);
+  };
+  const long INF = 1L << 60;
+  std::vector<std::vector<long>> best(W + 1, std::vector<long>(NK + 1, INF));
+  std::vector<std::vector<int>> from(W + 1, std::vector<int>(NK + 1, -1));
+  best[0][0] = 0;
+  for (int w = 1; w <= W; ++w)
+    for (int b = w; b <= NK; ++b)
+      for (int a = w - 1; a < b; ++a) {
+        if (best[w - 1][a] == INF) continue;
+        const long c = cost(a, b);
+        if (c < 0) continue;
+        const long v = std::max(best[w - 1][a], c);
+        if (v < best[w][b]) { best[w][b] = v; from[w][b] = a; }
+      }
+  if (best[W][NK] == INF) return false;
+  int edge[W + 1];
+  edge[W] = NK;
+  for (int w = W; w > 0; --w) edge[w - 1] = from[w][edge[w]];
+  int rows = 0;
+  std::vector<int> nrow(nm, 0);
+  for (int w = 0; w < W; ++w) {
+    const int a = edge[w], b = edge[w + 1];
+    const int lo = lo_of(a), hi = hi_of(b);
+    S.kk0[w] = (unsigned char)a;
+    S.kk0[w + 1] = (unsigned char)b;
+    S.row0[w] = (unsigned char)rows;
+    for (int m = lo; m <= hi; ++m, ++rows)
+      if (m >= 0 && m < nm) {
+        if (nrow[m] >= 2) return false;
+        comb[m] |= rows << (8 * nrow[m]);
+        ++nrow[m];
+      }
+    int cur = lo;
+    for (int k = a; k < b; ++k) {
+      S.step[k] = V3Step{bins[k].w0, bins[k].w1, bins[k].f0 - cur, 0};
+      cur = bins[k].f0;
+    }
+    S.tail[w] = (unsigned char)(hi - cur + 1);
+  }
+  if (rows >= kMaxRows400 || rows > 254) return false;
+  S.zero_row = rows;
+  for (int m = 0; m < nm; ++m) {
+    if (nrow[m] == 0) comb[m] = rows | (rows << 8);
+    else if (nrow[m] == 1) comb[m] |= rows << 8;
+  }
+  return true;
+}
+
 static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector<int2>& ranges, std::vector<int>& comb) {
   return build_combine_n(bins, nm, kBins, 32, ranges, comb);
 }
@@ -479,9 +537,9 @@ static bool f400_plan_supported(const mafe_frontend_desc* d) {
   if (d->power != 2.0f || d->preemph != 0.0 || d->remove_frame_mean || d->dither != 0.f) return false;
   if (d->n_mels < 2 || d->n_mels > kMaxMels400) return false;
   std::vector<BinEntry> bins;
-  std::vector<int2> ranges;
   std::vector<int> comb;
-  return build_bins_n(d, kBins400, 1.0f, bins) && build_combine_n(bins, d->n_mels, kBins400, kBinsPerWarp400, ranges, comb);
+  F400Sweep sw;
+  return build_bins_n(d, kBins400, 1.0f, bins) && build_f400_program(bins, d->n_mels, sw, comb);
 }
 
 bool fast_plan_supported(const mafe_frontend_desc* d) {
@@ -543,33 +601,15 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
         th->tw25[(j1 - 1) * 4 + (k1 - 1)] = make_float2((float)cos(a), (float)sin(a));
       }
     std::vector<BinEntry> bins;
-    std::vector<int2> ranges;
     std::vector<int> comb;
-    if (!build_bins_n(d, kBins400, 1.0f, bins) || !build_combine_n(bins, d->n_mels, kBins400, kBinsPerWarp400, ranges, comb)) {
+    if (!build_bins_n(d, kBins400, 1.0f, bins) || !build_f400_program(bins, d->n_mels, th->sweep400, comb)) {
       set_error("filterbank is not in per-bin form");
       return MAFE_E_UNSUPPORTED;
     }
-    std::vector<Step400> steps(kFastWarps * 32, Step400{0.f, 0.f, 0u, 0});
-    std::vector<Hdr400> hdr(kFastWarps);
-    for (int w = 0; w < kFastWarps; ++w) {
-      const int k_lo = kBinsPerWarp400 * w, k_hi = (w == kFastWarps - 1) ? kBins400 : std::min(k_lo + kBinsPerWarp400, kBins400);
-      int cur = ranges[w].x, n = 0;
-      for (int k = k_lo; k < k_hi; ++k, ++n) {
-        Step400 st;
-        st.w0 = bins[k].w0; st.w1 = bins[k].w1;
-        st.offs = (uint32_t)(k * 8) | ((uint32_t)(((kN400 - k) % kN400) * 8) << 16);
-        st.nflush = bins[k].f0 - cur;
-        cur = bins[k].f0;
-        steps[w * 32 + n] = st;
-      }
-      hdr[w] = Hdr400{ranges[w].x, n, n ? ranges[w].y - cur + 1 : 0, 0};
-    }
     if ((rc = up(&th->dev.window, w400))) return rc;
     if ((rc = up(&th->tw400_dev, tw400))) return rc;
-    if ((rc = up(&th->steps400_dev, steps))) return rc;
-    if ((rc = up(&th->hdr400_dev, hdr))) return rc;
     if ((rc = up(&th->dev.combine, comb))) return rc;
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f400_smem_bytes(kMaxMels400)));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f400_smem_bytes(kMaxRows400)));
     return MAFE_OK;
   }
   if (th->stft) {
@@ -619,7 +659,7 @@ void fast_plan_free(mafe_plan* p) {
   cudaFree(th->dev.window); cudaFree(th->dev.w512); cudaFree(th->dev.w256t);
   cudaFree(th->dev.bins); cudaFree(th->dev.warp_range); cudaFree(th->dev.combine); cudaFree(th->dev.cover);
   cudaFree(th->comb3_dev);
-  cudaFree(th->tw400_dev); cudaFree(th->steps400_dev); cudaFree(th->hdr400_dev);
+  cudaFree(th->tw400_dev);
   delete th;
   p->fast_tables = nullptr;
 }
@@ -642,7 +682,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     F.n_tiles = b->n_tiles; F.hop = d.hop; F.center = d.center; F.pad_mode = d.pad_mode; F.n_mels = d.n_mels;
     F.log_kind = d.out_kind == MAFE_OUT_MEL ? MAFE_LOG_NONE : d.log_kind;
     F.log_arg = d.log_arg; F.log_mult = d.log_mult; F.log_offset = d.log_offset;
-    F.window = th->dev.window; F.tw400 = th->tw400_dev; F.steps = th->steps400_dev; F.hdr = th->hdr400_dev;
+    F.window = th->dev.window; F.tw400 = th->tw400_dev; F.plane_rows = th->sweep400.zero_row + 1;
     F.combine = th->dev.combine; F.out = out; F.queue_head = b->queue_dev;
     F.db_group = (d.log_kind == MAFE_LOG_DB && d.top_db >= 0.f && d.out_kind != MAFE_OUT_MEL) ? db_group : MAFE_DBGROUP_NONE;
     F.group_max = b->group_max_dev; F.utt_group = b->utt_group_dev;
@@ -654,7 +694,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-    fbank400_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, f400_smem_bytes(d.n_mels), ctx->stream>>>(F);
+    fbank400_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, f400_smem_bytes(F.plane_rows), ctx->stream>>>(F, th->sweep400);
     MAFE_LAUNCH_CHECK(ctx);
     return kFastNeedsPost;
   }
