@@ -220,31 +220,97 @@ __global__ void db_clamp_kernel(float* data, int dim, const Tile* tiles, const i
 }
 
 // MFCC: out[f][c] = sum_m clamp(logmel[f][m]) * dct[m][c]   (features.py:356-361)
-__global__ void dct_kernel(const float* logmel, float* out, int n_mels, int n_mfcc, const float* dct, const Tile* tiles,
-                           const int64_t* frame_offsets, int tile_frames, const int* group_max, const int* utt_group,
-                           int db_group, float top_db) {
-  extern __shared__ float sm[];
-  float* sd = sm;                       // [n_mels][n_mfcc]
-  float* sx = sm + n_mels * n_mfcc;     // [tile_frames][n_mels]
-  const Tile tile = tiles[blockIdx.x];
-  const int64_t fo = frame_offsets[tile.utt];
-  const int64_t T = frame_offsets[tile.utt + 1] - fo;
-  int nf = (int)min((int64_t)tile_frames, T - tile.frame0);
-  float floor_v = -INFINITY;
-  if (db_group != MAFE_DBGROUP_NONE) {
-    int g = db_group == MAFE_DBGROUP_UTT ? tile.utt : (db_group == MAFE_DBGROUP_BATCH ? 0 : utt_group[tile.utt]);
-    floor_v = key_to_float(group_max[g]) - top_db;
+// Register-tiled small GEMM.  A CTA walks groups of 4 tiles (<= 128 frames): the (clamped) log-mel rows are transposed
+// into shared memory [m][frame], the DCT table (zero padded to 8*CPT columns) is loaded once per CTA; thread
+// (frame quad fq, coefficient group cg) keeps 4 x CPT accumulators: per mel bin one 16-byte load of 4 frames and CPT
+// table values feed 4*CPT FMAs.
+constexpr int kDctFrames = 128;
+constexpr int kDctXStride = kDctFrames + 4;   // 16 B aligned rows
+template <int CPT>
+__global__ void __launch_bounds__(256) dct_kernel(const float* __restrict__ logmel, float* __restrict__ out, int n_mels, int n_mfcc,
+                                                  const float* __restrict__ dct, const Tile* __restrict__ tiles, int n_tiles,
+                                                  const int64_t* __restrict__ frame_offsets, int tile_frames,
+                                                  const int* __restrict__ group_max, const int* __restrict__ utt_group, int db_group,
+                                                  float top_db) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NCP = 8 * CPT;
+  float* sd = sm;                         // [n_mels][NCP]
+  float* sx = sm + n_mels * NCP;          // [n_mels][kDctXStride]
+  __shared__ int64_t s_row[kDctFrames / 2];   // first output row of each tile of the group (tiles hold >= 2 frames)
+  __shared__ int s_nf[kDctFrames / 2];
+  __shared__ float s_floor[kDctFrames / 2];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_mels * NCP; i += 256) {
+    const int m = i / NCP, c = i - m * NCP;
+    sd[i] = c < n_mfcc ? dct[m * n_mfcc + c] : 0.f;
   }
-  for (int i = threadIdx.x; i < n_mels * n_mfcc; i += blockDim.x) sd[i] = dct[i];
-  const float* src = logmel + (fo + tile.frame0) * n_mels;
-  for (int i = threadIdx.x; i < nf * n_mels; i += blockDim.x) sx[i] = fmaxf(src[i], floor_v);
-  __syncthreads();
-  float* dst = out + (fo + tile.frame0) * n_mfcc;
-  for (int i = threadIdx.x; i < nf * n_mfcc; i += blockDim.x) {
-    int f = i / n_mfcc, c = i - f * n_mfcc;
-    float acc = 0.f;
-    for (int m = 0; m < n_mels; ++m) acc = fmaf(sx[f * n_mels + m], sd[m * n_mfcc + c], acc);
-    dst[i] = acc;
+  const int fq = tid >> 3, cg = tid & 7;
+  const int tiles_per_group = kDctFrames / tile_frames;   // tile_frames = 32 -> 4; always >= 1 (tile_frames <= 32)
+  const int group_frames = tiles_per_group * tile_frames;
+  const int n_groups = (n_tiles + tiles_per_group - 1) / tiles_per_group;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    __syncthreads();   // previous group's sx / s_* are no longer read
+    if (tid < tiles_per_group) {
+      const int ti = grp * tiles_per_group + tid;
+      int nf = 0;
+      int64_t row = 0;
+      float fl = -INFINITY;
+      if (ti < n_tiles) {
+        const Tile tile = tiles[ti];
+        const int64_t fo = frame_offsets[tile.utt];
+        const int64_t T = frame_offsets[tile.utt + 1] - fo;
+        nf = (int)min((int64_t)tile_frames, T - tile.frame0);
+        row = fo + tile.frame0;
+        if (db_group != MAFE_DBGROUP_NONE) {
+          const int g = db_group == MAFE_DBGROUP_UTT ? tile.utt : (db_group == MAFE_DBGROUP_BATCH ? 0 : utt_group[tile.utt]);
+          fl = key_to_float(group_max[g]) - top_db;
+        }
+      }
+      s_row[tid] = row; s_nf[tid] = nf; s_floor[tid] = fl;
+    }
+    __syncthreads();
+    for (int q = 0; q < tiles_per_group; ++q) {
+      const int nf = s_nf[q];
+      const float fl = s_floor[q];
+      const float* src = logmel + s_row[q] * n_mels;
+      for (int i = tid; i < tile_frames * n_mels; i += 256) {
+        const int f = i / n_mels, m = i - f * n_mels;
+        sx[m * kDctXStride + q * tile_frames + f] = f < nf ? fmaxf(src[i], fl) : 0.f;
+      }
+    }
+    __syncthreads();
+    float acc[4][CPT];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) acc[j][i] = 0.f;
+    const float* xp = sx + 4 * fq;
+    const float* dp = sd + cg * CPT;
+#pragma unroll 4
+    for (int m = 0; m < n_mels; ++m) {
+      const float4 x = *reinterpret_cast<const float4*>(xp + m * kDctXStride);
+      float d[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) d[i] = dp[m * NCP + i];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        acc[0][i] = fmaf(x.x, d[i], acc[0][i]);
+        acc[1][i] = fmaf(x.y, d[i], acc[1][i]);
+        acc[2][i] = fmaf(x.z, d[i], acc[2][i]);
+        acc[3][i] = fmaf(x.w, d[i], acc[3][i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = 4 * fq + j;
+      if (idx >= group_frames) continue;
+      const int q = idx / tile_frames, f = idx - q * tile_frames;
+      if (f >= s_nf[q]) continue;
+      float* dst = out + (s_row[q] + f) * n_mfcc + cg * CPT;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i)
+        if (cg * CPT + i < n_mfcc) dst[i] = acc[j][i];
+    }
   }
 }
 
@@ -406,15 +472,31 @@ int db_clamp_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, float* data, 
 int dct_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const float* logmel, float* out, int db_group) {
   if (b->n_tiles == 0) return MAFE_OK;
   const int nm = p->d.n_mels, nc = p->d.n_mfcc;
-  size_t smem = sizeof(float) * ((size_t)nm * nc + (size_t)p->tile_frames * nm);
-  if (smem > 48 * 1024) {
-    MAFE_REQUIRE(smem <= 200 * 1024, "DCT table %dx%d does not fit in shared memory", nm, nc);
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MAFE_REQUIRE(nc <= 128 && p->tile_frames >= 2 && p->tile_frames <= kDctFrames, "MFCC: n_mfcc %d / tile of %d frames not supported", nc, p->tile_frames);
+  const int cpt_need = (nc + 7) / 8;
+  const int cpt = cpt_need <= 2 ? 2 : cpt_need <= 4 ? 4 : cpt_need <= 5 ? 5 : cpt_need <= 8 ? 8 : 16;
+  const size_t smem = sizeof(float) * ((size_t)nm * 8 * cpt + (size_t)nm * kDctXStride);
+  MAFE_REQUIRE(smem <= 200 * 1024, "DCT table %dx%d does not fit in shared memory", nm, nc);
+  const bool clamp = p->d.log_kind == MAFE_LOG_DB && p->d.top_db >= 0.f && db_group != MAFE_DBGROUP_NONE;
+  const int tpg = kDctFrames / p->tile_frames;
+  const int n_groups = (b->n_tiles + tpg - 1) / tpg;
+  const int grid = std::min(n_groups, 4 * ctx->sm_count);
+  auto launch = [&](auto kern) -> int {
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, ctx->stream>>>(logmel, out, nm, nc, p->dct_dev, b->tiles_dev, b->n_tiles, b->frame_offsets_dev,
+                                           p->tile_frames, b->group_max_dev, b->utt_group_dev,
+                                           clamp ? db_group : MAFE_DBGROUP_NONE, p->d.top_db);
+    return MAFE_OK;
+  };
+  int rc;
+  switch (cpt) {
+    case 2: rc = launch(dct_kernel<2>); break;
+    case 4: rc = launch(dct_kernel<4>); break;
+    case 5: rc = launch(dct_kernel<5>); break;
+    case 8: rc = launch(dct_kernel<8>); break;
+    default: rc = launch(dct_kernel<16>); break;
   }
-  bool clamp = p->d.log_kind == MAFE_LOG_DB && p->d.top_db >= 0.f && db_group != MAFE_DBGROUP_NONE;
-  dct_kernel<<<b->n_tiles, 256, smem, ctx->stream>>>(logmel, out, nm, nc, p->dct_dev, b->tiles_dev, b->frame_offsets_dev,
-                                                     p->tile_frames, b->group_max_dev, b->utt_group_dev,
-                                                     clamp ? db_group : MAFE_DBGROUP_NONE, p->d.top_db);
+  if (rc) return rc;
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }

@@ -55,6 +55,15 @@ def test_fbank_mfcc_deltas_context(ma, golden):
     assert mfcc_err(ma.mfcc(x3), R.mfcc(x3)) <= TOL_LOGMEL                                # 4-D context route
 
 
+@pytest.mark.parametrize("n_fft,n_mels,n_mfcc", [(1024, 40, 13), (600, 64, 20), (2048, 128, 64), (400, 128, 128), (512, 23, 23)])
+def test_mfcc_other_sizes(ma, n_fft, n_mels, n_mfcc):
+    """MFCC through every DCT tiling (coefficients per thread 2/4/5/8/16) and generic-kernel tile sizes (2..16 frames)."""
+    x = synth(21, (3, 12000)) * np.array([1.0, 0.02, 1.0], dtype=np.float32)[:, None]
+    kw = dict(deltas=False, context=False, n_fft=n_fft, n_mels=n_mels, n_mfcc=n_mfcc)
+    assert mfcc_err(ma.mfcc(x, **kw), R.mfcc(x, **kw)) <= TOL_LOGMEL
+    assert mfcc_err(ma.mfcc(x[0], log_mels=True, **kw), R.mfcc(x[0], log_mels=True, **kw)) <= TOL_LOGMEL
+
+
 def test_deltas_and_context_standalone(ma, golden):
     fb = R.fbank(golden.wav(), n_mels=80, n_fft=400, hop_length=160)
     d = ma.compute_deltas(fb[:, :100], win_length=7, pad_mode="reflect")
