@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fft512.cuh"

@@ -1,12 +1,13 @@
 // stft512.cuh -- specialised STFT kernel for n_fft = 512 (spectrum.stft, mindaudio/data/spectrum.py:125-278,
 // e.g. BASELINE.json configs[1]: hop 256, hann, centred): complex64 [frame][257] out.  Included by fbank512.cu.
 //
-// HBM-bound path (hop*4 B in, 2056 B out per frame).  Same building blocks as the fbank kernel: persistent CTAs,
-// dynamic tile queue, staged next-tile preparation, TMA bulk prefetch of the waveform tile, frame PAIRS packed
-// as a + i*b, radix-2 fold + two 256-point register FFTs per pair.  Differences: no pre-emphasis / mean / mel;
-// every WARP owns two frame pairs from the load to the store (only __syncwarp inside a tile, one __syncthreads
-// per tile for the double-buffered waveform), and centre padding (constant / reflect / edge / symmetric) is an
-// index map that is only evaluated in the first / last tile of an utterance.
+// HBM-bound path (hop*4 B in, 2056 B out per frame).  Same building blocks as the fbank kernel: persistent CTAs
+// (2 per SM), dynamic tile queue, staged next-tile preparation, TMA bulk prefetch of the waveform tile, frame PAIRS
+// packed as a + i*b, radix-2 fold + two 256-point register FFTs per pair run through ONE rolled loop (the second
+// half re-reads the tile instead of holding 32 more registers).  Differences: no pre-emphasis / mean / mel; every
+// WARP owns two frame pairs from the load to the store (only __syncwarp between the phases of a half), and centre
+// padding (constant / reflect / edge / symmetric) is written in place by a short pad pass in the first / last tile
+// of an utterance, so the frame loads are one code path.
 #pragma once
 
 namespace mafe {
@@ -32,17 +33,19 @@ struct StftParams {
 struct StftTileInfo {
   int64_t out_row;     // first output frame of the tile
   int64_t p_lo;        // padded-signal index of the tile's first sample (may be negative)
-  int64_t u_lo;        // utterance index of raw element `shift`
+  int64_t u_lo;        // utterance index of the first loaded sample
   int64_t off, L;      // utterance start in the flat array / length
   int64_t cov_end, end_elem, base_elem;
-  int nf, shift, n_loaded, edge;
+  int nf, shift, n_loaded, lpad, tile_len, pad_;
 };
 static_assert(sizeof(StftTileInfo) <= 96, "StftTileInfo slot");
 
+constexpr int kStftSkew = kStftRawBytes / 4 + 16;   // floats from copy 0 to copy 1 of the tile: 16 banks apart
 struct StftSmem {
-  static constexpr size_t kRaw0 = 0;
-  static constexpr size_t kRaw1 = kStftRawBytes;
-  static constexpr size_t kZ = 2 * kStftRawBytes;
+  static constexpr size_t kRaw = 0;                    // the waveform tile TWICE: the two frame pairs a warp folds start
+                                                       // a multiple of 32 floats apart (hop 256), the upper half-warp
+                                                       // reads the skewed copy -> no 2-way bank conflicts
+  static constexpr size_t kZ = 2 * kStftRawBytes + 64;
   static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
   static constexpr size_t kWin = kZ + kZBytes;
   static constexpr size_t kW512 = kWin + sizeof(float) * kNfft;
@@ -53,9 +56,9 @@ struct StftSmem {
 };
 static_assert(StftSmem::kZ % 16 == 0 && StftSmem::kBar % 8 == 0, "smem alignment");
 
-__global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftParams P) {
+__global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_constant__ StftParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  auto raw_buf = [&](int b) -> float* { return reinterpret_cast<float*>(smem + (size_t)b * kStftRawBytes); };
+  float* rb = reinterpret_cast<float*>(smem + StftSmem::kRaw);
   float2* Zs = reinterpret_cast<float2*>(smem + StftSmem::kZ);
   float* s_win = reinterpret_cast<float*>(smem + StftSmem::kWin);
   float2* s_w512 = reinterpret_cast<float2*>(smem + StftSmem::kW512);
@@ -76,6 +79,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftPara
   __syncthreads();
 
   // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh) ----
+  // Centre padding: the first tile of an utterance lands `pad` floats into the buffer and the last one leaves room
+  // behind the data; the pad pass fills both in place.
   int nx_w = P.n_tiles;
   Tile nx_tile = {0, 0};
   int64_t nx_off = 0, nx_off1 = 0, nx_fo0 = 0, nx_fo1 = 0;
@@ -93,8 +98,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftPara
     const int64_t p_lo = (int64_t)nx_tile.frame0 * hop - pad;
     const int64_t p_hi = p_lo + (int64_t)(nf - 1) * hop + kNfft;
     const int64_t u_lo = p_lo < 0 ? 0 : p_lo, u_hi = p_hi > L ? L : p_hi;   // utterance samples inside the tile's span
+    const int lpad = (int)(u_lo - p_lo);   // 0 or pad (256 floats = 1 KB: keeps the 16 B alignment of the bulk copy)
     // bulk copy of the 16 B aligned superset of flat elements [off+u_lo, off+u_hi)
-    const int64_t g_lo = nx_off + u_lo, g_hi = nx_off + u_hi;
+    const int64_t g_lo = nx_off + u_lo, g_hi = nx_off + (u_hi > u_lo ? u_hi : u_lo);
     const int64_t ga = (g_lo * 4) & ~(int64_t)15;
     const int64_t total16 = (P.total_samples * 4) & ~(int64_t)15;
     int64_t gb = (g_hi * 4 + 15) & ~(int64_t)15;
@@ -102,8 +108,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftPara
     const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
-      mbar_expect_tx(&bars[slot], bytes);
-      tma_bulk_g2s(raw_buf(slot), (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+      mbar_expect_tx(&bars[slot], 2 * bytes);
+      tma_bulk_g2s(rb + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+      tma_bulk_g2s(rb + kStftSkew + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
     } else {
       mbar_arrive(&bars[slot]);
     }
@@ -118,8 +125,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftPara
     ti_.end_elem = g_hi;
     ti_.nf = nf;
     ti_.shift = (int)(g_lo - ga / 4);
-    ti_.n_loaded = (int)(u_hi - u_lo);
-    ti_.edge = (p_lo < 0 || p_hi > L) ? 1 : 0;
+    ti_.n_loaded = (int)(g_hi - g_lo);
+    ti_.lpad = lpad;
+    ti_.tile_len = (nf - 1) * hop + kNfft;
+    ti_.pad_ = 0;
     info[slot] = ti_;
   };
   if (tid == 0) {
@@ -139,75 +148,129 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const StftPara
     if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1: claim
     const StftTileInfo cur = info[buf];
     if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
-    float* rb = raw_buf(buf);
+    float* xr = rb + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
     if (cur.cov_end < cur.end_elem) {   // tail of the flat array the 16 B granule could not cover
-      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rb[e - cur.base_elem] = P.wave[e];
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
+        const float x = P.wave[e];
+        rb[cur.lpad + (e - cur.base_elem)] = x;
+        rb[kStftSkew + cur.lpad + (e - cur.base_elem)] = x;
+      }
       __syncthreads();
     }
-
-    // ---- fold: frame pair -> registers (window only; a = frame 2*pair, b = frame 2*pair+1) ----
-    cpx v0[16], v1[16];
-    {
-      // padded-signal index of frame a's first sample, relative to the tile start
-      const int ia = (2 * pair) * hop, ib = ia + hop;
-      const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
-      const float* xr = rb + cur.shift;   // xr[i] = utterance sample u_lo + i
-      auto sample = [&](int i) -> float {   // padded sample at tile-relative index i (edge tiles only)
+    if (cur.lpad > 0 || cur.lpad + cur.n_loaded < cur.tile_len) {
+      // ---- pad pass (first / last tile of an utterance): padded samples outside the loaded range, in place ----
+      const int d_end = cur.lpad + cur.n_loaded;
+      const int n_fill = cur.lpad + (cur.tile_len - d_end);
+#pragma unroll 1
+      for (int e = tid; e < n_fill; e += kFastThreads) {
+        const int i = e < cur.lpad ? e : d_end + (e - cur.lpad);
         const int64_t u = pad_index_fast(cur.p_lo + i, cur.L, P.pad_mode);
-        if (u < 0) return 0.f;
-        const int64_t r = u - cur.u_lo;
-        return (r >= 0 && r < cur.n_loaded) ? xr[r] : __ldg(P.wave + cur.off + u);
-      };
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = t + 16 * j;
-        float a0, b0, a1, b1;
-        if (!cur.edge) {
-          a0 = xr[ia + n]; a1 = xr[ia + n + 256];
-          b0 = fb_ok ? xr[ib + n] : 0.f; b1 = fb_ok ? xr[ib + n + 256] : 0.f;
-        } else {
-          a0 = fa_ok ? sample(ia + n) : 0.f; a1 = fa_ok ? sample(ia + n + 256) : 0.f;
-          b0 = fb_ok ? sample(ib + n) : 0.f; b1 = fb_ok ? sample(ib + n + 256) : 0.f;
+        float x = 0.f;
+        if (u >= 0) {
+          const int64_t r = u - cur.u_lo;
+          x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
         }
-        const float w0 = s_win[n], w1 = s_win[n + 256];
-        const cpx lo = cx(a0 * w0, b0 * w0), hi = cx(a1 * w1, b1 * w1);
-        const float2 tw = s_w512[n];
-        v0[j] = lo + hi;
-        v1[j] = cmulf(lo - hi, cx(tw.x, tw.y));
+        xr[i] = x;
+        xr[kStftSkew + i] = x;
       }
+      __syncthreads();
     }
-    __syncthreads();   // every warp has read raw[buf]: it may be refilled two iterations from now
-    if (tid == 0) {    // stage 2: publish the claim, fetch the tile record
-      s_work[buf ^ 1] = nx_w;
-      if (nx_w < P.n_tiles) nx_tile = P.tiles[nx_w];
-    }
+    const float* xa = xr + (lane >> 4) * kStftSkew + (2 * pair) * hop + t;
+    const float* xb = xa + hop;
+    const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 
-#pragma unroll
+    float2 hA[2][4], hB[2][4];   // even bins of the warp's two pairs, held until the odd bins exist
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      if (half == 0) fft256_group(v0, slot, s_w256, t); else fft256_group(v1, slot, s_w256, t);
-      __syncwarp();
-      if (half == 0 && tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3
-      // ---- emit: this warp's two pairs; lanes sweep the 128 (+1) bins of this half ----
+      // ---- fold: frame pair -> registers (window only; a = frame 2*pair, b = frame 2*pair+1) ----
+      cpx v[16];
+      {
+        const float sg = half ? -1.f : 1.f;
+        auto fold = [&](auto H256) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int pq = warp * 2 + q;
-        const int fa = 2 * pq, fb = fa + 1;
-        const float2* zp = Zs + pq * kSlotStride;
-        float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
-        float2* ob = oa + kBins;
-        const int n_kk = half == 0 ? 129 : 128;
-        for (int kk = lane; kk < n_kk; kk += 32) {
-          const int k = 2 * kk + half;
-          const int kr = half == 0 ? ((256 - kk) & 255) : (255 - kk);
-          const float2 zk = zp[kk & 255];
-          const float2 zn = zp[kr];
-          // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
-          if (fa < cur.nf) oa[k] = make_float2(zk.x + zn.x, zk.y - zn.y);
-          if (fb < cur.nf) ob[k] = make_float2(zk.y + zn.y, zn.x - zk.x);
+          for (int j = 0; j < 16; ++j) {
+            const int n = t + 16 * j;
+            const float a0 = fa_ok ? xa[16 * j] : 0.f, a1 = fa_ok ? xa[16 * j + 256] : 0.f;
+            // hop 256: frame b starts where the second half of frame a starts
+            const float b0 = decltype(H256)::value ? (fb_ok ? a1 : 0.f) : (fb_ok ? xb[16 * j] : 0.f);
+            const float b1 = fb_ok ? xb[16 * j + 256] : 0.f;
+            const float w0 = s_win[n], w1 = sg * s_win[n + 256];
+            v[j] = cx(fmaf(a1, w1, a0 * w0), fmaf(b1, w1, b0 * w0));
+          }
+        };
+        if (hop == 256) fold(std::true_type{}); else fold(std::false_type{});
+        if (half) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 tw = s_w512[t + 16 * j];
+            v[j] = cmulf(v[j], cx(tw.x, tw.y));
+          }
+        }
+      }
+      if (half == 1) {
+        __syncthreads();   // every warp has read the waveform tile for the last time: the buffer may be refilled
+        if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4
+      }
+      fft256_group(v, slot, s_w256, t);
+      __syncwarp();
+      if (half == 0 && tid == 0) {   // stages 2 + 3: publish the claim, fetch the tile record and its offsets
+        s_work[buf ^ 1] = nx_w;
+        if (nx_w < P.n_tiles) { nx_tile = P.tiles[nx_w]; load_offsets(); }
+      }
+      // ---- emit: this warp's two pairs.  Lane l owns sub-indices kk = l + 32 i: the even bins 2kk (half 0) wait in
+      // registers until the odd bins 2kk + 1 (half 1) exist, then both go out as one 16-byte piece -- whole 32-byte
+      // sectors per warp store instead of two half-filled passes (which cost +54 % DRAM traffic: partially written
+      // sectors were evicted and re-filled between the passes). ----
+      if (half == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float2* zp = Zs + (warp * 2 + q) * kSlotStride;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = lane + 32 * i;
+            const float2 zk = zp[kk];
+            const float2 zn = zp[256 - kk];
+            // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
+            hA[q][i] = make_float2(zk.x + zn.x, zk.y - zn.y);
+            hB[q][i] = make_float2(zk.y + zn.y, zn.x - zk.x);
+          }
+          if (lane == 0) {   // Nyquist bin 256 (kk = 128, its own partner)
+            const int fa = 2 * (warp * 2 + q);
+            const float2 z = zp[128];
+            float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
+            if (fa < cur.nf) oa[256] = make_float2(2.f * z.x, 0.f);
+            if (fa + 1 < cur.nf) oa[kBins + 256] = make_float2(2.f * z.y, 0.f);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int fa = 2 * (warp * 2 + q);
+          const float2* zp = Zs + (warp * 2 + q) * kSlotStride;
+          float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
+          float2* ob = oa + kBins;
+          const bool a_aligned = ((cur.out_row + fa) & 1) == 0;   // rows are 2056 B: every other one is 16 B aligned
+          const bool wa = fa < cur.nf, wb = fa + 1 < cur.nf;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = lane + 32 * i;
+            const float2 zk = zp[kk];
+            const float2 zn = zp[255 - kk];
+            const float2 A1 = make_float2(zk.x + zn.x, zk.y - zn.y);
+            const float2 B1 = make_float2(zk.y + zn.y, zn.x - zk.x);
+            const float4 va = make_float4(hA[q][i].x, hA[q][i].y, A1.x, A1.y);
+            const float4 vb = make_float4(hB[q][i].x, hB[q][i].y, B1.x, B1.y);
+            if (a_aligned) {
+              if (wa) *reinterpret_cast<float4*>(oa + 2 * kk) = va;
+              if (wb) { ob[2 * kk] = hB[q][i]; ob[2 * kk + 1] = B1; }
+            } else {
+              if (wa) { oa[2 * kk] = hA[q][i]; oa[2 * kk + 1] = A1; }
+              if (wb) *reinterpret_cast<float4*>(ob + 2 * kk) = vb;
+            }
+          }
         }
       }
       __syncwarp();
-      if (half == 0 && tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4 (raw[buf^1] was released by the barrier above)
     }
     __syncthreads();   // s_work / info of the next tile are visible; the Z slots may be overwritten
   }
