@@ -3,8 +3,7 @@
 //
 // HBM-bound path (hop*4 B in, 2056 B out per frame).  Same building blocks as the fbank kernel: persistent CTAs
 // (2 per SM), dynamic tile queue, staged next-tile preparation, TMA bulk prefetch of the waveform tile, frame PAIRS
-// packed as a + i*b, radix-2 fold + two 256-point register FFTs per pair run through ONE rolled loop (the second
-// half re-reads the tile instead of holding 32 more registers).  Differences: no pre-emphasis / mean / mel; every
+// packed as a + i*b, radix-2 fold + two 256-point register FFTs per pair.  Differences: no pre-emphasis / mean / mel; every
 // WARP owns two frame pairs from the load to the store (only __syncwarp between the phases of a half), and centre
 // padding (constant / reflect / edge / symmetric) is written in place by a short pad pass in the first / last tile
 // of an utterance, so the frame loads are one code path.
@@ -180,43 +179,37 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
     const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 
     float2 hA[2][4], hB[2][4];   // even bins of the warp's two pairs, held until the odd bins exist
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      // ---- fold: frame pair -> registers (window only; a = frame 2*pair, b = frame 2*pair+1) ----
-      cpx v[16];
-      {
-        const float sg = half ? -1.f : 1.f;
-        auto fold = [&](auto H256) {
+    // ---- fold: frame pair -> registers (window only; a = frame 2*pair, b = frame 2*pair+1), both halves at once ----
+    cpx v0[16], v1[16];
+    {
+      auto fold = [&](auto H256) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = t + 16 * j;
-            const float a0 = fa_ok ? xa[16 * j] : 0.f, a1 = fa_ok ? xa[16 * j + 256] : 0.f;
-            // hop 256: frame b starts where the second half of frame a starts
-            const float b0 = decltype(H256)::value ? (fb_ok ? a1 : 0.f) : (fb_ok ? xb[16 * j] : 0.f);
-            const float b1 = fb_ok ? xb[16 * j + 256] : 0.f;
-            const float w0 = s_win[n], w1 = sg * s_win[n + 256];
-            v[j] = cx(fmaf(a1, w1, a0 * w0), fmaf(b1, w1, b0 * w0));
-          }
-        };
-        if (hop == 256) fold(std::true_type{}); else fold(std::false_type{});
-        if (half) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 tw = s_w512[t + 16 * j];
-            v[j] = cmulf(v[j], cx(tw.x, tw.y));
-          }
+        for (int j = 0; j < 16; ++j) {
+          const int n = t + 16 * j;
+          const float a0 = fa_ok ? xa[16 * j] : 0.f, a1 = fa_ok ? xa[16 * j + 256] : 0.f;
+          // hop 256: frame b starts where the second half of frame a starts
+          const float b0 = decltype(H256)::value ? (fb_ok ? a1 : 0.f) : (fb_ok ? xb[16 * j] : 0.f);
+          const float b1 = fb_ok ? xb[16 * j + 256] : 0.f;
+          const float w0 = s_win[n], w1 = s_win[n + 256];
+          const cpx lo = cx(a0 * w0, b0 * w0), hi = cx(a1 * w1, b1 * w1);
+          const float2 tw = s_w512[n];
+          v0[j] = lo + hi;
+          v1[j] = cmulf(lo - hi, cx(tw.x, tw.y));
         }
-      }
-      if (half == 1) {
-        __syncthreads();   // every warp has read the waveform tile for the last time: the buffer may be refilled
-        if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4
-      }
+      };
+      if (hop == 256) fold(std::true_type{}); else fold(std::false_type{});
+    }
+    __syncthreads();   // every warp has read the waveform tile for the last time: the buffer may be refilled
+    if (tid == 0) {    // stage 2: publish the claim, fetch the tile record
+      s_work[buf ^ 1] = nx_w;
+      if (nx_w < P.n_tiles) nx_tile = P.tiles[nx_w];
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      cpx (&v)[16] = half ? v1 : v0;
       fft256_group(v, slot, s_w256, t);
       __syncwarp();
-      if (half == 0 && tid == 0) {   // stages 2 + 3: publish the claim, fetch the tile record and its offsets
-        s_work[buf ^ 1] = nx_w;
-        if (nx_w < P.n_tiles) { nx_tile = P.tiles[nx_w]; load_offsets(); }
-      }
+      if (half == 0 && tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3
       // ---- emit: this warp's two pairs.  Lane l owns sub-indices kk = l + 32 i: the even bins 2kk (half 0) wait in
       // registers until the odd bins 2kk + 1 (half 1) exist, then both go out as one 16-byte piece -- whole 32-byte
       // sectors per warp store instead of two half-filled passes (which cost +54 % DRAM traffic: partially written
@@ -271,6 +264,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
         }
       }
       __syncwarp();
+      if (half == 0 && tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4: the tile buffer was released by the barrier above
     }
     __syncthreads();   // s_work / info of the next tile are visible; the Z slots may be overwritten
   }
