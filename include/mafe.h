@@ -252,6 +252,15 @@ int mafe_compute_deltas(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32
 int mafe_context_window(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32_t n_mats, int32_t f, int32_t t,
                         int32_t left, int32_t right);
 
+/* ---- collate ("next" row f3: mindaudio/utils/common.py:10-52 pad_sequence, examples/conformer/dataset.py:563-569,
+ * 616-621) ---- */
+/* Ragged features [total_frames][dim] -> padded batch out_dev [n_utts][max_len][dim] (batch_first != 0) or
+ * [max_len][n_utts][dim].  Utterance i owns rows frame_offsets[i] .. frame_offsets[i+1]; rows beyond its length get
+ * padding_value, longer utterances are truncated to max_len.  mask_dev (may be NULL): float [n_utts][max_len], 1 for
+ * frames of the utterance, 0 for padding (= ~make_pad_mask(lengths, max_len) as float32). */
+int mafe_pad_sequence(mafe_ctx* ctx, const float* feats_dev, const int64_t* frame_offsets_dev, int32_t n_utts, int32_t dim,
+                      int32_t max_len, float padding_value, int32_t batch_first, float* out_dev, float* mask_dev);
+
 #ifdef __cplusplus
 }
 #endif

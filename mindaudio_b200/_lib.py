@@ -89,6 +89,7 @@ _PROTOS = {
     "mafe_cmvn_apply": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "mafe_compute_deltas": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I32, _I32]),
     "mafe_context_window": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32]),
+    "mafe_pad_sequence": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, C.c_float, _I32, _P, _P]),
 }
 
 _lib = None

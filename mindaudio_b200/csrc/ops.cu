@@ -292,6 +292,32 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
 
 using namespace mafe;
 
+// pad_sequence (mindaudio/utils/common.py:10-52): one thread per output element (or 4 when dim % 4 == 0)
+template <int V>
+__global__ void pad_sequence_kernel(const float* __restrict__ feats, const int64_t* __restrict__ fo, int n_utts, int dim, int max_len,
+                                    float pad, int batch_first, float* __restrict__ out, float* __restrict__ mask) {
+  const int dv = dim / V;
+  const int64_t total = (int64_t)n_utts * max_len * dv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % dv);
+    const int64_t r = i / dv;
+    int b, t;
+    if (batch_first) { b = (int)(r / max_len); t = (int)(r - (int64_t)b * max_len); }
+    else { t = (int)(r / n_utts); b = (int)(r - (int64_t)t * n_utts); }
+    const int64_t f0 = fo[b];
+    const int len = (int)(fo[b + 1] - f0);
+    const bool in = t < len;
+    if (V == 4) {
+      float4 v = make_float4(pad, pad, pad, pad);
+      if (in) v = *reinterpret_cast<const float4*>(feats + (f0 + t) * dim + 4 * d);
+      *reinterpret_cast<float4*>(out + r * dim + 4 * d) = v;
+    } else {
+      out[r * dim + d] = in ? feats[(f0 + t) * dim + d] : pad;
+    }
+    if (mask != nullptr && d == 0) mask[(int64_t)b * max_len + t] = in ? 1.f : 0.f;
+  }
+}
+
 extern "C" {
 
 int mafe_magphase(mafe_ctx* ctx, const float* z, int64_t n, float power, float* mag, float* phase) {
@@ -486,6 +512,25 @@ int mafe_context_window(mafe_ctx* ctx, const float* x, float* out, int32_t n_mat
   int roll = right > left ? right - left : 0;
   int64_t total = (int64_t)n_mats * f * csize * t;
   context_kernel<<<grid_for(ctx, total, 256 * 2), 256, 0, ctx->stream>>>(x, out, n_mats, f, t, csize, ksz, mf, roll);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_pad_sequence(mafe_ctx* ctx, const float* feats, const int64_t* frame_offsets, int32_t n_utts, int32_t dim, int32_t max_len,
+                      float padding_value, int32_t batch_first, float* out, float* mask) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(n_utts >= 0 && dim > 0 && max_len >= 0, "mafe_pad_sequence: bad shape (%d utterances, dim %d, max_len %d)", n_utts, dim, max_len);
+  if (n_utts == 0 || max_len == 0) return MAFE_OK;
+  MAFE_REQUIRE(frame_offsets && out, "mafe_pad_sequence: NULL buffer");
+  cudaSetDevice(ctx->device);
+  const bool vec = dim % 4 == 0 && ((uintptr_t)feats & 15) == 0 && ((uintptr_t)out & 15) == 0;
+  const int64_t total = (int64_t)n_utts * max_len * (vec ? dim / 4 : dim);
+  if (vec)
+    pad_sequence_kernel<4><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(feats, frame_offsets, n_utts, dim, max_len, padding_value,
+                                                                               batch_first, out, mask);
+  else
+    pad_sequence_kernel<1><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(feats, frame_offsets, n_utts, dim, max_len, padding_value,
+                                                                               batch_first, out, mask);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }

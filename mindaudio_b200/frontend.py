@@ -139,3 +139,42 @@ class FbankPipeline:
         fo = self.run_host(flat.ctypes.data, so, out.ctypes.data, L.WAVE_I16 if dt == np.int16 else L.WAVE_F32,
                            wave_scale, chunk_utts)
         return out, fo
+
+    def features_padded(self, waves, max_len=None, padding_value=0.0, wave_scale=1.0):
+        """Front-end + collate in one device round trip (examples/conformer/dataset.py:456-491, 563-569, 616-621):
+        list of 1-D waveforms -> ``(xs_pad [B, max_len, mel_bin] float32, xs_lengths [B] int32, xs_masks [B, 1, max_len]
+        float32)``.  The ragged feature matrix never leaves the GPU: the padded batch and the mask are written by
+        ``mafe_pad_sequence`` and only they are copied back.  Utterances longer than ``max_len`` are truncated like
+        ``pad_sequence`` does; ``xs_lengths`` are the untruncated frame counts, as in the reference."""
+        eng = self.eng
+        lens = [len(w) for w in waves]
+        dt = np.int16 if waves and all(np.asarray(w).dtype == np.int16 for w in waves) else np.float32
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=dt) for w in waves])) if waves else np.zeros(0, dt)
+        so = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=so[1:])
+        with eng.lock:
+            b = eng.batch(self.plan, so)
+            try:
+                xs_lengths = np.diff(b.frame_offsets).astype(np.int32)
+                if max_len is None:
+                    max_len = int(xs_lengths.max()) if len(lens) else 0
+                xs_pad = np.empty((len(lens), max_len, self.mel_bin), dtype=np.float32)
+                xs_masks = np.empty((len(lens), 1, max_len), dtype=np.float32)
+                if xs_pad.size:
+                    d_w = eng.buf("wave", max(flat.nbytes, 16))
+                    d_f = eng.buf("out", max(b.total_frames * self.mel_bin * 4, 16))
+                    d_p = eng.buf("pad", xs_pad.nbytes)
+                    d_m = eng.buf("aux", xs_masks.nbytes)
+                    keep = eng.h2d(d_w, flat)
+                    self.run(d_w.value if hasattr(d_w, "value") else d_w, b, d_f.value if hasattr(d_f, "value") else d_f,
+                             L.WAVE_I16 if dt == np.int16 else L.WAVE_F32, wave_scale)
+                    L.check(eng.lib.mafe_pad_sequence(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), len(lens), self.mel_bin,
+                                                      max_len, float(padding_value), 1, d_p, d_m))
+                    eng.d2h(xs_pad, d_p)
+                    eng.d2h(xs_masks, d_m)
+                    eng.sync()
+                    del keep
+                return xs_pad, xs_lengths, xs_masks
+            finally:
+                b.close()
+

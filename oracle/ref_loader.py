@@ -125,5 +125,16 @@ def load_json_cmvn():
     return _cache["jc"]
 
 
+def load_collate():
+    """``pad_sequence`` (mindaudio/utils/common.py:10-52) and ``make_pad_mask`` (mindaudio/utils/mask.py:44-67), as written."""
+    if "collate" not in _cache:
+        from typing import List, Tuple
+        g1 = _extract_functions(os.path.join(REF_ROOT, "mindaudio", "utils", "common.py"), ["pad_sequence"],
+                                {"List": List, "Tuple": Tuple})
+        g2 = _extract_functions(os.path.join(REF_ROOT, "mindaudio", "utils", "mask.py"), ["make_pad_mask"], {"List": List})
+        _cache["collate"] = types.SimpleNamespace(pad_sequence=g1["pad_sequence"], make_pad_mask=g2["make_pad_mask"])
+    return _cache["collate"]
+
+
 def sample_wav(name="BAC009S0002W0122.wav"):
     return os.path.join(REF_ROOT, "tests", "samples", "ASR", name)

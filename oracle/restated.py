@@ -575,3 +575,35 @@ def dither_noise(n, seed, utt_id):
     u1 = ((w0 >> np.uint32(8)).astype(np.float64) + 1.0) * 2.0 ** -24
     u2 = (w1 >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
     return (np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * math.pi * u2)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# collate (scope row f3): mindaudio/utils/common.py:10-52, mindaudio/utils/mask.py:44-67
+# ---------------------------------------------------------------------------------------------
+def pad_sequence(sequences, batch_first=True, padding_value=0, padding_max_len=None, atype=np.int32):
+    trailing = tuple(sequences[0].shape[1:])
+    max_len = padding_max_len if padding_max_len is not None else max(s.shape[0] for s in sequences)
+    dims = ((len(sequences), max_len) if batch_first else (max_len, len(sequences))) + trailing
+    out = np.full(dims, fill_value=padding_value).astype(atype)
+    for i, seq in enumerate(sequences):
+        n = min(seq.shape[0], max_len)
+        if batch_first:
+            out[i, :n] = seq[:n]
+        else:
+            out[:n, i] = seq[:n]
+    return out
+
+
+def make_pad_mask(lengths, max_len=0):
+    lengths = np.asarray(lengths)
+    max_len = max_len if max_len > 0 else int(lengths.max())
+    return np.arange(max_len)[None, :] >= lengths[:, None]
+
+
+def conformer_collate_x(feats, max_src_len):
+    """xs_pad, xs_lengths, xs_masks of examples/conformer/dataset.py:563-569, 616-621."""
+    xs_pad = pad_sequence(feats, batch_first=True, padding_value=0.0, padding_max_len=max_src_len, atype=np.float32)
+    xs_lengths = np.array([x.shape[0] for x in feats], dtype=np.int32)
+    xs_masks = np.expand_dims(~make_pad_mask(xs_lengths, max_len=max_src_len), 1).astype(np.float32)
+    return xs_pad, xs_lengths, xs_masks
+

@@ -231,3 +231,31 @@ def test_many_utterances_take_the_per_utterance_prepass(ma):
         got = out[fo[u]:fo[u + 1]]
         assert got.shape == ref.shape
         assert logmel_err(got, ref) <= 1.0, u
+
+
+def test_pad_sequence_and_padded_pipeline(ma):
+    """Scope row f3: pad_sequence on the device (bit exact vs the restated reference), and front-end + collate in one
+    device round trip (xs_pad / xs_lengths / xs_masks of examples/conformer/dataset.py:563-569, 616-621)."""
+    rng = np.random.default_rng(5)
+    seqs = [rng.standard_normal((n, 80)).astype(np.float32) for n in (17, 3, 40, 1, 25)]
+    for kw in (dict(), dict(padding_max_len=30), dict(batch_first=False, padding_max_len=48), dict(padding_max_len=2)):
+        out = ma.pad_sequence(seqs, padding_value=0.0, atype=np.float32, **kw)
+        ref = R.pad_sequence(seqs, padding_value=0.0, atype=np.float32, **kw)
+        assert out.dtype == ref.dtype and out.shape == ref.shape and np.array_equal(out, ref)
+    odd = [rng.standard_normal((n, 7)).astype(np.float32) for n in (5, 9)]       # dim % 4 != 0: scalar kernel
+    assert np.array_equal(ma.pad_sequence(odd, padding_value=-2.5, atype=np.float32), R.pad_sequence(odd, padding_value=-2.5, atype=np.float32))
+    labels = [rng.integers(0, 50, size=n).astype(np.int32) for n in (4, 9, 2)]   # host route, as the reference
+    assert np.array_equal(ma.pad_sequence(labels, padding_value=-1, padding_max_len=10), R.pad_sequence(labels, padding_value=-1, padding_max_len=10))
+    assert np.array_equal(ma.make_pad_mask(np.array([5, 3, 2]), 8), R.make_pad_mask(np.array([5, 3, 2]), 8))
+
+    lens = [16000, 5361, 400, 30000, 8000]
+    waves = [np.round(synth(70 + i, (n,)) * 32768).astype(np.float32) for i, n in enumerate(lens)]
+    pipe = ma.FbankPipeline(cmvn=None)
+    flat, fo = pipe.features(waves)
+    feats = [flat[fo[i]:fo[i + 1]] for i in range(len(lens))]
+    for max_len in (None, 120, 200):
+        xs_pad, xs_lengths, xs_masks = pipe.features_padded(waves, max_len=max_len)
+        ml = max_len if max_len is not None else max(f.shape[0] for f in feats)
+        r_pad, r_len, r_mask = R.conformer_collate_x(feats, ml)
+        assert np.array_equal(xs_pad, r_pad) and np.array_equal(xs_lengths, r_len) and np.array_equal(xs_masks, r_mask)
+

@@ -49,3 +49,21 @@ def test_context_window_matches_grouped_conv(ref):
         assert np.array_equal(ref["ft"].context_window(z, l, r), R.context_window(z, l, r))
     z4 = rng.standard_normal((2, 3, 7, 20)).astype(np.float32)
     assert np.array_equal(ref["ft"].context_window(z4, 2, 3), R.context_window(z4, 2, 3))
+
+
+def test_collate_matches_reference():
+    """pad_sequence / make_pad_mask restatements vs the reference's own functions (bit exact)."""
+    ref = ref_loader.load_collate()
+    rng = np.random.default_rng(7)
+    seqs = [rng.standard_normal((n, 5)).astype(np.float32) for n in (7, 3, 11, 1)]
+    labels = [rng.integers(0, 50, size=n).astype(np.int32) for n in (4, 9, 2)]
+    for kw in (dict(), dict(padding_max_len=9), dict(batch_first=False, padding_max_len=12), dict(padding_max_len=2)):
+        a = ref.pad_sequence(seqs, padding_value=0.0, atype=np.float32, **kw)
+        b = R.pad_sequence(seqs, padding_value=0.0, atype=np.float32, **kw)
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+    a, b = ref.pad_sequence(labels, padding_value=-1, padding_max_len=10), R.pad_sequence(labels, padding_value=-1, padding_max_len=10)
+    assert a.dtype == b.dtype and np.array_equal(a, b)
+    lens = np.array([5, 3, 2], dtype=np.int32)
+    assert np.array_equal(ref.make_pad_mask(lens), R.make_pad_mask(lens))
+    assert np.array_equal(ref.make_pad_mask(lens, max_len=8), R.make_pad_mask(lens, max_len=8))
+
