@@ -261,6 +261,19 @@ int mafe_context_window(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32
 int mafe_pad_sequence(mafe_ctx* ctx, const float* feats_dev, const int64_t* frame_offsets_dev, int32_t n_utts, int32_t dim,
                       int32_t max_len, float padding_value, int32_t batch_first, float* out_dev, float* mask_dev);
 
+/* ---- feature-domain ops of the pipelines ("next" row f4) ---- */
+/* sliding_window_cmn (mindaudio/data/processing.py:380-407 -> msaudio.SlidingWindowCmn; Kaldi's sliding-window CMN as
+ * in torchaudio.functional.sliding_window_cmn): x, out [n_channels][num_frames][num_feats]; out must NOT alias x
+ * (frames leave the window after they have been normalised). */
+int mafe_sliding_window_cmn(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32_t n_channels, int32_t num_frames,
+                            int32_t num_feats, int32_t cmn_window, int32_t min_cmn_window, int32_t center, int32_t norm_vars);
+/* Rectangle masking, in place (SpecAugment: examples/conformer/dataset.py:493-534; mindaudio/data/augment.py:28-98
+ * frequencymasking / timemasking).  feats_dev is a ragged [total_rows][dim] array with row offsets
+ * (frame_offsets_dev[n_items + 1]); rects_dev holds n_rects x (item, row0, row1, col0, col1) int32, half-open ranges
+ * relative to the item, clipped to the item's extent; every covered element is set to value. */
+int mafe_mask_rects(mafe_ctx* ctx, float* feats_dev, const int64_t* frame_offsets_dev, int32_t n_items, int32_t dim,
+                    const int32_t* rects_dev, int32_t n_rects, float value);
+
 #ifdef __cplusplus
 }
 #endif

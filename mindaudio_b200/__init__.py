@@ -6,8 +6,10 @@ Importing this package does not touch CUDA (fork safe); the first op creates the
 """
 from ._enums import BorderType, MelType, NormMode, NormType, WindowType  # noqa: F401
 from ._lib import MafeError  # noqa: F401
-from .data import cmvn, collate, features, spectrum  # noqa: F401
+from .data import cmvn, collate, features, masking, processing, spectrum  # noqa: F401
 from .data.collate import *  # noqa: F401,F403
+from .data.masking import *  # noqa: F401,F403
+from .data.processing import *  # noqa: F401,F403
 from .data.cmvn import *  # noqa: F401,F403
 from .data.features import *  # noqa: F401,F403
 from .data.spectrum import *  # noqa: F401,F403

@@ -90,6 +90,8 @@ _PROTOS = {
     "mafe_compute_deltas": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I32, _I32]),
     "mafe_context_window": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32]),
     "mafe_pad_sequence": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, C.c_float, _I32, _P, _P]),
+    "mafe_sliding_window_cmn": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
+    "mafe_mask_rects": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I32, C.c_float]),
 }
 
 _lib = None

@@ -318,6 +318,60 @@ __global__ void pad_sequence_kernel(const float* __restrict__ feats, const int64
   }
 }
 
+// sliding-window CMN: one thread per (channel, feature) walks the frames with running window sums in double.
+// Window rule of Kaldi / torchaudio.functional.sliding_window_cmn (the window moves by at most one frame per step).
+__global__ void sliding_cmn_kernel(const float* __restrict__ x, float* __restrict__ out, int n_ch, int T, int D, int cmn_window,
+                                   int min_cmn_window, int center, int norm_vars) {
+  const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= (int64_t)n_ch * D) return;
+  const int c = (int)(id / D), d = (int)(id - (int64_t)c * D);
+  const float* xc = x + (int64_t)c * T * D + d;
+  float* oc = out + (int64_t)c * T * D + d;
+  double sum = 0.0, sumsq = 0.0;
+  int last_start = -1, last_end = -1;
+  for (int t = 0; t < T; ++t) {
+    int ws, we;
+    if (center) { ws = t - cmn_window / 2; we = ws + cmn_window; }
+    else { ws = t - cmn_window; we = t + 1; }
+    if (ws < 0) { we -= ws; ws = 0; }
+    if (!center && we > t) we = max(t + 1, min_cmn_window);
+    if (we > T) { ws -= we - T; we = T; if (ws < 0) ws = 0; }
+    if (last_start == -1) {
+      for (int i = ws; i < we; ++i) { const double v = xc[(int64_t)i * D]; sum += v; sumsq += v * v; }
+    } else {
+      if (ws > last_start) { const double v = xc[(int64_t)last_start * D]; sum -= v; sumsq -= v * v; }
+      if (we > last_end) { const double v = xc[(int64_t)last_end * D]; sum += v; sumsq += v * v; }
+    }
+    const int n = we - ws;
+    last_start = ws; last_end = we;
+    const double xv = xc[(int64_t)t * D];
+    double y = xv - sum / n;
+    if (norm_vars) {
+      if (n == 1) y = 0.0;
+      else y *= 1.0 / sqrt(sumsq / n - (sum * sum) / ((double)n * n));
+    }
+    oc[(int64_t)t * D] = (float)y;
+  }
+}
+
+// rectangle masks: one CTA per rectangle
+__global__ void mask_rects_kernel(float* __restrict__ feats, const int64_t* __restrict__ fo, int n_items, int dim,
+                                  const int* __restrict__ rects, float value) {
+  const int* r = rects + 5 * blockIdx.x;
+  const int item = r[0];
+  if (item < 0 || item >= n_items) return;
+  const int64_t base = fo[item];
+  const int rows = (int)(fo[item + 1] - base);
+  const int r0 = max(r[1], 0), r1 = min(r[2], rows), c0 = max(r[3], 0), c1 = min(r[4], dim);
+  const int w = c1 - c0;
+  if (r1 <= r0 || w <= 0) return;
+  const int64_t n = (int64_t)(r1 - r0) * w;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int rr = (int)(i / w), cc = (int)(i - (int64_t)rr * w);
+    feats[(base + r0 + rr) * dim + c0 + cc] = value;
+  }
+}
+
 extern "C" {
 
 int mafe_magphase(mafe_ctx* ctx, const float* z, int64_t n, float power, float* mag, float* phase) {
@@ -531,6 +585,34 @@ int mafe_pad_sequence(mafe_ctx* ctx, const float* feats, const int64_t* frame_of
   else
     pad_sequence_kernel<1><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(feats, frame_offsets, n_utts, dim, max_len, padding_value,
                                                                                batch_first, out, mask);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_sliding_window_cmn(mafe_ctx* ctx, const float* x, float* out, int32_t n_channels, int32_t num_frames, int32_t num_feats,
+                            int32_t cmn_window, int32_t min_cmn_window, int32_t center, int32_t norm_vars) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(cmn_window >= 1 && min_cmn_window >= 0, "sliding_window_cmn: cmn_window %d / min_cmn_window %d out of range", cmn_window,
+               min_cmn_window);
+  if (n_channels <= 0 || num_frames <= 0 || num_feats <= 0) return MAFE_OK;
+  MAFE_REQUIRE(x && out, "mafe_sliding_window_cmn: NULL buffer");
+  MAFE_REQUIRE(x != out, "mafe_sliding_window_cmn: out must not alias x");
+  cudaSetDevice(ctx->device);
+  const int64_t n = (int64_t)n_channels * num_feats;
+  sliding_cmn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(x, out, n_channels, num_frames, num_feats, cmn_window,
+                                                                          min_cmn_window, center, norm_vars);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_mask_rects(mafe_ctx* ctx, float* feats, const int64_t* frame_offsets, int32_t n_items, int32_t dim, const int32_t* rects,
+                    int32_t n_rects, float value) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(n_items >= 0 && dim > 0 && n_rects >= 0, "mafe_mask_rects: bad shape");
+  if (n_rects == 0 || n_items == 0) return MAFE_OK;
+  MAFE_REQUIRE(feats && frame_offsets && rects, "mafe_mask_rects: NULL buffer");
+  cudaSetDevice(ctx->device);
+  mask_rects_kernel<<<n_rects, 256, 0, ctx->stream>>>(feats, frame_offsets, n_items, dim, rects, value);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }

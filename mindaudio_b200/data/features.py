@@ -12,7 +12,7 @@ import numpy as np
 from .. import _lib as L
 from .. import _tables as T
 from .._engine import get_engine
-from .._enums import BorderType, NormMode
+from .._enums import BorderType, NormMode, WindowType
 from . import spectrum as _sp
 
 __all__ = [
@@ -21,6 +21,7 @@ __all__ = [
     "fbank",
     "fbanks",
     "mfcc",
+    "spectral_centroid",
 ]
 
 
@@ -221,3 +222,26 @@ def mfcc(
     out = _features(waveforms, kw, n_mfcc, deltas, context, left_frames, right_frames, win_length, hop_length,
                     "hann", n_fft)
     return out
+
+
+def spectral_centroid(waveforms, sample_rate, n_fft=400, win_length=None, hop_length=None, pad=0, window="hann"):
+    """``features.py:22-66`` (``msaudio.SpectralCentroid`` = torchaudio.functional.spectral_centroid): the
+    magnitude-weighted mean frequency of every frame, ``[..., time]``.
+
+    One front-end pass: the magnitude spectrogram (power 1, reflect-centred) is projected on the two-row "filterbank"
+    ``[freqs; ones]`` inside the kernel, so only ``sum f|X|`` and ``sum |X|`` per frame leave the GPU."""
+    from .spectrum import _frames_to_ft, _out_dtype, _run_spec, _spectrogram_plan
+    waveforms = np.asarray(waveforms)
+    win_length = win_length if win_length else n_fft
+    hop_length = hop_length if hop_length else win_length // 2
+    window = WindowType(window)
+    n_bins = n_fft // 2 + 1
+    bank = np.stack([np.linspace(0, sample_rate // 2, n_bins), np.ones(n_bins)]).astype(np.float32)
+    plan = _spectrogram_plan(get_engine(), n_fft, win_length, hop_length, window, 1.0, False, True, "reflect",
+                             out_kind=L.OUT_MEL, mel_fb=bank)
+    out, lead, frames = _run_spec(plan, waveforms, pad, n_fft, True)
+    num_den = _frames_to_ft(out, lead, frames, 2).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cen = num_den[..., 0, :] / num_den[..., 1, :]
+    return cen.astype(_out_dtype(waveforms), copy=False)
+

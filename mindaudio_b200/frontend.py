@@ -140,12 +140,15 @@ class FbankPipeline:
                            wave_scale, chunk_utts)
         return out, fo
 
-    def features_padded(self, waves, max_len=None, padding_value=0.0, wave_scale=1.0):
+    def features_padded(self, waves, max_len=None, padding_value=0.0, wave_scale=1.0, spec_aug_conf=None, rng=None):
         """Front-end + collate in one device round trip (examples/conformer/dataset.py:456-491, 563-569, 616-621):
         list of 1-D waveforms -> ``(xs_pad [B, max_len, mel_bin] float32, xs_lengths [B] int32, xs_masks [B, 1, max_len]
         float32)``.  The ragged feature matrix never leaves the GPU: the padded batch and the mask are written by
         ``mafe_pad_sequence`` and only they are copied back.  Utterances longer than ``max_len`` are truncated like
-        ``pad_sequence`` does; ``xs_lengths`` are the untruncated frame counts, as in the reference."""
+        ``pad_sequence`` does; ``xs_lengths`` are the untruncated frame counts, as in the reference.
+        ``spec_aug_conf`` (dataset.py:493-534) masks time / frequency rectangles of the ragged features on the device
+        before the padding; the positions come from ``rng`` (a ``random.Random``; default the ``random`` module) with
+        the reference's call sequence."""
         eng = self.eng
         lens = [len(w) for w in waves]
         dt = np.int16 if waves and all(np.asarray(w).dtype == np.int16 for w in waves) else np.float32
@@ -168,12 +171,21 @@ class FbankPipeline:
                     keep = eng.h2d(d_w, flat)
                     self.run(d_w.value if hasattr(d_w, "value") else d_w, b, d_f.value if hasattr(d_f, "value") else d_f,
                              L.WAVE_I16 if dt == np.int16 else L.WAVE_F32, wave_scale)
+                    keep_r = None
+                    if spec_aug_conf:
+                        from .data.masking import spec_aug_rects
+                        rects = spec_aug_rects([(int(t), self.mel_bin) for t in xs_lengths], spec_aug_conf, rng)
+                        if len(rects):
+                            d_r = eng.buf("rects", rects.nbytes)
+                            keep_r = eng.h2d(d_r, rects)
+                            L.check(eng.lib.mafe_mask_rects(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), len(lens), self.mel_bin,
+                                                            d_r, len(rects), 0.0))
                     L.check(eng.lib.mafe_pad_sequence(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), len(lens), self.mel_bin,
                                                       max_len, float(padding_value), 1, d_p, d_m))
                     eng.d2h(xs_pad, d_p)
                     eng.d2h(xs_masks, d_m)
                     eng.sync()
-                    del keep
+                    del keep, keep_r
                 return xs_pad, xs_lengths, xs_masks
             finally:
                 b.close()

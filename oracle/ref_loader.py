@@ -136,5 +136,22 @@ def load_collate():
     return _cache["collate"]
 
 
+def load_spec_aug():
+    """The ``spec_aug`` METHOD of the conformer collate class (``examples/conformer/dataset.py:493-534``), as written,
+    exec'd as a plain function (``self`` is unused); it draws from the ``random`` MODULE."""
+    if "specaug" not in _cache:
+        import random
+        path = os.path.join(REF_ROOT, "examples", "conformer", "dataset.py")
+        with open(path) as fh:
+            tree = ast.parse(fh.read(), filename=path)
+        fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "spec_aug"]
+        if not fn:
+            raise RuntimeError("spec_aug not found in %s" % path)
+        g = {"random": random, "__name__": "ref_extract"}
+        exec(compile(ast.Module(body=[fn[0]], type_ignores=[]), path, "exec"), g)
+        _cache["specaug"] = g["spec_aug"]
+    return _cache["specaug"]
+
+
 def sample_wav(name="BAC009S0002W0122.wav"):
     return os.path.join(REF_ROOT, "tests", "samples", "ASR", name)

@@ -607,3 +607,89 @@ def conformer_collate_x(feats, max_src_len):
     xs_masks = np.expand_dims(~make_pad_mask(xs_lengths, max_len=max_src_len), 1).astype(np.float32)
     return xs_pad, xs_lengths, xs_masks
 
+
+# ---------------------------------------------------------------------------------------------
+# feature-domain ops of the pipelines (scope row f4)
+# ---------------------------------------------------------------------------------------------
+def sliding_window_cmn(x, cmn_window=600, min_cmn_window=100, center=False, norm_vars=False):
+    """[ms-op] ``msaudio.SlidingWindowCmn`` (processing.py:380-407) = Kaldi's sliding-window CMN as written in
+    torchaudio.functional.sliding_window_cmn: window rule per frame, mean (and variance) over the window.  Direct
+    window sums in float64 (torchaudio updates them incrementally in the input dtype)."""
+    x = np.asarray(x)
+    out_dtype = np.float64 if x.dtype == np.float64 else np.float32
+    xf = x.astype(np.float64)
+    T = xf.shape[-2]
+    out = np.zeros_like(xf)
+    for t in range(T):
+        if center:
+            ws = t - cmn_window // 2
+            we = ws + cmn_window
+        else:
+            ws, we = t - cmn_window, t + 1
+        if ws < 0:
+            we -= ws
+            ws = 0
+        if not center and we > t:
+            we = max(t + 1, min_cmn_window)
+        if we > T:
+            ws -= we - T
+            we = T
+            ws = max(ws, 0)
+        win = xf[..., ws:we, :]
+        n = we - ws
+        mean = win.sum(axis=-2) / n
+        y = xf[..., t, :] - mean
+        if norm_vars:
+            if n == 1:
+                y = np.zeros_like(y)
+            else:
+                var = (win ** 2).sum(axis=-2) / n - mean ** 2
+                y = y * var ** -0.5
+        out[..., t, :] = y
+    return out.astype(out_dtype)
+
+
+def spectral_centroid(waveforms, sample_rate, n_fft=400, win_length=None, hop_length=None, pad=0, window="hann"):
+    """[ms-op] ``msaudio.SpectralCentroid`` (features.py:22-66) = torchaudio.functional.spectral_centroid."""
+    x = np.asarray(waveforms)
+    out_dtype = np.float64 if x.dtype == np.float64 else np.float32
+    win_length = win_length if win_length else n_fft
+    hop_length = hop_length if hop_length else win_length // 2
+    spec = spectrogram(x.astype(np.float64), n_fft, win_length, hop_length, pad, window, 1.0, False, True, "reflect")
+    freqs = np.linspace(0, sample_rate // 2, 1 + n_fft // 2).reshape((-1, 1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return ((freqs * spec).sum(axis=-2) / spec.sum(axis=-2)).astype(out_dtype)
+
+
+def spec_aug(xs, spec_aug_conf, rng):
+    """examples/conformer/dataset.py:493-534, in place; ``rng`` is a ``random.Random`` (the reference uses the module)."""
+    num_t_mask = spec_aug_conf.get("num_t_mask", 0)
+    num_f_mask = spec_aug_conf.get("num_f_mask", 0)
+    max_t = spec_aug_conf.get("max_t", 0)
+    max_f = spec_aug_conf.get("max_f", 0)
+    for x in xs:
+        max_frames, max_freq = x.shape[0], x.shape[1]
+        for _ in range(num_t_mask):
+            start = rng.randint(0, max_frames - 1)
+            length = rng.randint(1, max_t)
+            end = min(max_frames, start + length)
+            if rng.randint(1, 100) > 20:
+                x[start:end, :] = 0
+        for _ in range(num_f_mask):
+            start = rng.randint(0, max_freq - 1)
+            length = rng.randint(1, max_f)
+            end = min(max_freq, start + length)
+            if rng.randint(1, 100) > 20:
+                x[:, start:end] = 0
+    return xs
+
+
+def mask_along_axis(spec, mask_param, mask_start, mask_value, axis):
+    """[ms-op, recalled] deterministic branch of ``msaudio.FrequencyMasking`` / ``TimeMasking`` (iid_masks=False):
+    ``mask_param`` consecutive indices from ``mask_start`` along ``axis`` (-2 = frequency, -1 = time) set to value."""
+    out = np.array(spec, copy=True)
+    idx = [slice(None)] * out.ndim
+    idx[axis] = slice(mask_start, mask_start + mask_param)
+    out[tuple(idx)] = mask_value
+    return out
+

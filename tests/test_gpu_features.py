@@ -258,4 +258,42 @@ def test_pad_sequence_and_padded_pipeline(ma):
         ml = max_len if max_len is not None else max(f.shape[0] for f in feats)
         r_pad, r_len, r_mask = R.conformer_collate_x(feats, ml)
         assert np.array_equal(xs_pad, r_pad) and np.array_equal(xs_lengths, r_len) and np.array_equal(xs_masks, r_mask)
+    # + SpecAugment between the front-end and the padding (dataset.py:560-569), same random draws as the reference
+    import random
+    conf = {"num_t_mask": 2, "num_f_mask": 2, "max_t": 50, "max_f": 10}
+    xs_pad, _, _ = pipe.features_padded(waves, max_len=150, spec_aug_conf=conf, rng=random.Random(5))
+    masked = R.spec_aug([f.copy() for f in feats], conf, random.Random(5))
+    assert np.array_equal(xs_pad, R.conformer_collate_x(masked, 150)[0])
+
+
+def test_feature_domain_ops(ma):
+    """Scope row f4: sliding-window CMN, spectral centroid, SpecAugment / frequency / time masking."""
+    import random
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((3, 90, 40)) * 3.0 + 1.0).astype(np.float32)
+    for kw in (dict(cmn_window=20, min_cmn_window=5), dict(cmn_window=15, center=True, norm_vars=True), dict(), dict(cmn_window=8, min_cmn_window=3, norm_vars=True)):
+        out, ref = ma.sliding_window_cmn(x, **kw), R.sliding_window_cmn(x, **kw)
+        assert out.dtype == ref.dtype and out.shape == ref.shape
+        assert np.max(np.abs(out - ref)) <= 1e-5 * max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(ma.sliding_window_cmn(x[0, :, :3].astype(np.float64), 30, 10) - R.sliding_window_cmn(x[0, :, :3].astype(np.float64), 30, 10))) <= 1e-5
+
+    w = synth(5, (2, 9000))
+    for kw in (dict(), dict(n_fft=512, win_length=400, hop_length=160)):
+        out, ref = ma.spectral_centroid(w, 16000, **kw), R.spectral_centroid(w, 16000, **kw)
+        assert out.shape == ref.shape and np.max(np.abs(out - ref) / np.abs(ref)) <= 1e-4
+    assert ma.spectral_centroid(w[0], 16000).shape == R.spectral_centroid(w[0], 16000).shape
+
+    conf = {"num_t_mask": 2, "num_f_mask": 2, "max_t": 50, "max_f": 10}
+    xs = [rng.standard_normal((n, 80)).astype(np.float32) + 5.0 for n in (120, 33, 400, 7)]
+    a = R.spec_aug([v.copy() for v in xs], conf, random.Random(77))
+    b = ma.spec_aug([v.copy() for v in xs], conf, random.Random(77))
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))                    # bit exact: same draws, same rectangles
+    spec = np.abs(rng.standard_normal((2, 3, 64, 50))).astype(np.float32)
+    assert np.array_equal(ma.frequencymasking(spec, frequency_mask_param=9, mask_start=5, mask_value=-1.0), R.mask_along_axis(spec, 9, 5, -1.0, -2))
+    assert np.array_equal(ma.timemasking(spec[0, 0], frequency_mask_param=20, mask_start=30), R.mask_along_axis(spec[0, 0], 20, 30, 0.0, -1))
+    m = ma.frequencymasking(spec, iid_masks=True, frequency_mask_param=9, rng=np.random.default_rng(1))
+    changed = (m != spec).any(axis=-1)                                        # [2, 3, 64]: masked frequency rows
+    assert changed.sum(axis=-1).max() <= 9 and m.shape == spec.shape
+    with pytest.raises(ValueError):
+        ma.frequencymasking(spec, frequency_mask_param=65)
 

@@ -67,3 +67,17 @@ def test_collate_matches_reference():
     assert np.array_equal(ref.make_pad_mask(lens), R.make_pad_mask(lens))
     assert np.array_equal(ref.make_pad_mask(lens, max_len=8), R.make_pad_mask(lens, max_len=8))
 
+
+def test_spec_aug_matches_reference():
+    """The restated SpecAugment draws the same ``random`` sequence as the reference method (bit exact)."""
+    import random
+    ref_fn = ref_loader.load_spec_aug()
+    conf = {"num_t_mask": 2, "num_f_mask": 2, "max_t": 50, "max_f": 10}
+    rng = np.random.default_rng(3)
+    xs = [rng.standard_normal((n, 80)).astype(np.float32) + 5.0 for n in (120, 33, 400)]
+    random.seed(1234)
+    a = ref_fn(None, [x.copy() for x in xs], conf)
+    b = R.spec_aug([x.copy() for x in xs], conf, random.Random(1234))
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    assert any((u == 0).any() for u in a)
+

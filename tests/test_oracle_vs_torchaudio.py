@@ -32,3 +32,20 @@ def test_melscale_fbanks_dct_deltas():
     x = np.random.default_rng(3).standard_normal((2, 13, 40))
     ref = F.compute_deltas(torch.from_numpy(x), win_length=5, mode="replicate").numpy()
     assert np.max(np.abs(R.compute_deltas(x, 5, "edge") - ref)) < 1e-12
+
+
+def test_sliding_window_cmn_and_spectral_centroid():
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, 50, 7)) * 3.0 + 1.0
+    for kw in (dict(cmn_window=20, min_cmn_window=5, center=False, norm_vars=False), dict(cmn_window=15, min_cmn_window=100, center=True, norm_vars=True),
+               dict(cmn_window=600, min_cmn_window=100, center=False, norm_vars=True), dict(cmn_window=8, min_cmn_window=3, center=False, norm_vars=True)):
+        ref = F.sliding_window_cmn(torch.from_numpy(x), **kw).numpy()
+        assert np.max(np.abs(R.sliding_window_cmn(x, **kw) - ref)) < 1e-9
+    assert np.max(np.abs(R.sliding_window_cmn(x[0], 20, 5) - F.sliding_window_cmn(torch.from_numpy(x[0]), 20, 5).numpy())) < 1e-9
+    from tests.util import synth
+    w = synth(5, (2, 8000)).astype(np.float64)
+    for n_fft, win, hop in ((400, 400, 200), (512, 400, 160)):
+        ref = F.spectral_centroid(torch.from_numpy(w), 16000, pad=0, window=torch.hann_window(win, dtype=torch.float64), n_fft=n_fft,
+                                  hop_length=hop, win_length=win).numpy()
+        assert np.max(np.abs(R.spectral_centroid(w, 16000, n_fft, win, hop) - ref)) < 1e-7
+
