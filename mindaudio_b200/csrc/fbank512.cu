@@ -324,12 +324,15 @@ namespace mafe {
 }  // namespace mafe
 #include "stft512.cuh"
 #include "fbank400.cuh"
+#include "stftn16.cuh"
 namespace mafe {
 
 struct FastTablesHost {
   FastTablesDev dev;
   int ylen;
   bool stft = false;      // n_fft = 512 complex STFT plan (stft512_kernel)
+  int stftn = 0;          // n_fft = 320 / 400 complex STFT plan (stftn16_kernel<20 / 25>): N1, else 0
+  float2 tws[16];         // W_N1^(j1 k1) of the in-register N1-point DFT
   bool f400 = false;      // n_fft = 400 mel front-end plan (fbank400_kernel)
   float2* tw400_dev = nullptr;
   F400Sweep sweep400;     // sweep program of fbank400_kernel (kernel-parameter bank)
@@ -532,6 +535,16 @@ static bool stft_plan_supported(const mafe_frontend_desc* d) {
          d->preemph == 0.0 && !d->remove_frame_mean && d->dither == 0.f && d->spec_scale == 1.0f;
 }
 
+// n_fft = 320 (deepspeech2) / 400 complex STFT: N1 of stftn16_kernel, or 0
+static int stftn_plan_supported(const mafe_frontend_desc* d) {
+  if (d->out_kind != MAFE_OUT_COMPLEX || d->frame_len != d->n_fft || d->preemph != 0.0 || d->remove_frame_mean || d->dither != 0.f ||
+      d->spec_scale != 1.0f)
+    return 0;
+  if (d->n_fft != 320 && d->n_fft != 400) return 0;
+  if (d->hop < 1 || d->hop > d->n_fft / 2) return 0;
+  return d->n_fft / 16;
+}
+
 static bool f400_plan_supported(const mafe_frontend_desc* d) {
   if (!(d->n_fft == kN400 && d->frame_len == kN400 && d->hop >= 1 && d->hop <= kMaxHop400)) return false;
   if (!(d->out_kind == MAFE_OUT_MEL || d->out_kind == MAFE_OUT_LOGMEL || d->out_kind == MAFE_OUT_MFCC)) return false;
@@ -545,6 +558,7 @@ static bool f400_plan_supported(const mafe_frontend_desc* d) {
 
 bool fast_plan_supported(const mafe_frontend_desc* d) {
   if (stft_plan_supported(d)) return true;
+  if (stftn_plan_supported(d)) return true;
   if (f400_plan_supported(d)) return true;
   if (d->n_fft != kNfft || d->center || d->out_kind != MAFE_OUT_LOGMEL || d->power != 2.0f || d->spec_scale != 1.0f)
     return false;
@@ -586,6 +600,29 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       w256[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
     }
   int rc;
+  th->stftn = stftn_plan_supported(d);
+  if (th->stftn) {
+    const int N1 = th->stftn, N = 16 * N1, B = N1 == 25 ? 5 : 4;   // N1 = 5 x B: twiddles W_N1^(j1 k1), j1 = 1..4, k1 = 1..B-1
+    std::vector<float> wn(N);
+    for (int i = 0; i < N; ++i) wn[i] = 0.5f * d->window[i];   // 1/2: the pair separation leaves 2X
+    std::vector<float2> twn(N);
+    for (int kj = 0; kj < N1; ++kj)
+      for (int t = 0; t < 16; ++t) {
+        double a = -2.0 * M_PI * (double)(t * kj) / (double)N;
+        twn[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
+      }
+    memset(th->tws, 0, sizeof(th->tws));
+    for (int j1 = 1; j1 < 5; ++j1)
+      for (int k1 = 1; k1 < B; ++k1) {
+        double a = -2.0 * M_PI * (double)(j1 * k1) / (double)N1;
+        th->tws[(j1 - 1) * (B - 1) + (k1 - 1)] = make_float2((float)cos(a), (float)sin(a));
+      }
+    if ((rc = up(&th->dev.window, wn))) return rc;
+    if ((rc = up(&th->tw400_dev, twn))) return rc;
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(stftn16_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftN<20>::kTotal));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(stftn16_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftN<25>::kTotal));
+    return MAFE_OK;
+  }
   th->f400 = !th->stft && f400_plan_supported(d);
   if (th->f400) {
     std::vector<float> w400(kN400);
@@ -698,6 +735,22 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     fbank400_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, f400_smem_bytes(F.plane_rows), ctx->stream>>>(F, th->sweep400);
     MAFE_LAUNCH_CHECK(ctx);
     return kFastNeedsPost;
+  }
+  if (th->stftn) {
+    if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
+    StftNParams S;
+    S.wave = (const float*)wave; S.total_samples = b->wave_len;
+    S.sample_offsets = b->sample_offsets_dev; S.frame_offsets = b->frame_offsets_dev; S.tiles = b->tiles_dev;
+    S.n_tiles = b->n_tiles; S.hop = d.hop; S.center = d.center; S.pad_mode = d.pad_mode;
+    S.window = th->dev.window; S.twn = th->tw400_dev; S.out = out; S.queue_head = b->queue_dev;
+    for (int i = 0; i < 16; ++i) S.tws[i] = th->tws[i];
+    MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
+    ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+    const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
+    if (th->stftn == 20) stftn16_kernel<20><<<grid, kFastThreads, StftN<20>::kTotal, ctx->stream>>>(S);
+    else stftn16_kernel<25><<<grid, kFastThreads, StftN<25>::kTotal, ctx->stream>>>(S);
+    MAFE_LAUNCH_CHECK(ctx);
+    return MAFE_OK;
   }
   if (th->stft) {
     if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;

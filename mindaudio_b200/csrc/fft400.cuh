@@ -50,4 +50,25 @@ MAFE_HD void fft25(cpx* v, const TW* tw25) {
   for (int k1 = 0; k1 < 5; ++k1) dft5(v[5 * k1], v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);  // over j1 -> X[k1 + 5 k2] at v[5 k1 + k2]
 }
 
+// ---- 20-point DFT (20 = 4 x 5) for the 320-point transform (320 = 20 x 16; deepspeech2's stft) ----
+// position of output bin k (0..19) inside v[] after fft20(): X[k1 + 4 k2] lives at v[5 k1 + k2]
+MAFE_HD constexpr int fft20_pos(int k) { return 5 * (k % 4) + k / 4; }
+
+// forward 20-point DFT of v[0..19] (natural order in: v[j], j = 5 j2 + j1, j1 = 0..4, j2 = 0..3); output bin k at
+// v[fft20_pos(k)].  tw20[(j1-1)*3 + (k1-1)] = W20^(j1 k1) for j1 = 1..4, k1 = 1..3 (12 entries).
+template <typename TW>
+MAFE_HD void fft20(cpx* v, const TW* tw20) {
+#pragma unroll
+  for (int j1 = 0; j1 < 5; ++j1) dft4(v[j1], v[j1 + 5], v[j1 + 10], v[j1 + 15]);   // over j2 -> A[j1][k1] at v[j1 + 5 k1]
+#pragma unroll
+  for (int j1 = 1; j1 < 5; ++j1)
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1) {
+      const TW w = tw20[(j1 - 1) * 3 + (k1 - 1)];
+      v[j1 + 5 * k1] = cmulf(v[j1 + 5 * k1], cx(w.x, w.y));
+    }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft5(v[5 * k1], v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);  // over j1 -> X[k1 + 4 k2] at v[5 k1 + k2]
+}
+
 }  // namespace mafe

@@ -1,0 +1,251 @@
+// stftn16.cuh -- specialised STFT kernel for n_fft = 16 * N1 with N1 = 20 (n_fft 320: deepspeech2's
+// mindaudio.stft(n_fft=320, hop_length=160, win_length=320), examples/deepspeech2/dataset.py:39-41) and N1 = 25
+// (n_fft 400): spectrum.stft, mindaudio/data/spectrum.py:125-278, complex64 [frame][n_fft/2 + 1] out.
+// Included by fbank512.cu.
+//
+// Same machinery as fbank400.cuh (persistent CTAs, tile queue, staged next-tile preparation, TMA bulk load of the
+// waveform tile, in-place pad pass for the first / last tile of an utterance,
+// frame pairs packed a + i*b): each lane of a 16-lane group transforms N1 points in registers (4 x 5 or 5 x 5),
+// W_N twiddle, the 16-point stage runs as 2 * N1 independent 16-point DFTs per warp in two rounds of 32 lanes.
+// Every warp owns its two pairs from the transform to the store; rows are written with lanes = consecutive bins.
+#pragma once
+#include "fft400.cuh"
+
+namespace mafe {
+
+template <int N1>
+struct StftN {
+  static constexpr int kN = 16 * N1;
+  static constexpr int kBins = kN / 2 + 1;
+  static constexpr int kSlot = N1 * kRowStride;                 // N1 rows x 17 >= kN + 1 outputs (340 / 425 complex)
+  static constexpr int kMaxHop = kN / 2;
+  static constexpr int kRawBytes = (((kTileFrames - 1) * kMaxHop + kN) * 4 + 64 + 127) & ~127;
+  static constexpr int kZBytes = ((kPairs * kSlot * 8) + 127) & ~127;
+  static constexpr size_t kRaw = kZBytes;                       // the waveform tile (own region: the next tile is
+                                                                // fetched while this one is transformed and stored)
+  static constexpr size_t kWin = kRaw + kRawBytes;              // float[kN]
+  static constexpr size_t kTw = kWin + sizeof(float) * kN;      // float2[N1][16]  W_N^(t kj)
+  static constexpr size_t kBar = kTw + sizeof(float2) * kN;
+  static constexpr size_t kInfo = kBar + 32;
+  static constexpr size_t kTotal = kInfo + 2 * 96;
+  static_assert(kRaw % 128 == 0 && 2 * (kTotal + 1024) <= 228 * 1024, "raw landing zone / 2 CTAs per SM");
+  static_assert(kSlot >= kN + 1, "slot holds the spectrum and the copy of bin 0");
+};
+
+struct StftNParams {
+  const float* wave;
+  int64_t total_samples;
+  const int64_t* sample_offsets;
+  const int64_t* frame_offsets;
+  const Tile* tiles;
+  int n_tiles;
+  int hop, center, pad_mode;
+  const float* window;     // [kN], pre-scaled by 1/2 (the pair separation leaves 2X)
+  const float2* twn;       // [N1][16]  W_N^(t kj)
+  float* out;              // [total_frames][kBins] complex64
+  int* queue_head;
+  float2 tws[16];          // W_N1^(j1 k1): 16 (N1 = 25) or 12 (N1 = 20) entries, kernel-parameter constant bank
+};
+
+template <int N1>
+__global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_constant__ StftNParams P) {
+  typedef StftN<N1> G;
+  constexpr int kN = G::kN, kBins = G::kBins, kSlot = G::kSlot;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* Zs = reinterpret_cast<float2*>(smem);
+  float* rawz = reinterpret_cast<float*>(smem + G::kRaw);
+  float* s_win = reinterpret_cast<float*>(smem + G::kWin);
+  float2* s_tw = reinterpret_cast<float2*>(smem + G::kTw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::kBar);
+  int* s_work = reinterpret_cast<int*>(bars) + 4;
+  F400TileInfo* info = reinterpret_cast<F400TileInfo*>(smem + G::kInfo);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hop = P.hop;
+  for (int i = tid; i < kN; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.twn[i]; }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh / fbank400.cuh) ----
+  int nx_w = P.n_tiles;
+  Tile nx_tile = {0, 0};
+  int64_t nx_off = 0, nx_off1 = 0, nx_fo0 = 0, nx_fo1 = 0;
+  auto load_offsets = [&]() {
+    nx_off = P.sample_offsets[nx_tile.utt];
+    nx_off1 = P.sample_offsets[nx_tile.utt + 1];
+    nx_fo0 = P.frame_offsets[nx_tile.utt];
+    nx_fo1 = P.frame_offsets[nx_tile.utt + 1];
+  };
+  auto issue_tile = [&](int slot) {
+    const int T = (int)(nx_fo1 - nx_fo0);
+    const int64_t L = nx_off1 - nx_off;
+    const int nf = min(kTileFrames, T - nx_tile.frame0);
+    const int pad = P.center ? kN / 2 : 0;
+    const int64_t p_lo = (int64_t)nx_tile.frame0 * hop - pad;
+    const int64_t p_hi = p_lo + (int64_t)(nf - 1) * hop + kN;
+    const int64_t u_lo = p_lo < 0 ? 0 : p_lo, u_hi = p_hi > L ? L : p_hi;
+    const int lpad = (int)(u_lo - p_lo);   // 0 or pad (160 / 200 floats: keeps the 16 B alignment of the bulk copy)
+    const int64_t g_lo = nx_off + u_lo, g_hi = nx_off + (u_hi > u_lo ? u_hi : u_lo);
+    const int64_t ga = (g_lo * 4) & ~(int64_t)15;
+    const int64_t total16 = (P.total_samples * 4) & ~(int64_t)15;
+    int64_t gb = (g_hi * 4 + 15) & ~(int64_t)15;
+    if (gb > total16) gb = total16;
+    const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (bytes) {
+      mbar_expect_tx(&bars[slot], bytes);
+      tma_bulk_g2s(rawz + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+    } else {
+      mbar_arrive(&bars[slot]);
+    }
+    F400TileInfo ti_;
+    ti_.out_row = nx_fo0 + nx_tile.frame0;
+    ti_.p_lo = p_lo; ti_.u_lo = u_lo; ti_.off = nx_off; ti_.L = L;
+    ti_.base_elem = ga / 4;
+    ti_.cov_end = bytes ? gb / 4 : g_lo;
+    ti_.end_elem = g_hi;
+    ti_.nf = nf;
+    ti_.shift = (int)(g_lo - ga / 4);
+    ti_.n_loaded = (int)(g_hi - g_lo);
+    ti_.lpad = lpad;
+    ti_.utt = nx_tile.utt;
+    ti_.tile_len = (nf - 1) * hop + kN;
+    info[slot] = ti_;
+  };
+  if (tid == 0) {
+    nx_w = atomicAdd(P.queue_head, 1);
+    s_work[0] = nx_w;
+    if (nx_w < P.n_tiles) { nx_tile = P.tiles[nx_w]; load_offsets(); issue_tile(0); }
+  }
+  __syncthreads();
+
+  uint32_t phase0 = 0, phase1 = 0;
+  int buf = 0;
+  const int t = lane & 15;
+  const int pair = warp * 2 + (lane >> 4);
+  for (;; buf ^= 1) {
+    if (s_work[buf] >= P.n_tiles) break;
+    if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1: claim
+    const F400TileInfo cur = info[buf];
+    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    float* xr = rawz + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
+    if (cur.cov_end < cur.end_elem) {   // bytes the 16 B-granular bulk copy could not cover (end of the flat array)
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rawz[cur.lpad + (e - cur.base_elem)] = P.wave[e];
+      __syncthreads();
+    }
+    if (cur.lpad > 0 || cur.lpad + cur.n_loaded < cur.tile_len) {
+      // ---- pad pass (first / last tile of an utterance): padded samples outside the loaded range, in place ----
+      const int d_end = cur.lpad + cur.n_loaded;
+      const int n_fill = cur.lpad + (cur.tile_len - d_end);
+#pragma unroll 1
+      for (int e = tid; e < n_fill; e += kFastThreads) {
+        const int i = e < cur.lpad ? e : d_end + (e - cur.lpad);
+        const int64_t u = pad_index_fast(cur.p_lo + i, cur.L, P.pad_mode);
+        float x = 0.f;
+        if (u >= 0) {
+          const int64_t r = u - cur.u_lo;
+          x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
+        }
+        xr[i] = x;
+      }
+      __syncthreads();
+    }
+
+    // ---- load: frame pair -> N1 windowed complex points per lane ----
+    cpx v[N1];
+    {
+      const float* xa = xr + (2 * pair) * hop + t;
+      const float* xb = xa + hop;
+      const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
+#pragma unroll
+      for (int j = 0; j < N1; ++j) {
+        const float a = fa_ok ? xa[16 * j] : 0.f;
+        const float b = fb_ok ? xb[16 * j] : 0.f;
+        const float w = s_win[t + 16 * j];
+        v[j] = cx(a * w, b * w);
+      }
+    }
+    __syncthreads();   // the waveform has been consumed: the buffer may be refilled
+    if (tid == 0) {    // stage 2: publish the claim, fetch the tile record
+      s_work[buf ^ 1] = nx_w;
+      if (nx_w < P.n_tiles) nx_tile = P.tiles[nx_w];
+    }
+
+    // ---- stage 1: N1-point DFT in registers, twiddle W_N^(t kj), rows [kj][t] of the pair's slot ----
+    if (N1 == 25) fft25(v, P.tws); else fft20(v, P.tws);
+    {
+      float2* slot = Zs + pair * kSlot;
+#pragma unroll
+      for (int kj = 0; kj < N1; ++kj) {
+        cpx x = v[N1 == 25 ? fft25_pos(kj) : fft20_pos(kj)];
+        if (kj > 0) {
+          const float2 tw = s_tw[kj * 16 + t];
+          x = cmulf(x, cx(tw.x, tw.y));
+        }
+        slot[kj * kRowStride + t] = make_float2(x.x, x.y);
+      }
+    }
+    __syncwarp();
+    if (tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3
+
+    // ---- stage 2: the warp's 2 x N1 sixteen-point DFTs over t, two rounds of 32 lanes ----
+    {
+      cpx u0[16], u1[16];
+      constexpr int kSecond = 2 * N1 - 32;                             // tasks of the second round (18 / 8)
+      const int q0 = lane / N1, kj0 = lane - N1 * q0;                  // task = lane        (0..31)
+      const int task1 = 32 + lane, q1 = task1 / N1, kj1 = task1 - N1 * q1;   // task = 32 + lane (valid for lane < kSecond)
+      const float2* s0 = Zs + (warp * 2 + q0) * kSlot;
+      const float2* s1 = Zs + (warp * 2 + (lane < kSecond ? q1 : 0)) * kSlot;
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) {
+        const float2 x = s0[kj0 * kRowStride + tt];
+        u0[tt] = cx(x.x, x.y);
+        const float2 y = s1[(lane < kSecond ? kj1 : 0) * kRowStride + tt];
+        u1[tt] = cx(y.x, y.y);
+      }
+      __syncwarp();
+      fft16(u0);
+      fft16(u1);
+      float2* d0 = Zs + (warp * 2 + q0) * kSlot;
+      float2* d1 = Zs + (warp * 2 + q1) * kSlot;
+#pragma unroll
+      for (int kt = 0; kt < 16; ++kt) {
+        const cpx x = u0[fft16_pos(kt)];
+        d0[kj0 + N1 * kt] = make_float2(x.x, x.y);
+        if (lane < kSecond) {
+          const cpx y = u1[fft16_pos(kt)];
+          d1[kj1 + N1 * kt] = make_float2(y.x, y.y);
+        }
+      }
+      if (kj0 == 0) d0[kN] = make_float2(u0[fft16_pos(0)].x, u0[fft16_pos(0)].y);   // bin 0 again: its own partner
+    }
+    __syncwarp();
+    if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4: the next tile lands while this one is stored
+
+    // ---- emit: this warp's two pairs, lanes = consecutive bins (rows of kBins complex64) ----
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int pq = warp * 2 + q;
+      const int fa = 2 * pq;
+      const float2* zp = Zs + pq * kSlot;
+      float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
+      float2* ob = oa + kBins;
+      const bool wa = fa < cur.nf, wb = fa + 1 < cur.nf;
+#pragma unroll 2
+      for (int k = lane; k < kBins; k += 32) {
+        const float2 zk = zp[k];
+        const float2 zn = zp[kN - k];
+        // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
+        if (wa) oa[k] = make_float2(zk.x + zn.x, zk.y - zn.y);
+        if (wb) ob[k] = make_float2(zk.y + zn.y, zn.x - zk.x);
+      }
+    }
+    __syncthreads();   // the Z slots may be overwritten; s_work / info of the next tile are visible
+  }
+}
+
+}  // namespace mafe

@@ -77,6 +77,28 @@ def test_stft_float64_int_and_edge_lengths(ma):
     assert ma.stft(np.zeros((0, 2048), dtype=np.float32)).shape == (0, 257, 17)
 
 
+@pytest.mark.parametrize("n_fft,hop,win,window,mode,center", [
+    (320, 160, 320, "hann", "constant", True),      # deepspeech2: examples/deepspeech2/dataset.py:39-41
+    (320, 80, None, "hann", "reflect", True), (320, 160, 200, "hamming", "edge", True), (320, 100, None, "hann", "constant", False),
+    (400, 160, None, "hann", "reflect", True), (400, 200, 400, "hann", "constant", True), (400, 100, 256, "blackman", "symmetric", True),
+    (400, 77, None, "hann", "constant", False),
+])
+def test_stft_320_400_kernel(ma, n_fft, hop, win, window, mode, center):
+    """stftn16_kernel<20 / 25>: 20- / 25-point register DFT x 16, pad pass in the edge tiles, every pad mode, ragged
+    lengths around the tile borders (a tile = 32 frames), single utterances shorter than one tile."""
+    kw = dict(n_fft=n_fft, hop_length=hop, win_length=win, window=window, pad_mode=mode, center=center)
+    for shape in ((3, 16000), (2, 32 * hop), (1, 32 * hop + n_fft - 1), (5, n_fft), (2, 1000)):
+        x = synth(sum(shape), shape)
+        out, ref = ma.stft(x, **kw), R.stft(x, **kw)
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        for b in range(shape[0]):
+            assert stft_err(out[b], ref[b]) <= TOL_STFT, (shape, b)
+    x1 = synth(9, (4001,)).astype(np.float64)
+    assert stft_err(ma.stft(x1, **kw), R.stft(x1, **kw)) <= TOL_STFT
+    mag, _ = ma.magphase(ma.stft(x1, **kw), 1.0)
+    assert np.max(np.abs(mag - np.abs(R.stft(x1, **kw)))) <= TOL_STFT * np.max(np.abs(R.stft(x1, **kw)))
+
+
 def test_istft_roundtrip_reference_assertion(ma, golden):
     x = golden.wav()
     res = ma.istft(ma.stft(x))
