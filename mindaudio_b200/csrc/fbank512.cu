@@ -450,9 +450,13 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
     for (int h = 0; h < 2; ++h) {
       const int kk_end = b + ((h == 0 && b == NK) ? 1 : 0);
       int cur = lo;
+      if (kk_end - a > 16 * kV3MaskWords) return false;
       for (int kk = a; kk < kk_end; ++kk) {
         const BinEntry& e = bins[2 * kk + h];
-        S.step[h * kV3HalfStride + kk] = V3Step{e.w0, e.w1, e.f0 - cur, 0};
+        const int nret = e.f0 - cur;
+        if (nret > 3) return false;   // 2 bits per step in the retire mask
+        S.step[h * kV3HalfStride + kk] = V3Step{e.w0, e.w1, nret, 0};
+        S.nret_mask[h * W + w][(kk - a) / 16] |= (uint32_t)nret << (2 * ((kk - a) % 16));
         cur = e.f0;
       }
       S.tail[h][w] = (unsigned char)(hi - cur + 1);

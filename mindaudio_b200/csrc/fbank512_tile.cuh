@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) frame_sum_utt_kernel(const V2Params P, co
 // ---------------------------------------------------------------------------------------------
 // utterance CMVN from the fused statistics: x = (x - mean) / std, tile-parallel, float4
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cmvn_utt_apply_kernel(float* __restrict__ feats, const Tile* __restrict__ tiles, int n_tiles,
+__global__ void __launch_bounds__(256, 8) cmvn_utt_apply_kernel(float* __restrict__ feats, const Tile* __restrict__ tiles, int n_tiles,
                                                              const int64_t* __restrict__ frame_offsets,
                                                              const double* __restrict__ utt_stats, int mean_norm, int std_norm) {
   __shared__ float s_mean[kV2Mels], s_inv[kV2Mels];

@@ -30,8 +30,11 @@ struct __align__(16) V3Step {
   int nret;
   int pad;
 };
+constexpr int kV3MaskWords = 4;      // 16 steps x 2 bits per word: a warp range may hold up to 64 bins
 struct V3Sweep {  // kernel-parameter resident (constant bank 0)
   V3Step step[2 * kV3HalfStride];
+  uint32_t nret_mask[2 * kFastWarps][kV3MaskWords];   // the retire counts of a (half, warp) range, 2 bits per step: kept in
+                                                      // a register so that the retire branch does not wait for a load
   unsigned char tail[2][kFastWarps];
   unsigned char kk0[kFastWarps + 1];
   unsigned char row0[kFastWarps];      // first plane row of a warp: it emits filters lo .. hi into consecutive rows
@@ -88,18 +91,27 @@ __device__ __forceinline__ void sweep_v3(const V3Sweep& S, int g, int warp, cons
       acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride;
     } while (--n);
   };
+  const int gw = g * kFastWarps + warp;
+  int word = 0;
 #pragma unroll 1
   do {
-    const V3Step st = S.step[si];
-    if (st.nret) retire(st.nret);
-    const float2 zk = lds_f2(ak);
-    const float2 zn = lds_f2(an);
-    bump<1>(si); bump<8>(ak); bump<-8>(an);
-    const float re = fmaf(sgn, zn.x, zk.x);
-    const float im = fmaf(-sgn, zn.y, zk.y);
-    const float pw = fmaf(re, re, im * im);
-    acc_lo = fmaf(st.w0, pw, acc_lo);
-    acc_hi = fmaf(st.w1, pw, acc_hi);
+    uint32_t m = S.nret_mask[gw][word++];   // retire counts of the next 16 steps
+    const int chunk_end = min(si + 16, si_end);
+#pragma unroll 1
+    do {
+      const float2 w = *reinterpret_cast<const float2*>(&S.step[si].w0);
+      const int nr = m & 3u;
+      m >>= 2;
+      if (nr) retire(nr);
+      const float2 zk = lds_f2(ak);
+      const float2 zn = lds_f2(an);
+      bump<1>(si); bump<8>(ak); bump<-8>(an);
+      const float re = fmaf(sgn, zn.x, zk.x);
+      const float im = fmaf(-sgn, zn.y, zk.y);
+      const float pw = fmaf(re, re, im * im);
+      acc_lo = fmaf(w.x, pw, acc_lo);
+      acc_hi = fmaf(w.y, pw, acc_hi);
+    } while (si != chunk_end);
   } while (si != si_end);
   retire(S.tail[g][warp]);   // >= 1: the last filter is always retired after the last bin
 }
