@@ -31,6 +31,7 @@ static_assert(kRaw400InZ % 128 == 0, "raw landing zone alignment");
 // filters, then accumulates bin k into filters (cur, cur + 1) with weights (w0, w1).  Cost balanced on the host.
 struct F400Sweep {
   V3Step step[kBins400 + 3];
+  uint32_t nret_mask[kFastWarps][kV3MaskWords];   // retire counts of a warp's range, 2 bits per step (register resident)
   unsigned char tail[kFastWarps];
   unsigned char kk0[kFastWarps + 1];
   unsigned char row0[kFastWarps];
@@ -273,18 +274,26 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
           acc_lo = acc_hi; acc_hi = 0.f; dst += kPlaneStride;
         } while (--n);
       };
+      int word = 0;
 #pragma unroll 1
       do {
-        const V3Step st = S.step[si];
-        if (st.nret) retire(st.nret);
-        const float2 zk = lds_f2(ak);
-        const float2 zn = lds_f2(an);
-        bump<1>(si); bump<8>(ak); bump<-8>(an);
-        const float re = fmaf(sgn, zn.x, zk.x);
-        const float im = fmaf(-sgn, zn.y, zk.y);
-        const float pw = fmaf(re, re, im * im);
-        acc_lo = fmaf(st.w0, pw, acc_lo);
-        acc_hi = fmaf(st.w1, pw, acc_hi);
+        uint32_t m = S.nret_mask[warp][word++];   // retire counts of the next 16 steps
+        const int chunk_end = min(si + 16, si_end);
+#pragma unroll 1
+        do {
+          const float2 w = *reinterpret_cast<const float2*>(&S.step[si].w0);
+          const int nr = m & 3u;
+          m >>= 2;
+          if (nr) retire(nr);
+          const float2 zk = lds_f2(ak);
+          const float2 zn = lds_f2(an);
+          bump<1>(si); bump<8>(ak); bump<-8>(an);
+          const float re = fmaf(sgn, zn.x, zk.x);
+          const float im = fmaf(-sgn, zn.y, zk.y);
+          const float pw = fmaf(re, re, im * im);
+          acc_lo = fmaf(w.x, pw, acc_lo);
+          acc_hi = fmaf(w.y, pw, acc_hi);
+        } while (si != chunk_end);
       } while (si != si_end);
       retire(S.tail[warp]);
     }

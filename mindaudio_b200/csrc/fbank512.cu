@@ -515,8 +515,12 @@ static bool build_f400_program(const std::vector<BinEntry>& bins, int nm, F400Sw
         ++nrow[m];
       }
     int cur = lo;
+    if (b - a > 16 * kV3MaskWords) return false;
     for (int k = a; k < b; ++k) {
-      S.step[k] = V3Step{bins[k].w0, bins[k].w1, bins[k].f0 - cur, 0};
+      const int nret = bins[k].f0 - cur;
+      if (nret > 3) return false;   // 2 bits per step in the retire mask
+      S.step[k] = V3Step{bins[k].w0, bins[k].w1, nret, 0};
+      S.nret_mask[w][(k - a) / 16] |= (uint32_t)nret << (2 * ((k - a) % 16));
       cur = bins[k].f0;
     }
     S.tail[w] = (unsigned char)(hi - cur + 1);
