@@ -297,3 +297,38 @@ def test_feature_domain_ops(ma):
     with pytest.raises(ValueError):
         ma.frequencymasking(spec, frequency_mask_param=65)
 
+
+def test_bench_size_batch_properties(ma):
+    """At the bench's scale (thousands of ragged utterances in ONE launch) the oracle cannot follow; size-independent
+    properties instead: (1) independence -- an utterance's features do not depend on its batch mates (a sample of them
+    recomputed in a small batch agree to FP32 rounding: the frame mean is summed by another kernel there); (2) utterance CMVN leaves zero mean / unit variance per
+    mel bin; (3) the frame count follows floor((L - 400) / 160) + 1 for every utterance."""
+    torch = pytest.importorskip("torch")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rng = np.random.default_rng(3)
+    n = 4096
+    lens = rng.integers(16000, 160001, size=n).astype(np.int64)
+    wave = torch.clamp(0.05 * torch.randn(int(lens.sum()), generator=g, device="cuda"), -1, 1) * 32768.0
+    so = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=so[1:])
+    raw_pipe, cmvn_pipe = ma.FbankPipeline(cmvn=None), ma.FbankPipeline(cmvn="utt")
+    b = raw_pipe.layout(lens.tolist())
+    out = raw_pipe(wave, batch=b)
+    outn = cmvn_pipe(wave, batch=cmvn_pipe.layout(lens.tolist()))
+    torch.cuda.synchronize()
+    fo = b.frame_offsets
+    assert np.array_equal(np.diff(fo), (lens - 400) // 160 + 1)
+    pick = rng.choice(n, size=24, replace=False)
+    sub = torch.cat([wave[so[u]:so[u + 1]] for u in pick])
+    sub_out = raw_pipe(sub, lengths=[int(lens[u]) for u in pick])
+    torch.cuda.synchronize()
+    pos = 0
+    for u in pick:
+        t = int(fo[u + 1] - fo[u])
+        assert logmel_err(out[fo[u]:fo[u + 1]].cpu().numpy(), sub_out[pos:pos + t].cpu().numpy().astype(np.float64)) <= 1.0, u
+        pos += t
+    for u in pick[:8]:
+        x = outn[fo[u]:fo[u + 1]].double()
+        assert float(x.mean(dim=0).abs().max()) < 1e-3 and float((x.std(dim=0, unbiased=False) - 1).abs().max()) < 1e-3, u
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(outn).all())
+
