@@ -16,4 +16,13 @@ for kw in (dict(n_fft=512, hop_length=256), dict(n_fft=512, hop_length=128, pad_
     assert np.abs(s - r).max() / np.abs(r).max() < 1e-5
 f = ma.fbank(x[0], n_mels=80, n_fft=400, hop_length=160)
 m = ma.mfcc(x)
+for kw in (dict(n_fft=320, hop_length=160, win_length=320), dict(n_fft=400, hop_length=100, pad_mode="reflect"), dict(n_fft=320, hop_length=80, center=False)):
+    s = ma.stft(x, **kw); r = R.stft(x, **kw)
+    assert np.abs(s - r).max() / np.abs(r).max() < 1e-5
+import random
+pipe = ma.FbankPipeline(cmvn=None)
+xs_pad, xs_len, xs_mask = pipe.features_padded([w for w in waves if len(w) >= 400], max_len=120, spec_aug_conf={"num_t_mask": 2, "num_f_mask": 2, "max_t": 50, "max_f": 10}, rng=random.Random(3))
+ma.sliding_window_cmn(np.asarray(xs_pad[:2]), 20, 5, norm_vars=True)
+ma.spectral_centroid(x, 16000)
+ma.mfcc(x, n_fft=1024, n_mels=40, n_mfcc=13, deltas=False, context=False)
 print("sanitize script ok")
