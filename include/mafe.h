@@ -274,6 +274,14 @@ int mafe_sliding_window_cmn(mafe_ctx* ctx, const float* x_dev, float* out_dev, i
 int mafe_mask_rects(mafe_ctx* ctx, float* feats_dev, const int64_t* frame_offsets_dev, int32_t n_items, int32_t dim,
                     const int32_t* rects_dev, int32_t n_rects, float value);
 
+/* ---- phase vocoder ("next" row f2: mindaudio/data/augment.py:795-871 time_stretch / _phase_vocoder) ---- */
+/* spec_dev [n_mats][n_frames][n_bins] complex64 frame-major -> out_dev [n_mats][n_steps][n_bins]: time step t reads
+ * frames floor(t*rate), +1 (zero beyond the end), interpolates the magnitudes and accumulates the phase advance
+ * (float32 accumulator updated in float64, as numpy does for `phase_acc += ...`).  phi_advance_dev: double[n_bins]
+ * expected phase advance per bin (linspace(0, pi*hop, n_bins)). */
+int mafe_phase_vocoder(mafe_ctx* ctx, const float* spec_dev, int32_t n_mats, int32_t n_frames, int32_t n_bins, double rate,
+                       const double* phi_advance_dev, int32_t n_steps, float* out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,7 @@ _PROTOS = {
     "mafe_pad_sequence": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, C.c_float, _I32, _P, _P]),
     "mafe_sliding_window_cmn": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
     "mafe_mask_rects": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I32, C.c_float]),
+    "mafe_phase_vocoder": (C.c_int, [_P, _P, _I32, _I32, _I32, C.c_double, _P, _I32, _P]),
 }
 
 _lib = None

@@ -372,6 +372,35 @@ __global__ void mask_rects_kernel(float* __restrict__ feats, const int64_t* __re
   }
 }
 
+// phase vocoder (augment.py:828-871): one thread per (matrix, bin) walks the output steps; lanes = consecutive bins
+__global__ void phase_vocoder_kernel(const float2* __restrict__ spec, int n_mats, int T, int F, double rate,
+                                     const double* __restrict__ phi, int n_steps, float2* __restrict__ out) {
+  const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= (int64_t)n_mats * F) return;
+  const int mat = (int)(id / F), k = (int)(id - (int64_t)mat * F);
+  const float2* sp = spec + (int64_t)mat * T * F + k;
+  float2* op = out + (int64_t)mat * n_steps * F + k;
+  const double phi_k = phi[k];
+  const double two_pi = 6.283185307179586476925286766559;
+  const float2 z0 = T > 0 ? sp[0] : make_float2(0.f, 0.f);
+  float phase_acc = atan2f(z0.y, z0.x);
+  for (int t = 0; t < n_steps; ++t) {
+    const double step = (double)t * rate;           // np.arange(0, T, rate)[t]
+    const int i0 = (int)step;
+    const double alpha = step - floor(step);        // np.mod(step, 1.0), step >= 0
+    const float2 c0 = i0 < T ? sp[(int64_t)i0 * F] : make_float2(0.f, 0.f);
+    const float2 c1 = i0 + 1 < T ? sp[(int64_t)(i0 + 1) * F] : make_float2(0.f, 0.f);
+    const float m0 = hypotf(c0.x, c0.y), m1 = hypotf(c1.x, c1.y);
+    const float mag = (float)((1.0 - alpha) * (double)m0 + alpha * (double)m1);
+    float sn, cs;
+    sincosf(phase_acc, &sn, &cs);
+    op[(int64_t)t * F] = make_float2(cs * mag, sn * mag);
+    double dphase = (double)atan2f(c1.y, c1.x) - (double)atan2f(c0.y, c0.x) - phi_k;
+    dphase = dphase - two_pi * rint(dphase / two_pi);
+    phase_acc = (float)((double)phase_acc + (phi_k + dphase));
+  }
+}
+
 extern "C" {
 
 int mafe_magphase(mafe_ctx* ctx, const float* z, int64_t n, float power, float* mag, float* phase) {
@@ -613,6 +642,21 @@ int mafe_mask_rects(mafe_ctx* ctx, float* feats, const int64_t* frame_offsets, i
   MAFE_REQUIRE(feats && frame_offsets && rects, "mafe_mask_rects: NULL buffer");
   cudaSetDevice(ctx->device);
   mask_rects_kernel<<<n_rects, 256, 0, ctx->stream>>>(feats, frame_offsets, n_items, dim, rects, value);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_phase_vocoder(mafe_ctx* ctx, const float* spec, int32_t n_mats, int32_t n_frames, int32_t n_bins, double rate,
+                       const double* phi_advance, int32_t n_steps, float* out) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(rate > 0.0, "rate must be a positive number");
+  MAFE_REQUIRE(n_mats >= 0 && n_frames >= 0 && n_bins > 0 && n_steps >= 0, "mafe_phase_vocoder: bad shape");
+  if (n_mats == 0 || n_steps == 0) return MAFE_OK;
+  MAFE_REQUIRE(spec && phi_advance && out, "mafe_phase_vocoder: NULL buffer");
+  cudaSetDevice(ctx->device);
+  const int64_t n = (int64_t)n_mats * n_bins;
+  phase_vocoder_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const float2*)spec, n_mats, n_frames, n_bins, rate,
+                                                                           phi_advance, n_steps, (float2*)out);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }

@@ -153,5 +153,13 @@ def load_spec_aug():
     return _cache["specaug"]
 
 
+def load_phase_vocoder():
+    """``_phase_vocoder`` (mindaudio/data/augment.py:828-871), as written."""
+    if "pvoc" not in _cache:
+        g = _extract_functions(os.path.join(REF_ROOT, "mindaudio", "data", "augment.py"), ["_phase_vocoder"])
+        _cache["pvoc"] = g["_phase_vocoder"]
+    return _cache["pvoc"]
+
+
 def sample_wav(name="BAC009S0002W0122.wav"):
     return os.path.join(REF_ROOT, "tests", "samples", "ASR", name)

@@ -693,3 +693,41 @@ def mask_along_axis(spec, mask_param, mask_start, mask_value, axis):
     out[tuple(idx)] = mask_value
     return out
 
+
+# ---------------------------------------------------------------------------------------------
+# phase vocoder / time_stretch (scope row f2): mindaudio/data/augment.py:795-871
+# ---------------------------------------------------------------------------------------------
+def phase_vocoder(matrix, rate, hop_length=None, n_fft=None):
+    """augment.py:828-871 with its dtype flow: complex64 in -> float32 phase accumulator updated in float64."""
+    matrix = np.asarray(matrix)
+    if n_fft is None:
+        n_fft = 2 * (matrix.shape[-2] - 1)
+    if hop_length is None:
+        hop_length = int(n_fft // 4)
+    time_steps = np.arange(0, matrix.shape[-1], rate, dtype=np.float64)
+    shape = list(matrix.shape)
+    shape[-1] = len(time_steps)
+    d_stretch = np.zeros_like(matrix, shape=shape)
+    phi_advance = np.linspace(0, np.pi * hop_length, matrix.shape[-2])
+    phase_acc = np.angle(matrix[..., 0])
+    padding = [(0, 0) for _ in matrix.shape]
+    padding[-1] = (0, 2)
+    matrix = np.pad(matrix, padding, mode="constant")
+    for t, step in enumerate(time_steps):
+        columns = matrix[..., int(step): int(step + 2)]
+        alpha = np.mod(step, 1.0)
+        mag = (1.0 - alpha) * np.abs(columns[..., 0]) + alpha * np.abs(columns[..., 1])
+        d_stretch[..., t] = (np.cos(phase_acc) + 1j * np.sin(phase_acc)) * mag
+        dphase = np.angle(columns[..., 1]) - np.angle(columns[..., 0]) - phi_advance
+        dphase = dphase - 2.0 * np.pi * np.round(dphase / (2.0 * np.pi))
+        phase_acc += phi_advance + dphase
+    return d_stretch
+
+
+def time_stretch(waveforms, rate):
+    if rate <= 0:
+        raise ValueError("rate must be a positive number")
+    waveforms = np.asarray(waveforms)
+    spec = stft(waveforms)
+    return istft(phase_vocoder(spec, rate), length=int(round(waveforms.shape[-1] / rate)))
+

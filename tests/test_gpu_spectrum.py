@@ -188,3 +188,27 @@ def test_spectrogram_melspectrogram_melscale(ma, golden):
     assert full.shape[0] == 400 and rel(full, R.spectrogram(x[:8000], onesided=False)) <= 1e-5
     xb = synth(9, (2, 3, 4000))
     assert rel(ma.spectrogram(xb, pad=7, power=0.5), R.spectrogram(xb, pad=7, power=0.5)) <= 1e-5
+
+
+def test_phase_vocoder_and_time_stretch(ma):
+    """Scope row f2: _phase_vocoder / time_stretch (augment.py:795-871), STFT -> vocoder -> ISTFT on the device.
+    The reference's phase accumulator is a FLOAT32 array (np.angle of complex64) that reaches ~pi * hop * T rad: one
+    float32 ulp of the phase is up to 2e-3 rad here, and a 1-ulp difference between CUDA's and numpy's atan2f can flip
+    a rounding of the accumulator.  Parity is therefore judged at one phase ulp x magnitude (3e-3 of the scale); most
+    elements agree to 1e-6."""
+    x = synth(13, (2, 6000))
+    spec = R.stft(x)
+    for rate in (0.8, 1.0, 1.3, 2.0):
+        out, ref = ma.augment._phase_vocoder(spec, rate), R.phase_vocoder(spec, rate)
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        err = np.abs(out - ref)
+        assert np.max(err) <= 3e-3 * np.max(np.abs(ref)), rate
+        assert np.mean(err <= 1e-5 * np.max(np.abs(ref))) >= 0.98, rate
+        y, yr = ma.time_stretch(x, rate), R.time_stretch(x, rate)
+        assert y.shape == yr.shape and y.dtype == yr.dtype
+        assert np.max(np.abs(y - yr)) <= 3e-3 * np.max(np.abs(yr)), rate
+    y1 = ma.time_stretch(x[0].astype(np.float64), 1.5)
+    assert y1.shape == (4000,) and np.max(np.abs(y1 - R.time_stretch(x[0].astype(np.float64), 1.5))) <= 3e-3 * np.max(np.abs(y1))
+    with pytest.raises(ValueError):
+        ma.time_stretch(x, 0.0)
+
