@@ -261,13 +261,16 @@ def main():
     fp32_peak = eng.fp32_fma_peak()          # measured on this box, this run (FFMA microbenchmark in libmafe)
     t_fp32 = FLOP_PER_FRAME * n_frames / (fp32_peak * 1e12)
     # DRAM traffic of one launch from the committed `ncu --set full` capture of this very workload (profiles/)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_pipes = None, None, None
     tp = os.path.join(REPO, "profiles", "r01_fbank512_traffic.json")
     if os.path.isfile(tp):
         with open(tp) as fh:
             td = json.load(fh)
         if int(td.get("frames_per_launch", -1)) == int(n_frames):
             traffic, traffic_src = td["traffic_bytes_per_launch"], "profiles/r01_fbank512_traffic.json (dram__bytes_read+write)"
+            # pipe utilisation of the same committed capture (not measured in this run)
+            ncu_pipes = {k: td[k] for k in ("issue_active_pct", "pipe_fma_cycles_active_pct", "pipe_lsu_pct", "tensor_pipe_pct",
+                                            "registers_per_thread", "grid", "block") if k in td}
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_FRAME * n_frames,
                 "peak_source": peak_src, "kernel": "fbank512_v3_kernel",
@@ -277,6 +280,7 @@ def main():
                          "note": "FP32 FMA peak measured in this run by mafe_fp32_fma_peak (not in MEASURED_PEAKS.json); "
                                  "algorithmic flops = 14 253 per frame (SURVEY.md 8d)"},
                 "frac_of_min_roofline": max(t_hbm, t_fp32) / k_avg_s,
+                "ncu_capture": ncu_pipes,
                 "step_share": {"fbank512_v3_kernel_ms": k_ms / max(k_n, 1), "frame_mean_prepass_ms": p_ms / max(p_n, 1),
                                "cmvn_apply_ms": c_ms / max(c_n, 1), "step_ms": ms / args.steps}}
 
