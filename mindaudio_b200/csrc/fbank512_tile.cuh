@@ -10,6 +10,7 @@ constexpr int kV2Flen = 400;
 constexpr int kV2Hop = 160;
 constexpr int kV2Mels = 80;
 constexpr int kV2Ylen = (kTileFrames - 1) * kV2Hop + kV2Flen;  // 5360 samples feed one tile
+constexpr int kCwRow = 172;        // coverage-table row: 160 + 8 (a vector group may run over the end) rounded to 16 B
 constexpr int kV2RawBytes = 21504;                              // (5360 + 1 prev) * 4 + alignment slack, 16 B multiple
 
 struct V2Params {
@@ -219,10 +220,15 @@ __global__ void __launch_bounds__(256) frame_sum_baked_kernel(const V2Params P, 
 // streams its whole utterance with deep load pipelining and issues a single atomic-free store.
 template <bool I16>
 __global__ void __launch_bounds__(256) frame_sum_utt_kernel(const V2Params P, const float* __restrict__ cw, double* utt_sum) {
-  __shared__ float s_cw[kV2Hop + 8];   // + 8: a vector group may run over the end of the table
+  // The coverage table four times, copy k shifted by k entries (s_cw4[k][j] = cw[(j + k) mod 160]): a thread's 4 (8)
+  // coefficients cw[r .. r+3] then are ONE aligned 16-byte load from copy r mod 4 -- lanes read consecutive quads.
+  // (With a single table the lane stride of 4 words made every scalar load a 4-way bank conflict: ncu showed 70 % of
+  // this kernel's shared-memory wavefronts were conflicts and the L1 data pipe, not HBM, at 81 %.)
+  __shared__ __align__(16) float s_cw4[4][kCwRow];
   __shared__ double ws[8];
   const int tid = threadIdx.x;
-  if (tid < kV2Hop + 8) s_cw[tid] = cw[tid % kV2Hop];
+  for (int i = tid; i < 4 * kCwRow; i += 256) s_cw4[i / kCwRow][i % kCwRow] = cw[(i % kCwRow + i / kCwRow) % kV2Hop];
+  const float* s_cw = s_cw4[0];
   __syncthreads();
   const uint32_t utt = blockIdx.x;
   const int64_t off = P.sample_offsets[utt];
@@ -268,7 +274,8 @@ __global__ void __launch_bounds__(256) frame_sum_utt_kernel(const V2Params P, co
     for (int64_t s = in_lo + tid; s < s_a; s += 256) scalar(s);
     for (int64_t s = s_b + tid; s < in_hi; s += 256) scalar(s);
     int r = (int)((s_a + (int64_t)V * tid) % kV2Hop);
-    constexpr int rstep = (V * 256) % kV2Hop;
+    constexpr int rstep = (V * 256) % kV2Hop;   // a multiple of 4: r mod 4 is fixed per thread
+    const float* cw_row = s_cw4[r & 3] - (r & 3);   // cw_row[r + i] = cw[(r + i) mod 160], 16 B aligned at r - (r & 3) ... see below
     const int64_t q_warp = tid & ~31;
 #pragma unroll 4
     for (int64_t q0 = 0; q0 + q_warp < nvec; q0 += 256) {   // warp-uniform trip count: the shuffle stays convergent
@@ -292,9 +299,15 @@ __global__ void __launch_bounds__(256) frame_sum_utt_kernel(const V2Params P, co
       float xp = __shfl_up_sync(0xffffffffu, x[V - 1], 1);
       if ((tid & 31) == 0 && ok) xp = gload<I16>(P.wave, g + s_a + V * q - 1, P.wave_scale);
       if (ok) {
+        float c[V];
+#pragma unroll
+        for (int i = 0; i < V; i += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cw_row + r + i);
+          c[i] = c4.x; c[i + 1] = c4.y; c[i + 2] = c4.z; c[i + 3] = c4.w;
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          acc = fmaf(fmaf(-P.pre_lo, xp, fmaf(-P.pre_hi, xp, x[i])), s_cw[r + i], acc);
+          acc = fmaf(fmaf(-P.pre_lo, xp, fmaf(-P.pre_hi, xp, x[i])), c[i], acc);
           xp = x[i];
         }
       }
