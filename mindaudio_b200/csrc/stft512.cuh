@@ -39,7 +39,8 @@ struct StftTileInfo {
 };
 static_assert(sizeof(StftTileInfo) <= 96, "StftTileInfo slot");
 
-constexpr int kStftSkew = kStftRawBytes / 4 + 16;   // floats from copy 0 to copy 1 of the tile: 16 banks apart
+constexpr int kStftSkew = kStftRawBytes / 4;   // floats from copy 0 to copy 1 of the tile
+static_assert(kStftSkew % 32 == 16 && (kStftSkew * 4) % 16 == 0, "copy 1 must sit 16 banks from copy 0 and keep the 16 B alignment of the bulk copy");
 struct StftSmem {
   static constexpr size_t kRaw = 0;                    // the waveform tile TWICE: the two frame pairs a warp folds start
                                                        // a multiple of 32 floats apart (hop 256), the upper half-warp
@@ -174,7 +175,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
       }
       __syncthreads();
     }
-    const float* xa = xr + (lane >> 4) * kStftSkew + (2 * pair) * hop + t;
+    // the upper half-warp's pair starts 2 * hop floats after the lower one: read the skewed copy when that offset would
+    // put both on (nearly) the same banks
+    const int pair_banks = (2 * hop) & 31;
+    const bool use_skew = pair_banks < 8 || pair_banks > 24;
+    const float* xa = xr + ((lane >> 4) && use_skew ? kStftSkew : 0) + (2 * pair) * hop + t;
     const float* xb = xa + hop;
     const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 
