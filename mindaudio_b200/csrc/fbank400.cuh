@@ -66,9 +66,14 @@ struct F400TileInfo {
 };
 static_assert(sizeof(F400TileInfo) <= 96, "F400TileInfo slot");
 
-// dynamic shared memory: [Z 54400][planes rows*33*4][window 1600][tw400 3200][bars 32][info 192]
+// dynamic shared memory: [Z 54400][planes rows*33*4][window 1600][tw400 3200][bars 32][info 192][skewed tile copy]
 __host__ __device__ inline size_t f400_planes_bytes(int rows) { return ((size_t)rows * kPlaneStride * 4 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t f400_smem_bytes(int rows) { return kZ400Bytes + f400_planes_bytes(rows) + 1600 + 3200 + 32 + 192; }
+// second copy of the waveform tile, 16 banks away from the first (which lands at float kRaw400InZ / 4 = 0 mod 32 of Z)
+__host__ __device__ inline size_t f400_skew_offset(int rows) {
+  return ((kZ400Bytes + f400_planes_bytes(rows) + 1600 + 3200 + 32 + 192 + 127) & ~(size_t)127) + 64;
+}
+__host__ __device__ inline size_t f400_smem_bytes(int rows) { return f400_skew_offset(rows) + kRaw400Bytes; }
+static_assert((kRaw400InZ / 4) % 32 == 0, "tile copy 0 starts on bank 0");
 
 __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_constant__ F400Params P,
                                                                    const __grid_constant__ F400Sweep S) {
@@ -86,6 +91,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
+  // the upper half-warp's pair starts 2 * hop floats after the lower one (hop 160: same bank): it reads a second copy
+  // of the tile that sits 16 banks away whenever the natural offset would collide
+  const int pair_banks = (2 * hop) & 31;
+  const bool use_skew = pair_banks < 8 || pair_banks > 24;
+  const int skew = (int)((f400_skew_offset(P.plane_rows) - kRaw400InZ) / 4);   // floats from copy 0 to copy 1
   for (int i = tid; i < kN400; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.tw400[i]; }
   if (tid < kPlaneStride) planes[S.zero_row * kPlaneStride + tid] = 0.f;
   if (tid == 0) {
@@ -125,8 +135,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
-      mbar_expect_tx(&bars[slot], bytes);
+      mbar_expect_tx(&bars[slot], use_skew ? 2 * bytes : bytes);
       tma_bulk_g2s(rawz + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+      if (use_skew) tma_bulk_g2s(rawz + skew + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
     } else {
       mbar_arrive(&bars[slot]);
     }
@@ -166,7 +177,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
     float* xr = rawz + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
     if (cur.cov_end < cur.end_elem) {   // bytes the 16 B-granular bulk copy could not cover (end of the flat array)
-      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rawz[cur.lpad + (e - cur.base_elem)] = P.wave[e];
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
+        const float x = P.wave[e];
+        rawz[cur.lpad + (e - cur.base_elem)] = x;
+        if (use_skew) rawz[skew + cur.lpad + (e - cur.base_elem)] = x;
+      }
       __syncthreads();
     }
     if (cur.lpad > 0 || cur.lpad + cur.n_loaded < cur.tile_len) {
@@ -183,6 +198,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
           x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
         }
         xr[i] = x;
+        if (use_skew) xr[skew + i] = x;
       }
       __syncthreads();
     }
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     // ---- load: frame pair -> 25 windowed complex points per lane ----
     cpx v[25];
     {
-      const float* xa = xr + (2 * pair) * hop + t;
+      const float* xa = xr + ((lane >> 4) && use_skew ? skew : 0) + (2 * pair) * hop + t;
       const float* xb = xa + hop;
       const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 #pragma unroll

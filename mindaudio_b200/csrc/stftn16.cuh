@@ -23,13 +23,16 @@ struct StftN {
   static constexpr int kZBytes = ((kPairs * kSlot * 8) + 127) & ~127;
   static constexpr size_t kRaw = kZBytes;                       // the waveform tile (own region: the next tile is
                                                                 // fetched while this one is transformed and stored)
-  static constexpr size_t kWin = kRaw + kRawBytes;              // float[kN]
+  static constexpr int kSkew = kRawBytes / 4 + 16;              // floats from copy 0 to the skewed copy 1 of the tile (16 banks
+                                                                // apart: with hop = 160 the two pairs of a warp start on the same bank)
+  static constexpr size_t kWin = kRaw + 2 * kRawBytes + 64;     // float[kN]
   static constexpr size_t kTw = kWin + sizeof(float) * kN;      // float2[N1][16]  W_N^(t kj)
   static constexpr size_t kBar = kTw + sizeof(float2) * kN;
   static constexpr size_t kInfo = kBar + 32;
   static constexpr size_t kTotal = kInfo + 2 * 96;
   static_assert(kRaw % 128 == 0 && 2 * (kTotal + 1024) <= 228 * 1024, "raw landing zone / 2 CTAs per SM");
   static_assert(kSlot >= kN + 1, "slot holds the spectrum and the copy of bin 0");
+  static_assert(kSkew % 32 == 16 && (kSkew * 4) % 16 == 0, "skewed copy: 16 banks away, 16 B aligned");
 };
 
 struct StftNParams {
@@ -62,6 +65,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
+  // the upper half-warp's pair starts 2 * hop floats after the lower one: it reads a second, skewed copy of the tile
+  // when that offset would put both on (nearly) the same banks
+  const int pair_banks = (2 * hop) & 31;
+  const bool use_skew = pair_banks < 8 || pair_banks > 24;
   for (int i = tid; i < kN; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.twn[i]; }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -97,8 +104,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
-      mbar_expect_tx(&bars[slot], bytes);
+      mbar_expect_tx(&bars[slot], use_skew ? 2 * bytes : bytes);
       tma_bulk_g2s(rawz + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
+      if (use_skew) tma_bulk_g2s(rawz + G::kSkew + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
     } else {
       mbar_arrive(&bars[slot]);
     }
@@ -134,7 +142,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
     float* xr = rawz + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
     if (cur.cov_end < cur.end_elem) {   // bytes the 16 B-granular bulk copy could not cover (end of the flat array)
-      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) rawz[cur.lpad + (e - cur.base_elem)] = P.wave[e];
+      for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
+        const float x = P.wave[e];
+        rawz[cur.lpad + (e - cur.base_elem)] = x;
+        if (use_skew) rawz[G::kSkew + cur.lpad + (e - cur.base_elem)] = x;
+      }
       __syncthreads();
     }
     if (cur.lpad > 0 || cur.lpad + cur.n_loaded < cur.tile_len) {
@@ -151,6 +163,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
           x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
         }
         xr[i] = x;
+        if (use_skew) xr[G::kSkew + i] = x;
       }
       __syncthreads();
     }
@@ -158,7 +171,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     // ---- load: frame pair -> N1 windowed complex points per lane ----
     cpx v[N1];
     {
-      const float* xa = xr + (2 * pair) * hop + t;
+      const float* xa = xr + ((lane >> 4) && use_skew ? G::kSkew : 0) + (2 * pair) * hop + t;
       const float* xb = xa + hop;
       const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 #pragma unroll
