@@ -282,6 +282,18 @@ int mafe_mask_rects(mafe_ctx* ctx, float* feats_dev, const int64_t* frame_offset
 int mafe_phase_vocoder(mafe_ctx* ctx, const float* spec_dev, int32_t n_mats, int32_t n_frames, int32_t n_bins, double rate,
                        const double* phi_advance_dev, int32_t n_steps, float* out_dev);
 
+/* ---- harmonic / percussive separation ("next" row f2: mindaudio/data/features.py:438-559 soft_mask / hpss / harmonic) ---- */
+/* scipy.ndimage.median_filter(x, size, mode="reflect") along one axis of n_mats row-major [rows][cols] matrices:
+ * window [i - size/2, i - size/2 + size), rank size/2, boundary d c b a | a b c d | d c b a.  axis 0 = along rows
+ * (frequency: the percussive filter), 1 = along columns (time: the harmonic filter).  out must not alias x. */
+int mafe_median_filter(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32_t n_mats, int32_t rows, int32_t cols,
+                       int32_t size, int32_t axis);
+/* soft masks of hpss (features.py:438-469, 513-528) from the two median-filtered magnitudes, elementwise over n values:
+ * mask_h = soft_mask(harm, perc * margin_h), mask_p = soft_mask(perc, harm * margin_p), power > 0 (INFINITY = hard
+ * mask), split_zeros as in the reference. */
+int mafe_hpss_masks(mafe_ctx* ctx, const float* harm_dev, const float* perc_dev, int64_t n, float margin_h, float margin_p,
+                    float power, int32_t split_zeros, float* mask_h_dev, float* mask_p_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,8 @@ _PROTOS = {
     "mafe_sliding_window_cmn": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
     "mafe_mask_rects": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I32, C.c_float]),
     "mafe_phase_vocoder": (C.c_int, [_P, _P, _I32, _I32, _I32, C.c_double, _P, _I32, _P]),
+    "mafe_median_filter": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32]),
+    "mafe_hpss_masks": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _I32, _P, _P]),
 }
 
 _lib = None

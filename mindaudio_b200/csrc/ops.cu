@@ -401,6 +401,65 @@ __global__ void phase_vocoder_kernel(const float2* __restrict__ spec, int n_mats
   }
 }
 
+// 1-D median filter along one axis (scipy.ndimage.median_filter, mode="reflect"): one thread per output element keeps
+// the size/2 + 1 smallest window values in a sorted register/local array (partial insertion sort) -- rank size/2.
+constexpr int kMedianMaxRank = 64;   // size <= 127
+__global__ void median_filter_kernel(const float* __restrict__ x, float* __restrict__ out, int n_mats, int rows, int cols, int size,
+                                     int axis) {
+  const int64_t total = (int64_t)n_mats * rows * cols;
+  const int len = axis == 0 ? rows : cols;
+  const int64_t stride = axis == 0 ? cols : 1;
+  const int rank = size / 2, keep = rank + 1;
+  for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(id % cols);
+    const int r = (int)((id / cols) % rows);
+    const int i = axis == 0 ? r : c;
+    const float* line = x + (id - (int64_t)i * stride);
+    float best[kMedianMaxRank];   // ascending, `filled` entries
+    int filled = 0;
+    for (int w = 0; w < size; ++w) {
+      int j = i - rank + w;
+      // reflect about the edges: d c b a | a b c d | d c b a (period 2 * len)
+      if (j < 0 || j >= len) {
+        const int p2 = 2 * len;
+        j %= p2;
+        if (j < 0) j += p2;
+        if (j >= len) j = p2 - 1 - j;
+      }
+      const float v = line[(int64_t)j * stride];
+      if (filled < keep) {
+        int k = filled++;
+        while (k > 0 && best[k - 1] > v) { best[k] = best[k - 1]; --k; }
+        best[k] = v;
+      } else if (v < best[keep - 1]) {
+        int k = keep - 1;
+        while (k > 0 && best[k - 1] > v) { best[k] = best[k - 1]; --k; }
+        best[k] = v;
+      }
+    }
+    out[id] = best[keep - 1];
+  }
+}
+
+__device__ __forceinline__ float soft_mask_one(float x, float ref, float power, int split_zeros) {
+  const float z0 = fmaxf(x, ref);
+  const bool bad = z0 < 1.17549435e-38f;   // np.finfo(float32).tiny
+  if (isinf(power)) return x > ref ? 1.f : 0.f;
+  if (bad) return split_zeros ? 0.5f : 0.f;
+  const float a = x / z0, b = ref / z0;
+  const float m = power == 2.f ? a * a : (power == 1.f ? a : powf(a, power));
+  const float rm = power == 2.f ? b * b : (power == 1.f ? b : powf(b, power));
+  return m / (m + rm);
+}
+__global__ void hpss_masks_kernel(const float* __restrict__ harm, const float* __restrict__ perc, int64_t n, float margin_h,
+                                  float margin_p, float power, int split_zeros, float* __restrict__ mh, float* __restrict__ mp) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float h = harm[i], p = perc[i];
+    mh[i] = soft_mask_one(h, p * margin_h, power, split_zeros);
+    mp[i] = soft_mask_one(p, h * margin_p, power, split_zeros);
+  }
+}
+
 extern "C" {
 
 int mafe_magphase(mafe_ctx* ctx, const float* z, int64_t n, float power, float* mag, float* phase) {
@@ -657,6 +716,33 @@ int mafe_phase_vocoder(mafe_ctx* ctx, const float* spec, int32_t n_mats, int32_t
   const int64_t n = (int64_t)n_mats * n_bins;
   phase_vocoder_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const float2*)spec, n_mats, n_frames, n_bins, rate,
                                                                            phi_advance, n_steps, (float2*)out);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_median_filter(mafe_ctx* ctx, const float* x, float* out, int32_t n_mats, int32_t rows, int32_t cols, int32_t size,
+                       int32_t axis) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(size >= 1 && size / 2 < kMedianMaxRank, "median_filter: size %d out of range (1..%d)", size, 2 * kMedianMaxRank - 1);
+  MAFE_REQUIRE(axis == 0 || axis == 1, "median_filter: axis must be 0 or 1");
+  if (n_mats <= 0 || rows <= 0 || cols <= 0) return MAFE_OK;
+  MAFE_REQUIRE(x && out && x != out, "mafe_median_filter: NULL or aliased buffer");
+  cudaSetDevice(ctx->device);
+  const int64_t total = (int64_t)n_mats * rows * cols;
+  median_filter_kernel<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(x, out, n_mats, rows, cols, size, axis);
+  MAFE_LAUNCH_CHECK(ctx);
+  return MAFE_OK;
+}
+
+int mafe_hpss_masks(mafe_ctx* ctx, const float* harm, const float* perc, int64_t n, float margin_h, float margin_p, float power,
+                    int32_t split_zeros, float* mask_h, float* mask_p) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  MAFE_REQUIRE(power > 0.f, "power must be strictly positive.");
+  if (n <= 0) return MAFE_OK;
+  MAFE_REQUIRE(harm && perc && mask_h && mask_p, "mafe_hpss_masks: NULL buffer");
+  cudaSetDevice(ctx->device);
+  hpss_masks_kernel<<<grid_for(ctx, n, 256 * 2), 256, 0, ctx->stream>>>(harm, perc, n, margin_h, margin_p, power, split_zeros, mask_h,
+                                                                       mask_p);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }

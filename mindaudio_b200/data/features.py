@@ -22,6 +22,9 @@ __all__ = [
     "fbanks",
     "mfcc",
     "spectral_centroid",
+    "soft_mask",
+    "hpss",
+    "harmonic",
 ]
 
 
@@ -244,4 +247,93 @@ def spectral_centroid(waveforms, sample_rate, n_fft=400, win_length=None, hop_le
     with np.errstate(divide="ignore", invalid="ignore"):
         cen = num_den[..., 0, :] / num_den[..., 1, :]
     return cen.astype(_out_dtype(waveforms), copy=False)
+
+
+def _masks_device(harm, perc, margin_h, margin_p, power, split_zeros):
+    harm = np.ascontiguousarray(harm, dtype=np.float32)
+    perc = np.ascontiguousarray(perc, dtype=np.float32)
+    mh, mp = np.empty_like(harm), np.empty_like(perc)
+    if harm.size:
+        eng = get_engine()
+        with eng.lock:
+            d_h, d_p = eng.buf("wave", harm.nbytes), eng.buf("out", perc.nbytes)
+            d_mh, d_mp = eng.buf("pad", harm.nbytes), eng.buf("aux", perc.nbytes)
+            keep = (eng.h2d(d_h, harm), eng.h2d(d_p, perc))
+            L.check(eng.lib.mafe_hpss_masks(eng.ctx, d_h, d_p, harm.size, float(margin_h), float(margin_p), float(power),
+                                            int(bool(split_zeros)), d_mh, d_mp))
+            eng.d2h(mh, d_mh)
+            eng.d2h(mp, d_mp)
+            eng.sync()
+            del keep
+    return mh, mp
+
+
+def soft_mask(x_input, x_ref, *, power=1, split_zeros=False):
+    """``features.py:438-469``: ``x^p / (x^p + ref^p)`` computed on the scale ``max(x, ref)``; ``power=inf`` = hard mask."""
+    x_input, x_ref = np.asarray(x_input), np.asarray(x_ref)
+    if np.any(x_input < 0) or np.any(x_ref < 0):
+        raise TypeError("x_input and x_ref must be non-negative")
+    if x_input.shape != x_ref.shape:
+        raise TypeError("x_input and x_ref shape mismatch.")
+    if power <= 0:
+        raise TypeError("power must be strictly positive.")
+    mh, _ = _masks_device(x_input, x_ref, 1.0, 1.0, power, split_zeros)
+    if not np.isfinite(power):
+        return mh.astype(bool)
+    return mh.astype(x_input.dtype if np.issubdtype(x_input.dtype, np.floating) else np.float32, copy=False)
+
+
+def hpss(spectrogram, *, kernel_size=31, power=2.0, mask=False, margin=1.0):
+    """``features.py:472-529``: median-filtering harmonic / percussive separation of a (complex or magnitude)
+    spectrogram ``[..., F, T]``.  Magnitude, the two median filters (31 along time / frequency, scipy ``reflect``
+    boundary) and the soft masks run on the GPU in one round trip."""
+    spectrogram = np.asarray(spectrogram)
+    if not np.iscomplexobj(spectrogram):
+        phase = 1
+        mag = spectrogram
+    else:
+        mag, phase = _sp.magphase(spectrogram, power=1)
+    margin_harmonic, margin_perc = (margin[0], margin[1]) if not np.isscalar(margin) else (margin, margin)
+    win_harmonic, win_perc = (kernel_size[0], kernel_size[1]) if not np.isscalar(kernel_size) else (kernel_size, kernel_size)
+    if margin_harmonic < 1 or margin_perc < 1:
+        raise TypeError("Margins must be >= 1.0. " "A typical range is between 1 and 10.")
+    if power <= 0:
+        raise TypeError("power must be strictly positive.")
+    if mag.ndim < 2:
+        raise ValueError("spectrogram must have at least 2 dimensions [..., F, T]")
+    x = np.ascontiguousarray(mag, dtype=np.float32)
+    F, T = x.shape[-2], x.shape[-1]
+    n = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    split_zeros = margin_harmonic == 1 and margin_perc == 1
+    mask_h, mask_p = np.empty_like(x), np.empty_like(x)
+    if x.size:
+        eng = get_engine()
+        with eng.lock:
+            d_x = eng.buf("wave", x.nbytes)
+            d_h, d_p = eng.buf("out", x.nbytes), eng.buf("scratch", x.nbytes)
+            d_mh, d_mp = eng.buf("pad", x.nbytes), eng.buf("aux", x.nbytes)
+            keep = eng.h2d(d_x, x)
+            L.check(eng.lib.mafe_median_filter(eng.ctx, d_x, d_h, n, F, T, int(win_harmonic), 1))   # along time
+            L.check(eng.lib.mafe_median_filter(eng.ctx, d_x, d_p, n, F, T, int(win_perc), 0))       # along frequency
+            L.check(eng.lib.mafe_hpss_masks(eng.ctx, d_h, d_p, x.size, float(margin_harmonic), float(margin_perc), float(power),
+                                            int(split_zeros), d_mh, d_mp))
+            eng.d2h(mask_h, d_mh)
+            eng.d2h(mask_p, d_mp)
+            eng.sync()
+            del keep
+    if not np.isfinite(power):
+        mask_h, mask_p = mask_h.astype(bool), mask_p.astype(bool)
+    elif mag.dtype == np.float64:
+        mask_h, mask_p = mask_h.astype(np.float64), mask_p.astype(np.float64)
+    if mask:
+        return mask_h, mask_p
+    return ((mag * mask_h) * phase, (mag * mask_p) * phase)
+
+
+def harmonic(y_input, **kwargs):
+    """``features.py:532-559``: ``istft(hpss(stft(y, n_fft=2048, pad_mode="constant"))[0], length=len(y))``."""
+    y_input = np.asarray(y_input)
+    y_stft = _sp.stft(y_input, n_fft=2048, pad_mode="constant")
+    stft_harm = hpss(y_stft, **kwargs)[0]
+    return _sp.istft(stft_harm, length=y_input.shape[-1])
 

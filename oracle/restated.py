@@ -731,3 +731,56 @@ def time_stretch(waveforms, rate):
     spec = stft(waveforms)
     return istft(phase_vocoder(spec, rate), length=int(round(waveforms.shape[-1] / rate)))
 
+
+# ---------------------------------------------------------------------------------------------
+# harmonic / percussive separation (scope row f2): mindaudio/data/features.py:438-559
+# ---------------------------------------------------------------------------------------------
+def median_filter_1d(x, size, axis):
+    """scipy.ndimage.median_filter(x, size=[.., size at axis ..], mode="reflect") restated with numpy: window
+    [i - size//2, i - size//2 + size), rank size//2, symmetric (half-sample) boundary."""
+    x = np.asarray(x)
+    lo = size // 2
+    pad = [(0, 0)] * x.ndim
+    pad[axis] = (lo, size - 1 - lo)
+    xp = np.pad(x, pad, mode="symmetric")
+    win = np.lib.stride_tricks.sliding_window_view(xp, size, axis=axis)
+    return np.sort(win, axis=-1)[..., size // 2]
+
+
+def soft_mask(x_input, x_ref, power=1, split_zeros=False):
+    input_type = x_input.dtype if np.issubdtype(x_input.dtype, np.floating) else np.float32
+    z = np.maximum(x_input, x_ref).astype(input_type)
+    bad_idx = z < np.finfo(input_type).tiny
+    z[bad_idx] = 1
+    if not np.isfinite(power):
+        return x_input > x_ref
+    mask = (x_input / z) ** power
+    ref_mask = (x_ref / z) ** power
+    good_idx = ~bad_idx
+    mask[good_idx] /= mask[good_idx] + ref_mask[good_idx]
+    mask[bad_idx] = 0.5 if split_zeros else 0.0
+    return mask
+
+
+def hpss(spectrogram, kernel_size=31, power=2.0, mask=False, margin=1.0):
+    spectrogram = np.asarray(spectrogram)
+    if np.iscomplexobj(spectrogram):
+        spectrogram, phase = magphase(spectrogram, power=1)
+    else:
+        phase = 1
+    margin_h, margin_p = (margin[0], margin[1]) if not np.isscalar(margin) else (margin, margin)
+    win_h, win_p = (kernel_size[0], kernel_size[1]) if not np.isscalar(kernel_size) else (kernel_size, kernel_size)
+    harm = median_filter_1d(spectrogram, win_h, -1)
+    perc = median_filter_1d(spectrogram, win_p, -2)
+    split_zeros = margin_h == 1 and margin_p == 1
+    mask_h = soft_mask(harm, perc * margin_h, power=power, split_zeros=split_zeros)
+    mask_p = soft_mask(perc, harm * margin_p, power=power, split_zeros=split_zeros)
+    if mask:
+        return mask_h, mask_p
+    return (spectrogram * mask_h) * phase, (spectrogram * mask_p) * phase
+
+
+def harmonic(y_input, **kwargs):
+    y_input = np.asarray(y_input)
+    return istft(hpss(stft(y_input, n_fft=2048, pad_mode="constant"), **kwargs)[0], length=y_input.shape[-1])
+

@@ -332,3 +332,24 @@ def test_bench_size_batch_properties(ma):
         assert float(x.mean(dim=0).abs().max()) < 1e-3 and float((x.std(dim=0, unbiased=False) - 1).abs().max()) < 1e-3, u
     assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(outn).all())
 
+
+def test_hpss_harmonic(ma):
+    """Scope row f2: soft_mask / hpss / harmonic (features.py:438-559).  The median filters are exact selections; the
+    soft masks are a handful of FP32 operations (1e-6)."""
+    x = synth(17, (2, 9000))
+    spec = R.stft(x, n_fft=512)
+    for kw in (dict(), dict(kernel_size=(13, 7), margin=(1.0, 3.0)), dict(power=1.0, kernel_size=8), dict(mask=True, margin=2.0)):
+        out, ref = ma.hpss(spec, **kw), R.hpss(spec, **kw)
+        for u, v in zip(out, ref):
+            assert u.shape == v.shape and u.dtype == v.dtype
+            assert np.max(np.abs(u - v)) <= 2e-6 * max(1.0, np.max(np.abs(v)))
+    mag = np.abs(spec[1]).astype(np.float32)
+    out, ref = ma.hpss(mag, power=np.inf, mask=True), R.hpss(mag, power=np.inf, mask=True)
+    assert all(u.dtype == v.dtype and np.array_equal(u, v) for u, v in zip(out, ref))
+    m, mr = ma.soft_mask(mag, mag[::-1].copy(), power=2, split_zeros=True), R.soft_mask(mag, mag[::-1].copy(), power=2, split_zeros=True)
+    assert m.dtype == mr.dtype and np.max(np.abs(m - mr)) <= 2e-6
+    y, yr = ma.harmonic(x[0].astype(np.float64), margin=3.0), R.harmonic(x[0].astype(np.float64), margin=3.0)
+    assert y.shape == yr.shape and y.dtype == yr.dtype and np.max(np.abs(y - yr)) <= 1e-5 * np.max(np.abs(yr))
+    with pytest.raises(TypeError):
+        ma.hpss(spec, margin=0.5)
+

@@ -97,3 +97,21 @@ def test_phase_vocoder_matches_reference(ref):
         yb = R.time_stretch(x, rate)
         assert ya.shape == yb.shape and np.max(np.abs(ya - yb)) <= 1e-6 * max(1.0, np.max(np.abs(ya)))
 
+
+def test_hpss_matches_reference(ref):
+    """Restated soft_mask / hpss / harmonic == the reference's own functions (scipy's median_filter included)."""
+    from tests.util import synth
+    ft = ref["ft"]
+    x = synth(17, (2, 9000)).astype(np.float64)
+    spec = ref["sp"].stft(x, n_fft=512)
+    for kw in (dict(), dict(kernel_size=(13, 7), margin=(1.0, 3.0)), dict(power=1.0, kernel_size=8), dict(mask=True, margin=2.0)):
+        a, b = ft.hpss(spec[0], **kw), R.hpss(spec[0], **kw)
+        for u, v in zip(a, b):
+            assert u.shape == v.shape and u.dtype == v.dtype and np.array_equal(u, v)
+    mag = np.abs(spec[1]).astype(np.float32)
+    a, b = ft.hpss(mag, power=np.inf, mask=True), R.hpss(mag, power=np.inf, mask=True)
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    ya, yb = ft.harmonic(x[0]), R.harmonic(x[0])
+    # the reference's istft runs numpy >= 2's single-precision irfft on complex64 here; the oracle transforms in float64
+    assert ya.shape == yb.shape and np.max(np.abs(ya - yb)) <= 1e-6 * max(1.0, np.max(np.abs(ya)))
+
