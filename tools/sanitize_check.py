@@ -25,4 +25,10 @@ xs_pad, xs_len, xs_mask = pipe.features_padded([w for w in waves if len(w) >= 40
 ma.sliding_window_cmn(np.asarray(xs_pad[:2]), 20, 5, norm_vars=True)
 ma.spectral_centroid(x, 16000)
 ma.mfcc(x, n_fft=1024, n_mels=40, n_mfcc=13, deltas=False, context=False)
+spec = R.stft(x[:, :4000], n_fft=512)
+ma.hpss(spec, kernel_size=(13, 7), margin=(1.0, 3.0))
+ma.hpss(np.abs(spec[0]).astype(np.float32), power=np.inf, mask=True)
+ma.harmonic(x[0, :6000])
+ma.time_stretch(x[:, :6000], 1.3)
+ma.augment._phase_vocoder(spec, 0.8)
 print("sanitize script ok")
