@@ -37,9 +37,14 @@ __device__ __forceinline__ C2* stockham_fft(C2* cur, C2* nxt, int pairs, int N, 
     const int M = N / R;               // butterflies per FFT
     const int tstep = N / (Ns * R);    // twiddle index step: W_{Ns*R}^{k} = W_N^{k*tstep}
     if (R <= 5) {
+      // power-of-two sizes (N, hence M and Ns for radices 4 / 2): shifts and masks instead of integer division --
+      // the division-heavy index arithmetic was 60 % of this loop's instructions (ncu, n_fft = 2048)
+      const bool pow2 = (N & (N - 1)) == 0 && (R == 2 || R == 4);
+      const int lgM = 31 - __clz(M);
       for (int idx = threadIdx.x; idx < pairs * M; idx += blockDim.x) {
-        int p = idx / M, j = idx - p * M;
-        int k = j % Ns;
+        int p, j, k;
+        if (pow2) { p = idx >> lgM; j = idx & (M - 1); k = j & (Ns - 1); }
+        else { p = idx / M; j = idx - p * M; k = j % Ns; }
         const C2* in = cur + (size_t)p * N;
         C2* outp = nxt + (size_t)p * N;
         int j0 = (j - k) * R + k;
@@ -48,7 +53,7 @@ __device__ __forceinline__ C2* stockham_fft(C2* cur, C2* nxt, int pairs, int N, 
         for (int r = 0; r < 5; ++r) {
           if (r < R) {
             C2 x = in[j + r * M];
-            if (r > 0 && k > 0) x = cmul(x, tw[(k * r * tstep) % N]);
+            if (r > 0 && k > 0) x = cmul(x, tw[pow2 ? ((k * r * tstep) & (N - 1)) : ((k * r * tstep) % N)]);
             v[r] = x;
           }
         }

@@ -74,7 +74,7 @@ __device__ __forceinline__ float frame_entry(const GenericParams& P, int64_t off
   if (f >= T || n >= P.frame_len) return 0.0f;
   int64_t s = f * P.hop + n;
   if (P.center) {
-    s = pad_index(s - P.n_fft / 2, L, P.pad_mode);
+    s = pad_index_fast(s - P.n_fft / 2, L, P.pad_mode);
     if (s < 0) return 0.0f;
   }
   return signal_sample(P, off, s, utt) * P.window[n];
@@ -128,16 +128,18 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   if (P.remove_mean) mu = (float)(P.utt_sum[utt] / ((double)T * (double)P.frame_len));
 
   // ---- load: frame pair p -> complex sequence a + i b, windowed, scalar mean removed ----
-  for (int idx = threadIdx.x; idx < pairs * N; idx += blockDim.x) {
-    int p = idx / N, n = idx - p * N;
-    int64_t fa = tile.frame0 + 2 * p;
-    float a = frame_entry(P, off, L, T, fa, n, utt);
-    float b = frame_entry(P, off, L, T, fa + 1, n, utt);
-    if (n < P.frame_len) {
-      if (fa < T) a -= mu;
-      if (fa + 1 < T) b -= mu;
+  for (int p = 0; p < pairs; ++p) {
+    const int64_t fa = tile.frame0 + 2 * p;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      if (n < P.frame_len) {   // zero padding of the window up to n_fft otherwise
+        a = frame_entry(P, off, L, T, fa, n, utt);
+        b = frame_entry(P, off, L, T, fa + 1, n, utt);
+        if (fa < T) a -= mu;
+        if (fa + 1 < T) b -= mu;
+      }
+      cur[(size_t)p * N + n] = make_float2(a, b);
     }
-    cur[idx] = make_float2(a, b);
   }
   __syncthreads();
 
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   const int nb = P.n_bins;
   float* pw = reinterpret_cast<float*>(nxt);  // [2*pairs][nb] power spectra (aliases the idle buffer)
   const float sc = P.spec_scale;
-  for (int idx = threadIdx.x; idx < pairs * nb; idx += blockDim.x) {
-    int p = idx / nb, k = idx - p * nb;
+  for (int p = 0; p < pairs; ++p)
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
     float2 za = cur[(size_t)p * N + k];
     float2 zr = cur[(size_t)p * N + (k == 0 ? 0 : N - k)];
     float2 xa = make_float2(0.5f * (za.x + zr.x) * sc, 0.5f * (za.y - zr.y) * sc);

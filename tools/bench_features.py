@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--mfcc", action="store_true")
+    ap.add_argument("--fastspeech2", action="store_true",
+                    help="melspectrogram n_fft=2048 win=1200 hop=300 128 mel at 22 050 Hz (examples/fastspeech2): generic kernel")
     args = ap.parse_args()
     eng = get_engine()
     eng.set_stream(torch.cuda.current_stream().cuda_stream or 1)
@@ -32,7 +34,14 @@ def main():
     bank = T.hz_triangle_bank(201, 80, 16000, 0.0, 8000.0)
     kw = dict(n_fft=400, hop=160, center=True, pad_mode="reflect", window=T.analysis_window("hann", 400, 400), power=2.0,
               mel_fb=bank, log_kind=L.LOG_DB, log_arg=1e-10, log_mult=10.0, log_offset=0.0, top_db=80.0)
-    if args.mfcc:
+    sr = 16000
+    if args.fastspeech2:
+        sr = 22050
+        n = int(args.seconds * sr)
+        bank = T.hz_triangle_bank(1025, 128, sr, 0.0, sr // 2)
+        plan = eng.plan(n_fft=2048, hop=300, center=True, pad_mode="reflect", window=T.analysis_window("hann", 1200, 2048),
+                        power=2.0, mel_fb=bank, out_kind=L.OUT_MEL)
+    elif args.mfcc:
         plan = eng.plan(out_kind=L.OUT_MFCC, dct=T.dct_matrix(40, 80, "ortho"), **kw)
     else:
         plan = eng.plan(out_kind=L.OUT_LOGMEL, **kw)
@@ -63,9 +72,10 @@ def main():
     k_ms, k_n = eng.profile_read(L.PROF_FBANK_MAIN)
     eng.profile(False)
     hours = args.batch * args.seconds / 3600.0
-    bpf = 160 * 4 + plan.out_dim * 4
-    print(json.dumps({"workload": "features.%s n_fft=400 hop=160 80 mel dB top_db=80 (batch floor), [%d, %d] f32" %
-                      ("mfcc(40)" if args.mfcc else "fbank", args.batch, n), "frames": frames, "fast_path": plan.is_fast,
+    bpf = (300 if args.fastspeech2 else 160) * 4 + plan.out_dim * 4
+    what = ("melspectrogram n_fft=2048 win=1200 hop=300 128 mel @22.05 kHz (fastspeech2), [%d, %d] f32" % (args.batch, n)) if args.fastspeech2 \
+        else "features.%s n_fft=400 hop=160 80 mel dB top_db=80 (batch floor), [%d, %d] f32" % ("mfcc(40)" if args.mfcc else "fbank", args.batch, n)
+    print(json.dumps({"workload": what, "frames": frames, "fast_path": plan.is_fast,
                       "ms": ms, "main_kernel_ms": k_ms / max(k_n, 1), "audio_hours_per_s": hours / (ms / 1e3), "GBps_algorithmic": bpf * frames / ms / 1e6}))
     batch.close()
 
