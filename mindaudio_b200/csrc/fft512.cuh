@@ -67,6 +67,20 @@ MAFE_HD void fft16(cpx* v) {
   for (int k2 = 0; k2 < 4; ++k2) dft4(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
 }
 
+// forward 8-point DFT of v[0..7] (natural order in, natural order out): radix-2 DIF split + two DFT4
+MAFE_HD void dft8(cpx* v) {
+  const float h = 0.70710678118654752440f;
+  cpx a0 = v[0] + v[4], a1 = v[1] + v[5], a2 = v[2] + v[6], a3 = v[3] + v[7];
+  cpx b0 = v[0] - v[4], b1 = v[1] - v[5], b2 = v[2] - v[6], b3 = v[3] - v[7];
+  b1 = cx(h * (b1.x + b1.y), h * (b1.y - b1.x));     // * W8^1 = (h, -h)
+  b2 = mul_neg_i(b2);                                // * W8^2 = -i
+  b3 = cx(h * (b3.y - b3.x), -h * (b3.x + b3.y));    // * W8^3 = (-h, -h)
+  dft4(a0, a1, a2, a3);                              // X[0], X[2], X[4], X[6]
+  dft4(b0, b1, b2, b3);                              // X[1], X[3], X[5], X[7]
+  v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+  v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+
 // shared-memory transpose slot of one 256-point transform: row stride 17 complex (conflict-free
 // for 8-byte accesses by 16 lanes), 16 rows -> 272 complex; slots are spaced kSlotStride apart so
 // that the same bin of 16 different slots falls into 16 different bank pairs.

@@ -2,6 +2,7 @@
 // fallback), forward transform, `pairs` independent length-N complex sequences per CTA.
 #pragma once
 #include "common.cuh"
+#include "fft512.cuh"
 
 namespace mafe {
 
@@ -25,18 +26,65 @@ struct FftStages {
   int n_stages;
 };
 
-// Forward DFT of `pairs` sequences held in cur[p*N + n]; returns the buffer holding the result
+// padded position inside a sequence: one spare element per 16 (radix-16 / 8 passes write 16 consecutive outputs
+// per thread; without the skew every lane of a warp would hit the same bank pair)
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+// Forward DFT of `pairs` sequences held in cur[p*stride + n]; returns the buffer holding the result
 // (cur or nxt).  All threads of the CTA must call it; starts and ends with data visible to all.
+// Radices 16 / 8 (float, power-of-two N only; chosen by the host for N >= 256) run as register-resident fft16 /
+// dft8 butterflies: 3 passes for N = 2048 instead of 6 radix-4/2 passes.  Their intermediate buffers are skewed by
+// pad16(); the first input and the final output are in natural order, so callers are not affected (`stride` must
+// leave room for N + N/16 elements per sequence).
 template <typename C2>
 __device__ __forceinline__ C2* stockham_fft(C2* cur, C2* nxt, int pairs, int N, const FftStages& S,
-                                            const C2* __restrict__ tw) {
+                                            const C2* __restrict__ tw, int stride = 0) {
   typedef typename Real<C2>::type Rt;
+  if (stride == 0) stride = N;
+  const bool skewed = S.radices[0] >= 8;   // the host uses 16 / 8 for every pass or for none... except a final 4 / 2
   int Ns = 1;
   for (int s = 0; s < S.n_stages; ++s) {
     const int R = S.radices[s];
     const int M = N / R;               // butterflies per FFT
     const int tstep = N / (Ns * R);    // twiddle index step: W_{Ns*R}^{k} = W_N^{k*tstep}
-    if (R <= 5) {
+    const bool in_skew = skewed && s > 0, out_skew = skewed && s + 1 < S.n_stages;
+    if (sizeof(Rt) == 4 && (R == 16 || R == 8)) {
+      const int lgM = 31 - __clz(M);
+      for (int idx = threadIdx.x; idx < pairs * M; idx += blockDim.x) {
+        const int p = idx >> lgM, j = idx & (M - 1), k = j & (Ns - 1);
+        const float2* in = reinterpret_cast<const float2*>(cur) + (size_t)p * stride;
+        float2* outp = reinterpret_cast<float2*>(nxt) + (size_t)p * stride;
+        const int j0 = (j - k) * R + k;
+        cpx v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          if (r < R) {
+            const int i = j + r * M;
+            const float2 x = in[in_skew ? pad16(i) : i];
+            v[r] = cx(x.x, x.y);
+            if (r > 0 && k > 0) {
+              const float2 w = reinterpret_cast<const float2*>(tw)[(k * r * tstep) & (N - 1)];
+              v[r] = cmulf(v[r], cx(w.x, w.y));
+            }
+          }
+        }
+        if (R == 16) {
+          fft16(v);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const int o = j0 + t * Ns;
+            outp[out_skew ? pad16(o) : o] = make_float2(v[fft16_pos(t)].x, v[fft16_pos(t)].y);
+          }
+        } else {
+          dft8(v);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int o = j0 + t * Ns;
+            outp[out_skew ? pad16(o) : o] = make_float2(v[t].x, v[t].y);
+          }
+        }
+      }
+    } else if (R <= 5) {
       // power-of-two sizes (N, hence M and Ns for radices 4 / 2): shifts and masks instead of integer division --
       // the division-heavy index arithmetic was 60 % of this loop's instructions (ncu, n_fft = 2048)
       const bool pow2 = (N & (N - 1)) == 0 && (R == 2 || R == 4);
@@ -45,14 +93,14 @@ __device__ __forceinline__ C2* stockham_fft(C2* cur, C2* nxt, int pairs, int N, 
         int p, j, k;
         if (pow2) { p = idx >> lgM; j = idx & (M - 1); k = j & (Ns - 1); }
         else { p = idx / M; j = idx - p * M; k = j % Ns; }
-        const C2* in = cur + (size_t)p * N;
-        C2* outp = nxt + (size_t)p * N;
+        const C2* in = cur + (size_t)p * stride;
+        C2* outp = nxt + (size_t)p * stride;
         int j0 = (j - k) * R + k;
         C2 v[5];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
           if (r < R) {
-            C2 x = in[j + r * M];
+            C2 x = in[in_skew ? pad16(j + r * M) : j + r * M];
             if (r > 0 && k > 0) x = cmul(x, tw[pow2 ? ((k * r * tstep) & (N - 1)) : ((k * r * tstep) % N)]);
             v[r] = x;
           }

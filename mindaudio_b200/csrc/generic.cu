@@ -36,6 +36,7 @@ struct GenericParams {
   const float2* tw;
   FftStages fft;
   int pairs;
+  int pair_stride;
   int out_kind;
   float power, spec_scale;
   int n_mels;
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   const int N = P.n_fft;
   const int pairs = P.pairs;
   float2* cur = smem;
-  float2* nxt = smem + (size_t)pairs * N;
+  const int ps = P.pair_stride;   // elements between the sequences of consecutive pairs (N, or N + N/16 with radix-16 passes)
+  float2* nxt = smem + (size_t)pairs * ps;
 
   Tile tile = P.tiles[blockIdx.x];
   tile.frame0 += blockIdx.y * 2 * pairs;   // batch tiles may be larger than this kernel's 2*pairs frames (gridDim.y sub-tiles)
@@ -138,14 +140,14 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
         if (fa < T) a -= mu;
         if (fa + 1 < T) b -= mu;
       }
-      cur[(size_t)p * N + n] = make_float2(a, b);
+      cur[(size_t)p * ps + n] = make_float2(a, b);
     }
   }
   __syncthreads();
 
   // ---- Stockham autosort stages ----
   {
-    float2* res = stockham_fft<float2>(cur, nxt, pairs, N, P.fft, P.tw);
+    float2* res = stockham_fft<float2>(cur, nxt, pairs, N, P.fft, P.tw, ps);
     if (res != cur) { nxt = cur; cur = res; }
   }
 
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   const float sc = P.spec_scale;
   for (int p = 0; p < pairs; ++p)
   for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-    float2 za = cur[(size_t)p * N + k];
-    float2 zr = cur[(size_t)p * N + (k == 0 ? 0 : N - k)];
+    float2 za = cur[(size_t)p * ps + k];
+    float2 zr = cur[(size_t)p * ps + (k == 0 ? 0 : N - k)];
     float2 xa = make_float2(0.5f * (za.x + zr.x) * sc, 0.5f * (za.y - zr.y) * sc);
     float2 xb = make_float2(0.5f * (za.y + zr.y) * sc, -0.5f * (za.x - zr.x) * sc);
     int64_t fa = tile.frame0 + 2 * p;
@@ -326,6 +328,13 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 // ---------------------------------------------------------------------------------------------
 static void factorize(int n, std::vector<int>& out) {
   out.clear();
+  if (n >= 256 && (n & (n - 1)) == 0) {
+    // power of two: register-resident radix-16 passes, one smaller pass last (8 / 4 / 2) -- 2048 = 16 * 16 * 8
+    while (n % 16 == 0 && n > 16) { out.push_back(16); n /= 16; }
+    if (n == 16) { out.push_back(16); n = 1; }
+    if (n > 1) out.push_back(n);   // 8, 4 or 2
+    return;
+  }
   while (n % 4 == 0) { out.push_back(4); n /= 4; }
   while (n % 2 == 0) { out.push_back(2); n /= 2; }
   while (n % 3 == 0) { out.push_back(3); n /= 3; }
@@ -348,8 +357,10 @@ int generic_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) 
   MAFE_REQUIRE((int)p->radices.size() <= kMaxStages, "n_fft=%d has too many factors", N);
   p->n_stages = (int)p->radices.size();
   // tile size: as many frame pairs as fit ~64 KB of ping-pong buffers, 1..8
-  size_t per_pair = (size_t)N * sizeof(float2) * 2;
-  int pairs = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / per_pair));
+  // radix-16 / 8 passes skew their intermediate buffers by one element per 16 (fft_generic.cuh: pad16)
+  const int pair_stride = p->radices[0] >= 8 ? N + N / 16 : N;
+  size_t per_pair = (size_t)pair_stride * sizeof(float2) * 2;
+  int pairs = (int)std::min<size_t>(8, std::max<size_t>(1, (68 * 1024) / per_pair));
   p->pairs_per_tile = pairs;
   p->tile_frames = 2 * pairs;
   p->smem_bytes = per_pair * pairs;
@@ -416,7 +427,7 @@ static void fill_params(GenericParams& P, const mafe_plan* p, const mafe_batch* 
   P.dither = d.dither; P.seed = d.dither_seed;
   P.window = p->window_dev; P.tw = p->twiddle_dev;
   for (int i = 0; i < kMaxStages; ++i) P.fft.radices[i] = i < p->n_stages ? p->radices[i] : 1;
-  P.fft.n_stages = p->n_stages; P.pairs = p->pairs_per_tile;
+  P.fft.n_stages = p->n_stages; P.pairs = p->pairs_per_tile; P.pair_stride = p->radices[0] >= 8 ? p->d.n_fft + p->d.n_fft / 16 : p->d.n_fft;
   P.out_kind = d.out_kind; P.power = d.power; P.spec_scale = d.spec_scale;
   P.n_mels = d.n_mels; P.row_ptr = p->mel.row_ptr; P.col = p->mel.col; P.val = p->mel.val;
   P.log_kind = d.log_kind; P.log_arg = d.log_arg; P.log_mult = d.log_mult; P.log_offset = d.log_offset;

@@ -54,6 +54,8 @@ def test_stft_shapes_and_layout(ma, golden):
     (98, 49, None, "hann", "constant"), (202, 50, None, "hann", "reflect"),             # 2*7^2 and 2*101: prime radix
     (512, 400, None, "hann", "constant"), (512, 500, None, "hann", "constant"),         # hop > n_fft/2 (reference bug)
     (512, 256, None, "hann", "wrap"),                                                    # host-pad fallback
+    (256, 64, None, "hann", "reflect"), (4096, 1024, None, "hann", "constant"), (8192, 2048, 6000, "hamming", "constant"),
+    (1024, 256, None, "hann", "constant"), (128, 32, None, "hann", "constant"),          # radix-16 passes: 16*16, 16^3, 16^3*2, 16*16*4; 128 = 4^3*2
 ])
 def test_stft_batch_vs_oracle(ma, n_fft, hop, win, window, mode):
     x = synth(2, (3, 16000))
