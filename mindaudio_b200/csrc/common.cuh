@@ -110,7 +110,8 @@ struct mafe_plan {
   std::vector<int> radices;
   int* radices_dev = nullptr;
   int n_stages = 0;
-  int pairs_per_tile = 0;  // complex FFTs per CTA; tile_frames = 2 * pairs
+  int pairs_per_tile = 0;  // complex FFTs per CTA and pass; a batch tile holds several such groups
+  bool tables_in_smem = false;   // generic kernel: window / mel CSR staged in shared memory
   int tile_frames = 0;
   size_t smem_bytes = 0;
   float2* twiddle_dev = nullptr;  // [n_fft] W_N^k

@@ -37,6 +37,9 @@ struct GenericParams {
   FftStages fft;
   int pairs;
   int pair_stride;
+  int sub_tiles;        // groups of 2*pairs frames per batch tile
+  int tables_in_smem;   // window (+ mel CSR) staged in shared memory behind the ping-pong buffers
+  int nnz;
   int out_kind;
   float power, spec_scale;
   int n_mels;
@@ -70,15 +73,15 @@ __device__ __forceinline__ float signal_sample(const GenericParams& P, int64_t o
 }
 
 // windowed entry n of frame f (before the scalar mean is removed); 0 outside the utterance's frames
-__device__ __forceinline__ float frame_entry(const GenericParams& P, int64_t off, int64_t L, int64_t T, int64_t f, int n,
-                                             uint32_t utt) {
+__device__ __forceinline__ float frame_entry(const GenericParams& P, const float* __restrict__ win, int64_t off, int64_t L, int64_t T,
+                                             int64_t f, int n, uint32_t utt) {
   if (f >= T || n >= P.frame_len) return 0.0f;
   int64_t s = f * P.hop + n;
   if (P.center) {
     s = pad_index_fast(s - P.n_fft / 2, L, P.pad_mode);
     if (s < 0) return 0.0f;
   }
-  return signal_sample(P, off, s, utt) * P.window[n];
+  return signal_sample(P, off, s, utt) * win[n];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(kGenericThreads) frame_sum_kernel(GenericParam
   const int total = tile_frames * P.frame_len;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     int f = idx / P.frame_len, n = idx - f * P.frame_len;
-    acc += (double)frame_entry(P, off, L, T, tile.frame0 + f, n, (uint32_t)tile.utt);
+    acc += (double)frame_entry(P, P.window, off, L, T, tile.frame0 + f, n, (uint32_t)tile.utt);
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __shared__ double warp_sums[kGenericThreads / 32];
@@ -114,20 +117,47 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   extern __shared__ float2 smem[];
   const int N = P.n_fft;
   const int pairs = P.pairs;
-  float2* cur = smem;
   const int ps = P.pair_stride;   // elements between the sequences of consecutive pairs (N, or N + N/16 with radix-16 passes)
-  float2* nxt = smem + (size_t)pairs * ps;
+  float2* buf0 = smem;
+  float2* buf1 = smem + (size_t)pairs * ps;
 
-  Tile tile = P.tiles[blockIdx.x];
-  tile.frame0 += blockIdx.y * 2 * pairs;   // batch tiles may be larger than this kernel's 2*pairs frames (gridDim.y sub-tiles)
-  const uint32_t utt = (uint32_t)tile.utt;
+  // per-plan tables staged once per CTA (the CTA then walks all sub-tiles of its batch tile): window, mel CSR
+  const float* win = P.window;
+  const int* row_ptr = P.row_ptr;
+  const int* col = P.col;
+  const float* val = P.val;
+  if (P.tables_in_smem) {
+    float* t_win = reinterpret_cast<float*>(smem + (size_t)2 * pairs * ps);
+    for (int i = threadIdx.x; i < P.frame_len; i += blockDim.x) t_win[i] = P.window[i];
+    win = t_win;
+    if (P.out_kind >= MAFE_OUT_MEL) {
+      int* t_rp = reinterpret_cast<int*>(t_win + P.frame_len);
+      int* t_col = t_rp + P.n_mels + 1;
+      float* t_val = reinterpret_cast<float*>(t_col + P.nnz);
+      for (int i = threadIdx.x; i <= P.n_mels; i += blockDim.x) t_rp[i] = P.row_ptr[i];
+      for (int i = threadIdx.x; i < P.nnz; i += blockDim.x) { t_col[i] = P.col[i]; t_val[i] = P.val[i]; }
+      row_ptr = t_rp; col = t_col; val = t_val;
+    }
+    __syncthreads();
+  }
+
+  const Tile tile0 = P.tiles[blockIdx.x];
+  const uint32_t utt = (uint32_t)tile0.utt;
   const int64_t off = P.sample_offsets[utt];
   const int64_t L = P.sample_offsets[utt + 1] - off;
   const int64_t fo = P.frame_offsets[utt];
   const int64_t T = P.frame_offsets[utt + 1] - fo;
-  if (tile.frame0 >= T) return;
   float mu = 0.0f;
   if (P.remove_mean) mu = (float)(P.utt_sum[utt] / ((double)T * (double)P.frame_len));
+  float vmax = -INFINITY;
+
+  for (int sub = 0; sub < P.sub_tiles; ++sub) {
+  Tile tile = tile0;
+  tile.frame0 += sub * 2 * pairs;   // the batch tile holds sub_tiles groups of 2*pairs frames
+  if (tile.frame0 >= T) break;
+  if (sub > 0) __syncthreads();     // the previous group's buffers have been read
+  float2* cur = buf0;
+  float2* nxt = buf1;
 
   // ---- load: frame pair p -> complex sequence a + i b, windowed, scalar mean removed ----
   for (int p = 0; p < pairs; ++p) {
@@ -135,8 +165,8 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       float a = 0.f, b = 0.f;
       if (n < P.frame_len) {   // zero padding of the window up to n_fft otherwise
-        a = frame_entry(P, off, L, T, fa, n, utt);
-        b = frame_entry(P, off, L, T, fa + 1, n, utt);
+        a = frame_entry(P, win, off, L, T, fa, n, utt);
+        b = frame_entry(P, win, off, L, T, fa + 1, n, utt);
         if (fa < T) a -= mu;
         if (fa + 1 < T) b -= mu;
       }
@@ -180,18 +210,17 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
       }
     }
   }
-  if (P.out_kind <= MAFE_OUT_POWER) return;
+  if (P.out_kind <= MAFE_OUT_POWER) continue;
   __syncthreads();
 
   // ---- sparse mel projection (CSR by filter) + log ----
-  float vmax = -INFINITY;
   const int nm = P.n_mels;
   for (int idx = threadIdx.x; idx < 2 * pairs * nm; idx += blockDim.x) {
     int f = idx / nm, m = idx - f * nm;
     if (tile.frame0 + f >= T) continue;
     const float* row = pw + f * nb;
     float acc = 0.f;
-    for (int i = P.row_ptr[m]; i < P.row_ptr[m + 1]; ++i) acc = fmaf(__ldg(&P.val[i]), row[__ldg(&P.col[i])], acc);
+    for (int i = row_ptr[m]; i < row_ptr[m + 1]; ++i) acc = fmaf(val[i], row[col[i]], acc);
     float o = acc;
     switch (P.log_kind) {
       case MAFE_LOG_LN_EPS_IF_ZERO: o = logf(acc == 0.f ? 2.220446049250313e-16f : acc); break;
@@ -201,7 +230,8 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
     }
     P.out[(fo + tile.frame0 + f) * P.out_dim + m] = o;
   }
-  if (P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE) {
+  }   // sub-tile loop
+  if (P.out_kind >= MAFE_OUT_MEL && P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE) {
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) {
       int g = P.db_group == MAFE_DBGROUP_UTT ? (int)utt : (P.db_group == MAFE_DBGROUP_BATCH ? 0 : P.utt_group[utt]);
@@ -362,7 +392,9 @@ int generic_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) 
   size_t per_pair = (size_t)pair_stride * sizeof(float2) * 2;
   int pairs = (int)std::min<size_t>(8, std::max<size_t>(1, (68 * 1024) / per_pair));
   p->pairs_per_tile = pairs;
-  p->tile_frames = 2 * pairs;
+  // a batch tile = several groups of 2*pairs frames walked by ONE CTA (~32 frames): the window and the mel CSR are
+  // staged in shared memory once per CTA instead of being fetched from global memory for every 2*pairs frames
+  p->tile_frames = 2 * pairs * std::max(1, 16 / pairs);
   p->smem_bytes = per_pair * pairs;
   if (p->smem_bytes > 200 * 1024) {
     set_error("n_fft=%d needs %zu bytes of shared memory per frame pair (max n_fft is 8192)", N, p->smem_bytes);
@@ -398,6 +430,13 @@ int generic_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) 
   if (d->out_kind == MAFE_OUT_MFCC) {
     if ((rc = upload(&p->dct_dev, d->dct, (size_t)d->n_mels * d->n_mfcc))) return rc;
   }
+  {
+    size_t tab = sizeof(float) * (size_t)d->frame_len;
+    if (d->out_kind >= MAFE_OUT_MEL) tab += sizeof(int) * (size_t)(d->n_mels + 1) + (sizeof(int) + sizeof(float)) * (size_t)p->mel.nnz;
+    tab = (tab + 15) & ~(size_t)15;
+    p->tables_in_smem = tab <= 48 * 1024 && p->smem_bytes + tab <= 200 * 1024;
+    if (p->tables_in_smem) p->smem_bytes += tab;
+  }
   if (p->smem_bytes > 48 * 1024)
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(generic_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p->smem_bytes));
@@ -428,6 +467,8 @@ static void fill_params(GenericParams& P, const mafe_plan* p, const mafe_batch* 
   P.window = p->window_dev; P.tw = p->twiddle_dev;
   for (int i = 0; i < kMaxStages; ++i) P.fft.radices[i] = i < p->n_stages ? p->radices[i] : 1;
   P.fft.n_stages = p->n_stages; P.pairs = p->pairs_per_tile; P.pair_stride = p->radices[0] >= 8 ? p->d.n_fft + p->d.n_fft / 16 : p->d.n_fft;
+  P.sub_tiles = (p->tile_frames + 2 * p->pairs_per_tile - 1) / (2 * p->pairs_per_tile);
+  P.tables_in_smem = p->tables_in_smem; P.nnz = p->mel.nnz;
   P.out_kind = d.out_kind; P.power = d.power; P.spec_scale = d.spec_scale;
   P.n_mels = d.n_mels; P.row_ptr = p->mel.row_ptr; P.col = p->mel.col; P.val = p->mel.val;
   P.log_kind = d.log_kind; P.log_arg = d.log_arg; P.log_mult = d.log_mult; P.log_offset = d.log_offset;
@@ -468,8 +509,7 @@ int generic_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wa
     MAFE_LAUNCH_CHECK(ctx);
   }
   ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-  const int sub = (p->tile_frames + 2 * p->pairs_per_tile - 1) / (2 * p->pairs_per_tile);
-  generic_frontend_kernel<<<dim3(b->n_tiles, sub), kGenericThreads, p->smem_bytes, ctx->stream>>>(P);
+  generic_frontend_kernel<<<b->n_tiles, kGenericThreads, p->smem_bytes, ctx->stream>>>(P);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
 }
