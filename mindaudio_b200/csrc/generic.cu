@@ -162,6 +162,27 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
   // ---- load: frame pair p -> complex sequence a + i b, windowed, scalar mean removed ----
   for (int p = 0; p < pairs; ++p) {
     const int64_t fa = tile.frame0 + 2 * p;
+    // interior pair (both frames exist, no sample outside the utterance, float input without dither / pre-emphasis):
+    // straight coalesced loads, four in flight per thread
+    const int64_t s_lo = fa * P.hop - (P.center ? P.n_fft / 2 : 0);
+    const bool interior = fa + 1 < T && s_lo >= 0 && s_lo + P.hop + P.frame_len <= L && P.wave_dtype == MAFE_WAVE_F32 &&
+                          P.dither == 0.0f && !P.preemph_on;
+    if (interior) {
+      const float* wa = (const float*)P.wave + off + s_lo;
+      const float* wb = wa + P.hop;
+      const float sc_w = P.wave_scale;
+#pragma unroll 4
+      for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        if (n < P.frame_len) {
+          const float w = win[n];
+          a = fmaf(__ldg(wa + n) * sc_w, w, -mu);
+          b = fmaf(__ldg(wb + n) * sc_w, w, -mu);
+        }
+        cur[(size_t)p * ps + n] = make_float2(a, b);
+      }
+      continue;
+    }
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       float a = 0.f, b = 0.f;
       if (n < P.frame_len) {   // zero padding of the window up to n_fft otherwise
