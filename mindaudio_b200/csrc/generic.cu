@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
       const float* wa = (const float*)P.wave + off + s_lo;
       const float* wb = wa + P.hop;
       const float sc_w = P.wave_scale;
-#pragma unroll 4
+#pragma unroll 8
       for (int n = threadIdx.x; n < N; n += blockDim.x) {
         float a = 0.f, b = 0.f;
         if (n < P.frame_len) {
@@ -241,7 +241,22 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
     if (tile.frame0 + f >= T) continue;
     const float* row = pw + f * nb;
     float acc = 0.f;
-    for (int i = row_ptr[m]; i < row_ptr[m + 1]; ++i) acc = fmaf(val[i], row[col[i]], acc);
+    if (P.tables_in_smem) {
+      // explicit shared-memory loads (through the generic pointers the compiler emits LD, not LDS)
+      const uint32_t a_rp = (uint32_t)__cvta_generic_to_shared(row_ptr), a_col = (uint32_t)__cvta_generic_to_shared(col),
+                     a_val = (uint32_t)__cvta_generic_to_shared(val);
+      int i0, i1;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(i0) : "r"(a_rp + 4u * m));
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(i1) : "r"(a_rp + 4u * m + 4u));
+      for (int i = i0; i < i1; ++i) {
+        int c; float v;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(c) : "r"(a_col + 4u * i));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a_val + 4u * i));
+        acc = fmaf(v, row[c], acc);
+      }
+    } else {
+      for (int i = row_ptr[m]; i < row_ptr[m + 1]; ++i) acc = fmaf(__ldg(&val[i]), row[__ldg(&col[i])], acc);
+    }
     float o = acc;
     switch (P.log_kind) {
       case MAFE_LOG_LN_EPS_IF_ZERO: o = logf(acc == 0.f ? 2.220446049250313e-16f : acc); break;
