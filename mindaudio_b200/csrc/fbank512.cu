@@ -545,9 +545,10 @@ static bool stft_plan_supported(const mafe_frontend_desc* d) {
 
 // n_fft = 320 (deepspeech2) / 400 complex STFT: N1 of stftn16_kernel, or 0
 static int stftn_plan_supported(const mafe_frontend_desc* d) {
-  if (d->out_kind != MAFE_OUT_COMPLEX || d->frame_len != d->n_fft || d->preemph != 0.0 || d->remove_frame_mean || d->dither != 0.f ||
-      d->spec_scale != 1.0f)
+  if (!(d->out_kind == MAFE_OUT_COMPLEX || d->out_kind == MAFE_OUT_POWER) || d->frame_len != d->n_fft || d->preemph != 0.0 ||
+      d->remove_frame_mean || d->dither != 0.f)
     return 0;
+  if (d->out_kind == MAFE_OUT_POWER && !(d->power > 0.f)) return 0;
   if (d->n_fft != 320 && d->n_fft != 400) return 0;
   if (d->hop < 1 || d->hop > d->n_fft / 2) return 0;
   return d->n_fft / 16;
@@ -612,7 +613,7 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
   if (th->stftn) {
     const int N1 = th->stftn, N = 16 * N1, B = N1 == 25 ? 5 : 4;   // N1 = 5 x B: twiddles W_N1^(j1 k1), j1 = 1..4, k1 = 1..B-1
     std::vector<float> wn(N);
-    for (int i = 0; i < N; ++i) wn[i] = 0.5f * d->window[i];   // 1/2: the pair separation leaves 2X
+    for (int i = 0; i < N; ++i) wn[i] = 0.5f * d->spec_scale * d->window[i];   // 1/2: the pair separation leaves 2X
     std::vector<float2> twn(N);
     for (int kj = 0; kj < N1; ++kj)
       for (int t = 0; t < 16; ++t) {
@@ -751,6 +752,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     S.sample_offsets = b->sample_offsets_dev; S.frame_offsets = b->frame_offsets_dev; S.tiles = b->tiles_dev;
     S.n_tiles = b->n_tiles; S.hop = d.hop; S.center = d.center; S.pad_mode = d.pad_mode;
     S.window = th->dev.window; S.twn = th->tw400_dev; S.out = out; S.queue_head = b->queue_dev;
+    S.out_power = d.out_kind == MAFE_OUT_POWER; S.power = d.power;
     for (int i = 0; i < 16; ++i) S.tws[i] = th->tws[i];
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);

@@ -7,7 +7,8 @@
 // waveform tile, in-place pad pass for the first / last tile of an utterance,
 // frame pairs packed a + i*b): each lane of a 16-lane group transforms N1 points in registers (4 x 5 or 5 x 5),
 // W_N twiddle, the 16-point stage runs as 2 * N1 independent 16-point DFTs per warp in two rounds of 32 lanes.
-// Every warp owns its two pairs from the transform to the store; rows are written with lanes = consecutive bins.
+// Every warp owns its two pairs from the transform to the store; rows are written with lanes = consecutive bins --
+// complex64 (stft) or |X|^power (spectrogram: msaudio.Spectrogram, window pre-scaled by the normalisation).
 #pragma once
 #include "fft400.cuh"
 
@@ -45,7 +46,9 @@ struct StftNParams {
   int hop, center, pad_mode;
   const float* window;     // [kN], pre-scaled by 1/2 (the pair separation leaves 2X)
   const float2* twn;       // [N1][16]  W_N^(t kj)
-  float* out;              // [total_frames][kBins] complex64
+  float* out;              // [total_frames][kBins] complex64, or float |X|^power (out_power != 0)
+  int out_power;           // 0: complex STFT; 1: power / magnitude spectrogram (spectrum.spectrogram, spectrum.py:547-606)
+  float power;
   int* queue_head;
   float2 tws[16];          // W_N1^(j1 k1): 16 (N1 = 25) or 12 (N1 = 20) entries, kernel-parameter constant bank
 };
@@ -239,22 +242,40 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     __syncwarp();
     if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4: the next tile lands while this one is stored
 
-    // ---- emit: this warp's two pairs, lanes = consecutive bins (rows of kBins complex64) ----
+    // ---- emit: this warp's two pairs, lanes = consecutive bins ----
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int pq = warp * 2 + q;
       const int fa = 2 * pq;
       const float2* zp = Zs + pq * kSlot;
-      float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
-      float2* ob = oa + kBins;
       const bool wa = fa < cur.nf, wb = fa + 1 < cur.nf;
+      if (P.out_power == 0) {   // rows of kBins complex64
+        float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
+        float2* ob = oa + kBins;
 #pragma unroll 2
-      for (int k = lane; k < kBins; k += 32) {
-        const float2 zk = zp[k];
-        const float2 zn = zp[kN - k];
-        // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
-        if (wa) oa[k] = make_float2(zk.x + zn.x, zk.y - zn.y);
-        if (wb) ob[k] = make_float2(zk.y + zn.y, zn.x - zk.x);
+        for (int k = lane; k < kBins; k += 32) {
+          const float2 zk = zp[k];
+          const float2 zn = zp[kN - k];
+          // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
+          if (wa) oa[k] = make_float2(zk.x + zn.x, zk.y - zn.y);
+          if (wb) ob[k] = make_float2(zk.y + zn.y, zn.x - zk.x);
+        }
+      } else {                  // rows of kBins floats: |X|^power
+        float* oa = P.out + (cur.out_row + fa) * (int64_t)kBins;
+        float* ob = oa + kBins;
+#pragma unroll 2
+        for (int k = lane; k < kBins; k += 32) {
+          const float2 zk = zp[k];
+          const float2 zn = zp[kN - k];
+          const float ra = zk.x + zn.x, ia = zk.y - zn.y, rb = zk.y + zn.y, ib = zn.x - zk.x;
+          float pa = fmaf(ra, ra, ia * ia), pb = fmaf(rb, rb, ib * ib);
+          if (P.power != 2.0f) {
+            if (P.power == 1.0f) { pa = sqrtf(pa); pb = sqrtf(pb); }
+            else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
+          }
+          if (wa) oa[k] = pa;
+          if (wb) ob[k] = pb;
+        }
       }
     }
     __syncthreads();   // the Z slots may be overwritten; s_work / info of the next tile are visible
