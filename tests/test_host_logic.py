@@ -1,0 +1,49 @@
+"""Host-side logic that needs no GPU: SpecAugment rectangle drawing (same `random` sequence as the reference), the
+host route of pad_sequence (label sequences), make_pad_mask, the phase-vocoder step tables, enum coercion."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import restated as R
+
+
+def test_spec_aug_rects_reproduce_reference_draws():
+    from mindaudio_b200.data.masking import spec_aug_rects
+    conf = {"num_t_mask": 3, "num_f_mask": 2, "max_t": 40, "max_f": 12}
+    rng = np.random.default_rng(2)
+    xs = [rng.standard_normal((n, 80)).astype(np.float32) + 3.0 for n in (90, 17, 333, 1)]
+    ref = R.spec_aug([x.copy() for x in xs], conf, random.Random(99))
+    rects = spec_aug_rects([x.shape for x in xs], conf, random.Random(99))
+    assert rects.dtype == np.int32 and rects.shape[1] == 5
+    out = [x.copy() for x in xs]
+    for item, r0, r1, c0, c1 in rects:
+        out[item][r0:r1, c0:c1] = 0
+    assert all(np.array_equal(a, b) for a, b in zip(out, ref))
+    assert spec_aug_rects([(10, 80)], {}, random.Random(1)).shape == (0, 5)
+
+
+def test_pad_sequence_host_route_and_masks():
+    from mindaudio_b200.data.collate import make_pad_mask, pad_sequence
+    rng = np.random.default_rng(4)
+    labels = [rng.integers(0, 50, size=n).astype(np.int32) for n in (4, 9, 2)]
+    for kw in (dict(padding_value=-1, padding_max_len=10), dict(padding_value=0), dict(batch_first=False, padding_value=7, padding_max_len=3)):
+        a, b = pad_sequence(labels, **kw), R.pad_sequence(labels, **kw)
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert np.array_equal(make_pad_mask([5, 3, 2]), R.make_pad_mask([5, 3, 2]))
+    assert np.array_equal(make_pad_mask(np.array([5, 3, 2]), 8), R.make_pad_mask(np.array([5, 3, 2]), 8))
+
+
+def test_vocoder_tables_match_numpy_arange():
+    from mindaudio_b200.data.augment import _vocoder_tables
+    for n_frames, rate in ((47, 0.8), (47, 1.0), (47, 1.3), (100, 2.0), (3, 7.5)):
+        n_steps, phi = _vocoder_tables(n_frames, 257, rate, 128)
+        assert n_steps == len(np.arange(0, n_frames, rate, dtype=np.float64))
+        assert phi.shape == (257,) and phi[0] == 0.0 and np.isclose(phi[-1], np.pi * 128)
+
+
+def test_enums_accept_strings_and_members():
+    import mindaudio_b200 as ma
+    assert ma.WindowType("hann") is ma.WindowType.HANN and ma.BorderType("reflect") is ma.BorderType.REFLECT
+    with pytest.raises(ValueError):
+        ma.WindowType("nope")
