@@ -539,8 +539,9 @@ static bool build_combine(const std::vector<BinEntry>& bins, int nm, std::vector
 }
 
 static bool stft_plan_supported(const mafe_frontend_desc* d) {
-  return d->n_fft == kNfft && d->frame_len == kNfft && d->out_kind == MAFE_OUT_COMPLEX && d->hop >= 1 && d->hop <= kStftMaxHop &&
-         d->preemph == 0.0 && !d->remove_frame_mean && d->dither == 0.f && d->spec_scale == 1.0f;
+  if (!(d->out_kind == MAFE_OUT_COMPLEX || (d->out_kind == MAFE_OUT_POWER && d->power > 0.f))) return false;
+  return d->n_fft == kNfft && d->frame_len == kNfft && d->hop >= 1 && d->hop <= kStftMaxHop &&
+         d->preemph == 0.0 && !d->remove_frame_mean && d->dither == 0.f;
 }
 
 // n_fft = 320 (deepspeech2) / 400 complex STFT: N1 of stftn16_kernel, or 0
@@ -597,7 +598,7 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
   p->fast_tables = th;
   th->stft = stft_plan_supported(d);
   std::vector<float> win(kNfft, 0.f);
-  for (int i = 0; i < d->frame_len; ++i) win[i] = th->stft ? 0.5f * d->window[i] : d->window[i];
+  for (int i = 0; i < d->frame_len; ++i) win[i] = th->stft ? 0.5f * d->spec_scale * d->window[i] : d->window[i];
   std::vector<float2> w512(256), w256(256);
   for (int n = 0; n < 256; ++n) {
     double a = -2.0 * M_PI * n / 512.0;
@@ -663,7 +664,8 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     if ((rc = up(&th->dev.window, win))) return rc;
     if ((rc = up(&th->dev.w512, w512))) return rc;
     if ((rc = up(&th->dev.w256t, w256))) return rc;
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftSmem::kTotal));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftSmem::kTotal));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StftSmem::kTotal));
     return MAFE_OK;
   }
   std::vector<BinEntry> bins;
@@ -770,9 +772,11 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     S.n_tiles = b->n_tiles; S.hop = d.hop; S.center = d.center; S.pad_mode = d.pad_mode;
     S.window = th->dev.window; S.w512 = th->dev.w512; S.w256t = th->dev.w256t;
     S.out = out; S.queue_head = b->queue_dev;
+    S.out_power = d.out_kind == MAFE_OUT_POWER; S.power = d.power;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-    stft512_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, StftSmem::kTotal, ctx->stream>>>(S);
+    if (S.out_power) stft512_kernel<true><<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, StftSmem::kTotal, ctx->stream>>>(S);
+    else stft512_kernel<false><<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, StftSmem::kTotal, ctx->stream>>>(S);
     MAFE_LAUNCH_CHECK(ctx);
     return MAFE_OK;
   }

@@ -25,7 +25,9 @@ struct StftParams {
   const float* window;  // [512], pre-scaled by 1/2 (the pair separation leaves 2X)
   const float2* w512;
   const float2* w256t;
-  float* out;           // [total_frames][257] complex64
+  float* out;           // [total_frames][257] complex64, or float |X|^power (out_power != 0: spectrum.spectrogram)
+  int out_power;
+  float power;
   int* queue_head;
 };
 
@@ -56,6 +58,7 @@ struct StftSmem {
 };
 static_assert(StftSmem::kZ % 16 == 0 && StftSmem::kBar % 8 == 0, "smem alignment");
 
+template <bool POWER>   // POWER: |X|^power rows of 257 floats (spectrogram) instead of complex64 rows
 __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_constant__ StftParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* rb = reinterpret_cast<float*>(smem + StftSmem::kRaw);
@@ -219,6 +222,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
       // registers until the odd bins 2kk + 1 (half 1) exist, then both go out as one 16-byte piece -- whole 32-byte
       // sectors per warp store instead of two half-filled passes (which cost +54 % DRAM traffic: partially written
       // sectors were evicted and re-filled between the passes). ----
+      auto pw_of = [&](float re, float im) -> float {   // |X|^power of the power-spectrogram output kind
+        float p = fmaf(re, re, im * im);
+        if (P.power != 2.0f) p = P.power == 1.0f ? sqrtf(p) : powf(sqrtf(p), P.power);
+        return p;
+      };
       if (half == 0) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -231,13 +239,45 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
             // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
             hA[q][i] = make_float2(zk.x + zn.x, zk.y - zn.y);
             hB[q][i] = make_float2(zk.y + zn.y, zn.x - zk.x);
+            if (POWER) { hA[q][i].x = pw_of(hA[q][i].x, hA[q][i].y); hB[q][i].x = pw_of(hB[q][i].x, hB[q][i].y); }
           }
           if (lane == 0) {   // Nyquist bin 256 (kk = 128, its own partner)
             const int fa = 2 * (warp * 2 + q);
             const float2 z = zp[128];
-            float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
-            if (fa < cur.nf) oa[256] = make_float2(2.f * z.x, 0.f);
-            if (fa + 1 < cur.nf) oa[kBins + 256] = make_float2(2.f * z.y, 0.f);
+            if (POWER) {
+              float* oa = P.out + (cur.out_row + fa) * (int64_t)kBins;
+              if (fa < cur.nf) oa[256] = pw_of(2.f * z.x, 0.f);
+              if (fa + 1 < cur.nf) oa[kBins + 256] = pw_of(2.f * z.y, 0.f);
+            } else {
+              float2* oa = reinterpret_cast<float2*>(P.out + (cur.out_row + fa) * (int64_t)(2 * kBins));
+              if (fa < cur.nf) oa[256] = make_float2(2.f * z.x, 0.f);
+              if (fa + 1 < cur.nf) oa[kBins + 256] = make_float2(2.f * z.y, 0.f);
+            }
+          }
+        }
+      } else if (POWER) {
+        // rows of 257 floats (1028 B): bins (2kk, 2kk + 1) go out as one 8-byte piece on the even rows
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int fa = 2 * (warp * 2 + q);
+          const float2* zp = Zs + (warp * 2 + q) * kSlotStride;
+          float* oa = P.out + (cur.out_row + fa) * (int64_t)kBins;
+          float* ob = oa + kBins;
+          const bool a_aligned = ((cur.out_row + fa) & 1) == 0;
+          const bool wa = fa < cur.nf, wb = fa + 1 < cur.nf;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = lane + 32 * i;
+            const float2 zk = zp[kk];
+            const float2 zn = zp[255 - kk];
+            const float pa1 = pw_of(zk.x + zn.x, zk.y - zn.y), pb1 = pw_of(zk.y + zn.y, zn.x - zk.x);
+            if (a_aligned) {
+              if (wa) *reinterpret_cast<float2*>(oa + 2 * kk) = make_float2(hA[q][i].x, pa1);
+              if (wb) { ob[2 * kk] = hB[q][i].x; ob[2 * kk + 1] = pb1; }
+            } else {
+              if (wa) { oa[2 * kk] = hA[q][i].x; oa[2 * kk + 1] = pa1; }
+              if (wb) *reinterpret_cast<float2*>(ob + 2 * kk) = make_float2(hB[q][i].x, pb1);
+            }
           }
         }
       } else {

@@ -192,8 +192,10 @@ def test_spectrogram_melspectrogram_melscale(ma, golden):
     assert rel(ma.spectrogram(xb, pad=7, power=0.5), R.spectrogram(xb, pad=7, power=0.5)) <= 1e-5
     # stftn16 kernels with power output: n_fft 320 / 400, every power / normalisation / pad mode, tile borders
     for kw in (dict(n_fft=320, hop_length=160, power=1.0, normalized=True), dict(n_fft=400, hop_length=100, power=2.0, pad_mode="constant"),
-               dict(n_fft=320, win_length=200, hop_length=80, power=3.0, window="hamming", pad_mode="edge"), dict(n_fft=400, center=False)):
-        for shape in ((3, 16000), (2, 32 * 200 + 399), (4, 400)):
+               dict(n_fft=320, win_length=200, hop_length=80, power=3.0, window="hamming", pad_mode="edge"), dict(n_fft=400, center=False),
+               dict(n_fft=512, hop_length=256), dict(n_fft=512, hop_length=100, power=1.0, normalized=True, pad_mode="symmetric"),
+               dict(n_fft=512, win_length=400, hop_length=160, power=0.5, center=False)):   # stft512 kernel, power output
+        for shape in ((3, 16000), (2, 32 * 200 + 399), (4, kw["n_fft"])):
             xs = synth(31 + shape[1] % 7, shape)
             assert rel(ma.spectrogram(xs, **kw), R.spectrogram(xs, **kw)) <= 1e-5, (kw, shape)
 
