@@ -294,6 +294,57 @@ int mafe_median_filter(mafe_ctx* ctx, const float* x_dev, float* out_dev, int32_
 int mafe_hpss_masks(mafe_ctx* ctx, const float* harm_dev, const float* perc_dev, int64_t n, float margin_h, float margin_p,
                     float power, int32_t split_zeros, float* mask_h_dev, float* mask_p_dev);
 
+/* ---- WAV decode ("next" row f3: mindaudio/data/io.py:347-747 read / _fmt_chunk / _data_chunk / _skip_unknown_chunk) ---- */
+enum {  /* mafe_wav_info.sample_kind: the container of one item of the data chunk (io.py:444-470) */
+  MAFE_WAV_U8 = 1,   /* PCM, bit depth 1..8: unsigned bytes */
+  MAFE_WAV_I8 = 2,
+  MAFE_WAV_I16 = 3,
+  MAFE_WAV_I24 = 4,  /* 3-byte container, returned left-justified in an int32 (io.py:505-512) */
+  MAFE_WAV_I32 = 5,
+  MAFE_WAV_I40 = 6,  /* 5/6/7-byte containers, left-justified in an int64 */
+  MAFE_WAV_I48 = 7,
+  MAFE_WAV_I56 = 8,
+  MAFE_WAV_I64 = 9,
+  MAFE_WAV_F32 = 10,
+  MAFE_WAV_F64 = 11
+};
+enum { MAFE_WAV_OUT_F32 = 0, MAFE_WAV_OUT_F64 = 1, MAFE_WAV_OUT_I16 = 2 };
+enum {  /* mafe_wav_info.warnings: the reference's WavFileWarning cases */
+  MAFE_WAV_WARN_UNKNOWN_CHUNK = 1,  /* "Chunk (non-data) not understood, skipping it." (io.py:730-736) */
+  MAFE_WAV_WARN_EOF = 2,            /* "Reached EOF prematurely" (io.py:684-691) */
+  MAFE_WAV_WARN_INCOMPLETE_ID = 4   /* "Incomplete chunk ID ... ignoring it." (io.py:697-700) */
+};
+enum {  /* mafe_wav_info.error_kind when mafe_wav_parse fails: the exception class the reference raises */
+  MAFE_WAV_ERR_VALUE = 1, MAFE_WAV_ERR_TYPE = 2, MAFE_WAV_ERR_UNBOUND = 3, MAFE_WAV_ERR_ZERODIV = 4
+};
+typedef struct mafe_wav_info {
+  int32_t format_tag;        /* 1 PCM, 3 IEEE float (WAVE_FORMAT_EXTENSIBLE resolved through its GUID, io.py:364-382) */
+  int32_t channels;
+  int32_t sample_rate;
+  int32_t bytes_per_second;
+  int32_t block_align;
+  int32_t bit_depth;
+  int32_t big_endian;        /* RIFX */
+  int32_t sample_kind;       /* MAFE_WAV_* */
+  int32_t bytes_per_sample;  /* block_align / channels */
+  int32_t warnings;          /* MAFE_WAV_WARN_* bits */
+  int32_t error_kind;        /* MAFE_WAV_ERR_* when the call failed */
+  int32_t reserved;
+  int64_t data_offset;       /* byte offset in the buffer of the first item `read` returns */
+  int64_t n_items;           /* items `read` returns, over all channels */
+  int64_t data_chunk_bytes;  /* the data chunk's size field */
+} mafe_wav_info;
+/* Host only, no device work: walk the RIFF/RIFX container held in bytes[0..n_bytes) exactly as `read(file, offset,
+ * duration)` does (duration_s = 0 stands for None).  filelike != 0 selects the reference's path for file objects
+ * without a C-level descriptor (io.BytesIO: read(size) of the whole chunk, `duration` ignored, io.py:500-503). */
+int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_s, double duration_s, int32_t filelike, mafe_wav_info* info);
+/* Device: n_items items of kind sample_kind at payload_dev (byte pointer, any alignment) -> out_dev as float32 / float64
+ * in `read`'s unified output format (int16 / 32768, int32 and 24-bit / 2^31, everything else unchanged; io.py:741-746)
+ * times `scale` (the conformer pipeline's `* (1 << 15)`, examples/conformer/dataset.py:389-390), or as raw int16 in
+ * host byte order (MAFE_WAV_OUT_I16, PCM16 only: the front-end's MAFE_WAVE_I16 input). */
+int mafe_wav_decode(mafe_ctx* ctx, const void* payload_dev, int64_t n_items, int32_t sample_kind, int32_t big_endian,
+                    int32_t out_dtype, double scale, void* out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,2 +1,2 @@
 from mindaudio_b200.data import *  # noqa: F401,F403
-from . import features, spectrum  # noqa: F401
+from . import augment, features, io, processing, spectrum  # noqa: F401

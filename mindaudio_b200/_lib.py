@@ -95,7 +95,23 @@ _PROTOS = {
     "mafe_phase_vocoder": (C.c_int, [_P, _P, _I32, _I32, _I32, C.c_double, _P, _I32, _P]),
     "mafe_median_filter": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32]),
     "mafe_hpss_masks": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _I32, _P, _P]),
+    "mafe_wav_parse": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, _I32, _P]),
+    "mafe_wav_decode": (C.c_int, [_P, _P, C.c_int64, _I32, _I32, _I32, C.c_double, _P]),
 }
+
+
+class WavInfo(C.Structure):
+    """``mafe_wav_info`` (include/mafe.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("format_tag", "channels", "sample_rate", "bytes_per_second", "block_align",
+                                         "bit_depth", "big_endian", "sample_kind", "bytes_per_sample", "warnings",
+                                         "error_kind", "reserved")] + \
+               [(n, C.c_int64) for n in ("data_offset", "n_items", "data_chunk_bytes")]
+
+
+WAV_U8, WAV_I8, WAV_I16, WAV_I24, WAV_I32, WAV_I40, WAV_I48, WAV_I56, WAV_I64, WAV_F32, WAV_F64 = range(1, 12)
+WAV_OUT_F32, WAV_OUT_F64, WAV_OUT_I16 = 0, 1, 2
+WAV_WARN_UNKNOWN_CHUNK, WAV_WARN_EOF, WAV_WARN_INCOMPLETE_ID = 1, 2, 4
+WAV_ERR_VALUE, WAV_ERR_TYPE, WAV_ERR_UNBOUND, WAV_ERR_ZERODIV = 1, 2, 3, 4
 
 _lib = None
 

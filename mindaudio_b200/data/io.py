@@ -1,0 +1,201 @@
+"""WAV input for the feature path ("next" row f3 of the scope table): ``mindaudio/data/io.py:541-747`` (``read``).
+
+* the RIFF / RIFX container walk is native host code (``mafe_wav_parse``: the reference's chunk state machine over
+  a byte buffer, quirks included -- ``offset`` skips BYTES (io.py:489-491), ``duration`` counts items over all
+  channels (io.py:497-498), ``raise <str>`` for a non-WAVE form type surfaces as TypeError (io.py:676));
+* the sample arithmetic of the "unified output format" (io.py:741-746: int16 / 32768, int32 and left-justified
+  24-bit / 2^31) runs in ``mafe_wav_decode`` on the GPU, for ``read`` (numpy out, like every call of this package)
+  and for :func:`load_batch` (payloads of many files -> one device-resident waveform batch for the front-end).
+
+There is no CPU decode path: integer PCM goes through the device kernel, float / 8-bit payloads are returned as the
+dtype view of the file's bytes exactly as the reference returns them (no arithmetic is defined for them).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from .. import _lib as L
+from .._engine import get_engine
+
+__all__ = ["read", "wav_info", "WavFileWarning", "load_batch", "WavBatch"]
+
+
+class WavFileWarning(UserWarning):
+    """io.py:339-340."""
+
+
+_ERRORS = {L.WAV_ERR_VALUE: ValueError, L.WAV_ERR_TYPE: TypeError, L.WAV_ERR_UNBOUND: UnboundLocalError,
+           L.WAV_ERR_ZERODIV: ZeroDivisionError}
+_DTYPES = {L.WAV_U8: "u1", L.WAV_I8: "i1", L.WAV_I16: "i2", L.WAV_I32: "i4", L.WAV_I64: "i8", L.WAV_F32: "f4", L.WAV_F64: "f8"}
+
+
+def wav_info(raw, offset=0.0, duration=None, filelike=False):
+    """Walk the container held in ``raw`` (bytes-like) the way ``read(file, offset, duration)`` does.  Returns the
+    filled :class:`mindaudio_b200._lib.WavInfo`; raises what the reference raises; warns what it warns."""
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    info = L.WavInfo()
+    lib = L.load()
+    rc = lib.mafe_wav_parse(buf.ctypes.data_as(C.c_void_p), buf.size, float(offset or 0.0), float(duration or 0.0),
+                            int(bool(filelike)), C.byref(info))
+    if rc != L.OK:
+        msg = lib.mafe_last_error().decode("utf-8", "replace")
+        raise _ERRORS.get(info.error_kind, L.MafeError)(msg)
+    if info.warnings & L.WAV_WARN_UNKNOWN_CHUNK:
+        warnings.warn("Chunk (non-data) not understood, skipping it.", WavFileWarning, stacklevel=3)
+    if info.warnings & L.WAV_WARN_INCOMPLETE_ID:
+        warnings.warn("Incomplete chunk ID, ignoring it.", WavFileWarning, stacklevel=3)
+    if info.warnings & L.WAV_WARN_EOF:
+        warnings.warn("Reached EOF prematurely; finished at {:d} bytes.".format(buf.size), WavFileWarning, stacklevel=3)
+    return info
+
+
+def _file_bytes(file):
+    """(bytes of the file from its current position, filelike flag) -- io.py:644-647, 500-503."""
+    if hasattr(file, "read"):
+        try:
+            file.fileno()
+            filelike = False
+        except (OSError, AttributeError):   # io.UnsupportedOperation is an OSError: np.fromfile cannot be used (io.py:500)
+            filelike = True
+        try:
+            raw = file.read()
+        finally:
+            file.seek(0)                      # io.py:738-739
+        return raw, filelike
+    with open(file, "rb") as fh:
+        return fh.read(), False
+
+
+def _decode_device(raw_u8, info, out_dtype, scale=1.0):
+    """Integer PCM payload -> float array through ``mafe_wav_decode`` (numpy in / numpy out)."""
+    n = int(info.n_items)
+    bps = {L.WAV_I16: 2, L.WAV_I24: 3, L.WAV_I32: 4}[info.sample_kind]
+    out = np.empty(n, dtype=out_dtype)
+    if n:
+        payload = raw_u8[info.data_offset: info.data_offset + n * bps]
+        eng = get_engine()
+        with eng.lock:
+            d_in = eng.buf("wave", max(payload.nbytes, 16))
+            d_out = eng.buf("out", out.nbytes)
+            keep = eng.h2d(d_in, payload)
+            L.check(eng.lib.mafe_wav_decode(eng.ctx, d_in, n, info.sample_kind, info.big_endian,
+                                            L.WAV_OUT_F64 if out.dtype == np.float64 else L.WAV_OUT_F32, float(scale), d_out))
+            eng.d2h(out, d_out)
+            eng.sync()
+            del keep
+    return out
+
+
+def read(file, offset=0.0, duration=None):
+    """``mindaudio.data.io.read`` (io.py:552-747): ``(audio, samplerate)``.
+
+    Little-endian int16 PCM -> float64 in [-1, 1) (``/ 32768``), int32 and 24-bit PCM -> float64 (``/ 2147483648``);
+    8-bit PCM -> uint8 unchanged, IEEE float -> the file's float dtype (byte order included), 5/6/7-byte containers ->
+    int64 left-justified, RIFX (big-endian) integer PCM -> the big-endian integers unscaled (the reference's dtype
+    test at io.py:741-746 never matches a big-endian dtype); 1-D for one channel, ``(n, channels)`` otherwise."""
+    raw, filelike = _file_bytes(file)
+    info = wav_info(raw, offset, duration, filelike)
+    u8 = np.frombuffer(raw, dtype=np.uint8)
+    kind, n, e = info.sample_kind, int(info.n_items), (">" if info.big_endian else "<")
+    if kind in (L.WAV_I16, L.WAV_I24, L.WAV_I32) and not info.big_endian:
+        audio = _decode_device(u8, info, np.float64)
+    elif kind in (L.WAV_I24, L.WAV_I40, L.WAV_I48, L.WAV_I56):
+        # byte placement only (io.py:505-512).  No arithmetic is applied to int64 containers, nor to RIFX integer
+        # files: the reference compares the dtype with "int16" / "int32", which a big-endian dtype never equals
+        # (io.py:741-746), so it returns the left-justified integers as they are.
+        bps, wide = info.bytes_per_sample, (4 if kind == L.WAV_I24 else 8)
+        a = np.zeros((n, wide), dtype=np.uint8)
+        rows = u8[info.data_offset: info.data_offset + n * bps].reshape(n, bps)
+        if info.big_endian:
+            a[:, :bps] = rows
+        else:
+            a[:, wide - bps:] = rows
+        audio = a.view(e + "i%d" % wide).reshape(n)
+    else:
+        audio = np.array(np.frombuffer(raw, dtype=e + _DTYPES[kind] if kind not in (L.WAV_U8, L.WAV_I8) else _DTYPES[kind],
+                                       count=n, offset=int(info.data_offset)))
+    if info.channels > 1:
+        audio = audio.reshape(-1, info.channels)
+    return audio, int(np.uint32(info.sample_rate))
+
+
+class WavBatch:
+    """A batch of decoded mono waveforms resident on the GPU: ``wave_dev`` (device pointer), ``dtype`` (``L.WAVE_I16``
+    or ``L.WAVE_F32``), ``sample_offsets`` int64 ``[B + 1]``, ``sample_rates``."""
+
+    def __init__(self, wave_dev, dtype, sample_offsets, sample_rates, wave_scale):
+        self.wave_dev, self.dtype, self.sample_offsets = wave_dev, dtype, sample_offsets
+        self.sample_rates, self.wave_scale = sample_rates, wave_scale
+
+    @property
+    def lengths(self):
+        return np.diff(self.sample_offsets)
+
+
+def load_batch(files, int16_scaled=True, buffer_name="wavbatch"):
+    """Decode mono WAV files straight into one device-resident waveform batch (no host-side float pass).
+
+    ``int16_scaled=True`` produces what the conformer pipeline feeds its front-end, ``read(path) * (1 << 15)``
+    (examples/conformer/dataset.py:389-390): PCM16 files are uploaded as they are (2 bytes / sample) and consumed by
+    the front-end's int16 input path; every other format is decoded on the device to float32 with the factor folded
+    into the decode.  ``int16_scaled=False`` gives ``read(path)`` as float32.
+
+    Returns a :class:`WavBatch`; its device buffer belongs to the engine (name ``buffer_name``) and stays valid until
+    the next ``load_batch`` with the same name."""
+    raws, infos = [], []
+    for f in files:
+        raw, filelike = _file_bytes(f)
+        info = wav_info(raw, 0.0, None, filelike)
+        if info.channels != 1:
+            raise ValueError("load_batch: %r has %d channels; the feature front-end takes mono waveforms" % (f, info.channels))
+        if info.sample_kind in (L.WAV_I40, L.WAV_I48, L.WAV_I56, L.WAV_I64):
+            raise ValueError("load_batch: %r holds 64-bit integer samples, which have no unit-range scaling in read()" % (f,))
+        raws.append(np.frombuffer(raw, dtype=np.uint8))
+        infos.append(info)
+    n = len(infos)
+    so = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([int(i.n_items) for i in infos], out=so[1:])
+    total = int(so[-1])
+    scale = 32768.0 if int16_scaled else 1.0
+    all_pcm16 = int16_scaled and n > 0 and all(i.sample_kind == L.WAV_I16 and not i.big_endian for i in infos)
+    eng = get_engine()
+    item_out = 2 if all_pcm16 else 4
+    with eng.lock:
+        d_wave = eng.buf(buffer_name, max(total * item_out, 16))
+        # one staging buffer for all payloads (a single H2D), decoded per run of files sharing a format
+        sizes = [int(i.n_items) * L_BYTES[i.sample_kind] for i in infos]
+        bo = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(sizes, out=bo[1:])
+        stage = np.empty(max(int(bo[-1]), 1), dtype=np.uint8)
+        for k, (u8, i) in enumerate(zip(raws, infos)):
+            stage[bo[k]: bo[k + 1]] = u8[i.data_offset: i.data_offset + sizes[k]]
+        if all_pcm16:
+            keep = eng.h2d(d_wave, stage[: int(bo[-1])]) if total else None          # the payload IS the int16 batch
+        else:
+            d_stage = eng.buf("wavstage", max(stage.nbytes, 16))
+            keep = eng.h2d(d_stage, stage)
+            k = 0
+            while k < n:
+                j = k
+                while j + 1 < n and (infos[j + 1].sample_kind, infos[j + 1].big_endian) == (infos[k].sample_kind, infos[k].big_endian):
+                    j += 1
+                items = int(so[j + 1] - so[k])
+                if items:
+                    # read() leaves RIFX integer PCM unscaled (io.py:741-746 never matches a big-endian dtype)
+                    undo = 1.0
+                    if infos[k].big_endian:
+                        undo = {L.WAV_I16: 32768.0, L.WAV_I24: 2147483648.0, L.WAV_I32: 2147483648.0}.get(infos[k].sample_kind, 1.0)
+                    L.check(eng.lib.mafe_wav_decode(
+                        eng.ctx, C.c_void_p(d_stage.value + int(bo[k])), items, infos[k].sample_kind, infos[k].big_endian,
+                        L.WAV_OUT_F32, scale * undo,
+                        C.c_void_p(d_wave.value + int(so[k]) * item_out)))
+                k = j + 1
+        eng.sync()
+        del keep
+    return WavBatch(d_wave, L.WAVE_I16 if all_pcm16 else L.WAVE_F32, so, [int(np.uint32(i.sample_rate)) for i in infos], 1.0)
+
+
+L_BYTES = {L.WAV_U8: 1, L.WAV_I8: 1, L.WAV_I16: 2, L.WAV_I24: 3, L.WAV_I32: 4, L.WAV_F32: 4, L.WAV_F64: 8}

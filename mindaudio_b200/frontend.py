@@ -149,28 +149,55 @@ class FbankPipeline:
         ``spec_aug_conf`` (dataset.py:493-534) masks time / frequency rectangles of the ragged features on the device
         before the padding; the positions come from ``rng`` (a ``random.Random``; default the ``random`` module) with
         the reference's call sequence."""
-        eng = self.eng
         lens = [len(w) for w in waves]
         dt = np.int16 if waves and all(np.asarray(w).dtype == np.int16 for w in waves) else np.float32
         flat = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=dt) for w in waves])) if waves else np.zeros(0, dt)
         so = np.zeros(len(lens) + 1, dtype=np.int64)
         np.cumsum(lens, out=so[1:])
+        eng = self.eng
+        with eng.lock:
+            d_w = eng.buf("wave", max(flat.nbytes, 16))
+            keep = eng.h2d(d_w, flat)
+            res = self._padded_from_device(d_w, L.WAVE_I16 if dt == np.int16 else L.WAVE_F32, so, max_len, padding_value,
+                                           wave_scale, spec_aug_conf, rng)
+            del keep
+        return res
+
+    def features_from_wav(self, files, max_len=None, padding_value=0.0, spec_aug_conf=None, rng=None):
+        """WAV files -> padded feature batch, the whole ``read -> * (1 << 15) -> compute_fbank_feats -> CMVN ->
+        spec_aug -> pad_sequence`` chain of the conformer input pipeline (examples/conformer/dataset.py:384-395,
+        456-534, 563-621) with one upload (the files' PCM payloads, 2 bytes / sample for PCM16) and one download (the
+        padded batch + mask).  ``files``: paths or binary file objects of mono WAV files
+        (:func:`mindaudio_b200.data.io.load_batch`).  Returns ``(xs_pad, xs_lengths, xs_masks)`` like
+        :meth:`features_padded`."""
+        from .data.io import load_batch
+        eng = self.eng
+        with eng.lock:
+            wb = load_batch(files, int16_scaled=True)
+            for sr in wb.sample_rates:
+                if sr != self.sample_rate:
+                    raise ValueError("features_from_wav: file sampled at %d Hz, pipeline built for %d Hz" % (sr, self.sample_rate))
+            return self._padded_from_device(wb.wave_dev, wb.dtype, wb.sample_offsets, max_len, padding_value, wb.wave_scale,
+                                            spec_aug_conf, rng)
+
+    def _padded_from_device(self, d_w, wave_dtype, so, max_len, padding_value, wave_scale, spec_aug_conf, rng):
+        """front-end + spec_aug + pad_sequence on a device-resident flat waveform batch (engine lock held)."""
+        eng = self.eng
+        n = len(so) - 1
         with eng.lock:
             b = eng.batch(self.plan, so)
             try:
                 xs_lengths = np.diff(b.frame_offsets).astype(np.int32)
                 if max_len is None:
-                    max_len = int(xs_lengths.max()) if len(lens) else 0
-                xs_pad = np.empty((len(lens), max_len, self.mel_bin), dtype=np.float32)
-                xs_masks = np.empty((len(lens), 1, max_len), dtype=np.float32)
+                    max_len = int(xs_lengths.max()) if n else 0
+                xs_pad = np.empty((n, max_len, self.mel_bin), dtype=np.float32)
+                xs_masks = np.empty((n, 1, max_len), dtype=np.float32)
                 if xs_pad.size:
-                    d_w = eng.buf("wave", max(flat.nbytes, 16))
                     d_f = eng.buf("out", max(b.total_frames * self.mel_bin * 4, 16))
                     d_p = eng.buf("pad", xs_pad.nbytes)
                     d_m = eng.buf("aux", xs_masks.nbytes)
-                    keep = eng.h2d(d_w, flat)
                     self.run(d_w.value if hasattr(d_w, "value") else d_w, b, d_f.value if hasattr(d_f, "value") else d_f,
-                             L.WAVE_I16 if dt == np.int16 else L.WAVE_F32, wave_scale)
+                             wave_dtype, wave_scale)
                     keep_r = None
                     if spec_aug_conf:
                         from .data.masking import spec_aug_rects
@@ -178,14 +205,14 @@ class FbankPipeline:
                         if len(rects):
                             d_r = eng.buf("rects", rects.nbytes)
                             keep_r = eng.h2d(d_r, rects)
-                            L.check(eng.lib.mafe_mask_rects(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), len(lens), self.mel_bin,
+                            L.check(eng.lib.mafe_mask_rects(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), n, self.mel_bin,
                                                             d_r, len(rects), 0.0))
-                    L.check(eng.lib.mafe_pad_sequence(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), len(lens), self.mel_bin,
+                    L.check(eng.lib.mafe_pad_sequence(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), n, self.mel_bin,
                                                       max_len, float(padding_value), 1, d_p, d_m))
                     eng.d2h(xs_pad, d_p)
                     eng.d2h(xs_masks, d_m)
                     eng.sync()
-                    del keep, keep_r
+                    del keep_r
                 return xs_pad, xs_lengths, xs_masks
             finally:
                 b.close()

@@ -784,3 +784,150 @@ def harmonic(y_input, **kwargs):
     y_input = np.asarray(y_input)
     return istft(hpss(stft(y_input, n_fft=2048, pad_mode="constant"), **kwargs)[0], length=y_input.shape[-1])
 
+
+
+# --------------------------------------------------------------------------
+# WAV decode ("next" row f3): mindaudio/data/io.py:347-747
+# --------------------------------------------------------------------------
+
+class WavWarning(UserWarning):
+    """stands for io.py:339 WavFileWarning"""
+
+
+def wav_read(raw, offset=0.0, duration=None, filelike=False):
+    """``mindaudio.data.io.read`` over the bytes of a file (io.py:552-747), returning ``(audio, samplerate, notes)``.
+
+    ``filelike`` selects the branch the reference takes for objects without a file descriptor (``np.fromfile`` raises
+    ``io.UnsupportedOperation`` -> ``read(size)``, io.py:500-503).  ``notes`` lists the warnings the reference would
+    emit ("unknown", "eof", "incomplete")."""
+    import struct
+    raw = bytes(raw)
+    pos = 0
+    notes = []
+
+    def take(k):                      # file.read(k)
+        nonlocal pos
+        out = raw[pos:pos + k] if pos < len(raw) else b""
+        pos += len(out)
+        return out
+
+    magic = take(4)                   # io.py:652-665
+    if magic == b"RIFF":
+        e = "<"
+    elif magic == b"RIFX":
+        e = ">"
+    else:
+        raise ValueError("File format %r not understood. Only 'RIFF' and 'RIFX' supported." % (magic,))
+    total = struct.unpack(e + "I", take(4))[0] + 8            # io.py:668-670
+    if take(4) != b"WAVE":
+        raise TypeError("exceptions must derive from BaseException")   # io.py:676 raises a str
+
+    def skip_chunk():                 # io.py:520-538
+        nonlocal pos
+        d = take(4)
+        if d:
+            size = struct.unpack(e + "I", d)[0]
+            pos += size + (size & 1)
+
+    fmt_seen = data_seen = False
+    audio = None
+    tag = channels = rate = align = depth = None
+    while pos < total:                # io.py:680-736
+        cid = take(4)
+        if not cid:
+            if data_seen:
+                notes.append("eof")
+                break
+            raise ValueError("Unexpected end of file.")
+        if len(cid) < 4:
+            if fmt_seen and data_seen:
+                notes.append("incomplete")
+            else:
+                raise ValueError("Incomplete chunk ID: %r" % (cid,))
+        if cid == b"fmt ":            # io.py:347-424
+            fmt_seen = True
+            csize = struct.unpack(e + "I", take(4))[0]
+            if csize < 16:
+                raise ValueError("Binary structure of wave file is not compliant")
+            tag, channels, rate, bps_sec, align, depth = struct.unpack(e + "HHIIHH", take(16))
+            used = 16
+            if tag == 0xFFFE and csize >= used + 2:
+                ext = struct.unpack(e + "H", take(2))[0]
+                used += 2
+                if ext < 22:
+                    raise ValueError("Binary structure of wave file is not compliant")
+                blob = take(22)
+                used += 22
+                guid = blob[6:22]
+                tail = (b"\x00\x00\x00\x10" if e == ">" else b"\x00\x00\x10\x00") + b"\x80\x00\x00\xAA\x00\x38\x9B\x71"
+                if guid.endswith(tail):
+                    tag = struct.unpack(e + "I", guid[:4])[0]
+            if tag not in (1, 3):
+                raise ValueError("Unknown wave file format: %#06x" % tag)
+            if csize > used:
+                take(csize - used)
+            pos += csize & 1
+            if tag == 1 and bps_sec != rate * align:
+                raise ValueError("WAV header is invalid: nAvgBytesPerSec must equal product of nSamplesPerSec and nBlockAlign")
+        elif cid == b"data":          # io.py:427-517
+            data_seen = True
+            if not fmt_seen:
+                raise ValueError("No fmt chunk before data")
+            size = struct.unpack(e + "I", take(4))[0]
+            width = align // channels
+            n_samples = size // width
+            if tag == 1:
+                if 1 <= depth <= 8:
+                    dt = "u1"
+                elif width in (3, 5, 6, 7):
+                    dt = "V1"
+                elif depth <= 64:
+                    dt = e + "i%d" % width
+                else:
+                    raise ValueError("Unsupported bit depth: the WAV file has %d-bit integer data." % depth)
+            else:
+                if depth not in (32, 64):
+                    raise ValueError("Unsupported bit depth: the WAV file has %d-bit floating-point data." % depth)
+                dt = e + "f%d" % width
+            skip = 0
+            if offset > 0:
+                skip = int(offset * rate)
+                take(skip)                                    # BYTES, not samples (io.py:489-491)
+            start = pos
+            item = np.dtype(dt).itemsize
+            if not filelike:
+                count = size if dt == "V1" else n_samples
+                if skip <= count:
+                    count -= skip
+                if duration and duration * rate < count:
+                    count = int(duration * rate)
+                got = min(count, max(0, len(raw) - start) // item)
+                data = np.frombuffer(raw, dtype=dt, count=got, offset=start) if got else np.zeros(0, dtype=dt)
+                pos = start + got * item
+            else:
+                data = np.frombuffer(take(size), dtype=dt)
+            if dt == "V1":                                    # io.py:505-512
+                wide = e + ("i4" if width == 3 else "i8")
+                nb = np.dtype(wide).itemsize
+                box = np.zeros((len(data) // width, nb), dtype="V1")
+                if e == ">":
+                    box[:, :width] = data.reshape((-1, width))
+                else:
+                    box[:, nb - width:] = data.reshape((-1, width))
+                data = box.view(wide).reshape(box.shape[:-1])
+            pos += size & 1
+            audio = np.array(data)
+            if channels > 1:
+                audio = audio.reshape(-1, channels)
+        elif cid in (b"fact", b"LIST", b"JUNK", b"Fake"):
+            skip_chunk()
+        else:
+            notes.append("unknown")
+            skip_chunk()
+    if audio is None:
+        raise UnboundLocalError("cannot access local variable 'audio' where it is not associated with a value")
+    if audio.dtype == "int32":        # io.py:741-746
+        audio = audio / 2147483648
+    elif audio.dtype == "int16":
+        audio = audio / 32768
+    return audio, rate, notes
