@@ -345,6 +345,16 @@ int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_s, double d
 int mafe_wav_decode(mafe_ctx* ctx, const void* payload_dev, int64_t n_items, int32_t sample_kind, int32_t big_endian,
                     int32_t out_dtype, double scale, void* out_dev);
 
+/* ---- Fourier-method resampling ("next" row f2: the `resample` step of augment.pitch_shift, mindaudio/data/augment.py:
+ * 874-901 -> processing.resample res_type "fft" / "scipy", mindaudio/data/processing.py:132-186 -> scipy.signal.resample) ---- */
+/* x_dev [rows][n_in] float64 -> out_dev [rows][n_out] float64 = irfft(rfft(x)[: m/2 + 1] (unpaired bin at m/2 doubled
+ * when shrinking, halved when growing; m = min(n_in, n_out)), n_out) * n_out / n_in.  Lengths are arbitrary: both DFTs
+ * run as Bluestein chirp-z transforms over a power-of-two FFT in complex128.  work_dev: scratch of at least
+ * mafe_resample_workspace(...) bytes (256-byte aligned). */
+int mafe_resample_workspace(int32_t rows, int64_t n_in, int64_t n_out, size_t* bytes);
+int mafe_resample_fft(mafe_ctx* ctx, const double* x_dev, int32_t rows, int64_t n_in, int64_t n_out, double* out_dev,
+                      void* work_dev, size_t work_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmafe.so")
-SOURCES = ["api.cu", "generic.cu", "fbank512.cu", "ops.cu", "istft.cu", "wav.cu"]
+SOURCES = ["api.cu", "generic.cu", "fbank512.cu", "ops.cu", "istft.cu", "wav.cu", "resample.cu"]
 HEADERS = [os.path.join("..", "..", "include", "mafe.h")]   # + every *.cuh / *.inc next to the sources (see _digest)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

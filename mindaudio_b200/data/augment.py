@@ -15,9 +15,10 @@ from .. import _lib as L
 from .. import _tables as T
 from .._engine import get_engine
 from .masking import frequencymasking, timemasking  # noqa: F401
+from .processing import resample
 from .spectrum import _dense_offsets, _flatten_batch, _pad_shape
 
-__all__ = ["time_stretch", "_phase_vocoder", "frequencymasking", "timemasking"]
+__all__ = ["time_stretch", "pitch_shift", "_phase_vocoder", "frequencymasking", "timemasking"]
 
 
 def _vocoder_tables(n_frames, n_bins, rate, hop_length):
@@ -97,3 +98,13 @@ def time_stretch(waveforms, rate=None):
                 b.close()
     y = y64.reshape(lead + (y64.shape[-1],))
     return _pad_shape(y[..., n_fft // 2:], data_shape=length_stretch)
+
+
+def pitch_shift(waveforms, sr, n_steps, bins_per_octave=12):
+    """``augment.py:874-901``: ``time_stretch`` by ``2 ** (-n_steps / bins_per_octave)``, then Fourier resampling from
+    ``sr / rate`` back to ``sr`` (``processing.resample``), then crop / zero-pad to the length of the STRETCHED signal
+    (the reference passes ``waveforms_stretch.shape[-1]`` to ``_pad_shape``, not the input length)."""
+    rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+    stretched = time_stretch(waveforms, rate=rate)
+    y_shift = resample(stretched, orig_freq=float(sr) / rate, new_freq=sr)
+    return _pad_shape(y_shift, data_shape=stretched.shape[-1])

@@ -161,5 +161,21 @@ def load_phase_vocoder():
     return _cache["pvoc"]
 
 
+def load_pitch_shift():
+    """``time_stretch`` / ``_phase_vocoder`` / ``pitch_shift`` (mindaudio/data/augment.py:795-901) and ``resample``
+    (mindaudio/data/processing.py:132-186), as written, wired to the reference's own ``stft`` / ``istft`` / ``_pad_shape``."""
+    if "pitch" not in _cache:
+        import scipy
+        import scipy.signal
+        _, sp, _ = load_data_modules()
+        gr = _extract_functions(os.path.join(REF_ROOT, "mindaudio", "data", "processing.py"), ["resample"],
+                                {"scipy": scipy})
+        g = _extract_functions(os.path.join(REF_ROOT, "mindaudio", "data", "augment.py"),
+                               ["time_stretch", "_phase_vocoder", "pitch_shift"],
+                               {"stft": sp.stft, "istft": sp.istft, "_pad_shape": sp._pad_shape, "resample": gr["resample"]})
+        _cache["pitch"] = types.SimpleNamespace(resample=gr["resample"], pitch_shift=g["pitch_shift"], time_stretch=g["time_stretch"])
+    return _cache["pitch"]
+
+
 def sample_wav(name="BAC009S0002W0122.wav"):
     return os.path.join(REF_ROOT, "tests", "samples", "ASR", name)

@@ -931,3 +931,37 @@ def wav_read(raw, offset=0.0, duration=None, filelike=False):
     elif audio.dtype == "int16":
         audio = audio / 32768
     return audio, rate, notes
+
+
+# --------------------------------------------------------------------------
+# pitch shift ("next" row f2): mindaudio/data/augment.py:874-901, processing.py:132-186
+# --------------------------------------------------------------------------
+
+def resample(waveform, orig_freq=16000, new_freq=16000, res_type="fft"):
+    """``processing.py:132-186``, "fft" / "scipy" branch: the reference hands the work to ``scipy.signal.resample``
+    (third-party, ``requirements.txt``), and so does the oracle -- same call, same arguments."""
+    import scipy.signal
+    if orig_freq == new_freq:
+        return waveform
+    assert res_type in ("scipy", "fft")
+    ratio = float(new_freq) / orig_freq
+    n_samples = int(np.ceil(waveform.shape[-1] * ratio))
+    return np.asarray(scipy.signal.resample(waveform, n_samples, axis=-1), dtype=waveform.dtype)
+
+
+def pad_shape(y_shift, data_shape):
+    """``spectrum.py:307-320``: crop or zero-pad the last axis to ``data_shape`` samples."""
+    n = y_shift.shape[-1]
+    if n > data_shape:
+        return y_shift[..., :data_shape]
+    if n < data_shape:
+        return np.pad(y_shift, [(0, 0)] * (y_shift.ndim - 1) + [(0, data_shape - n)], mode="constant")
+    return y_shift
+
+
+def pitch_shift(waveforms, sr, n_steps, bins_per_octave=12):
+    """``augment.py:874-901``."""
+    rate = 2.0 ** (-float(n_steps) / bins_per_octave)
+    stretched = time_stretch(waveforms, rate)
+    y = resample(stretched, orig_freq=float(sr) / rate, new_freq=sr)
+    return pad_shape(y, stretched.shape[-1])

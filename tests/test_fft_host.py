@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-@pytest.mark.parametrize("name", ["fft512_host_check", "fft400_host_check", "fft320_host_check"])
+@pytest.mark.parametrize("name", ["fft512_host_check", "fft400_host_check", "fft320_host_check", "resample_host_check"])
 def test_fft_maps_on_host(name, tmp_path):
     if not os.path.exists(NVCC):
         pytest.skip("nvcc not available")

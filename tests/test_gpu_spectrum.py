@@ -222,3 +222,31 @@ def test_phase_vocoder_and_time_stretch(ma):
     with pytest.raises(ValueError):
         ma.time_stretch(x, 0.0)
 
+
+
+def test_resample_and_pitch_shift(ma):
+    """Scope row f2: processing.resample (Fourier method, arbitrary lengths through Bluestein in complex128) against
+    scipy.signal.resample as the reference calls it, and augment.pitch_shift = time_stretch -> resample -> crop / pad."""
+    rng = np.random.default_rng(23)
+    cases = [(997, 16000, 8000), (4001, 16000, 22050), (6000, 12700.3, 16000), (4096, 16000, 8000), (5000, 8000, 16000),
+             (1, 16000, 48000), (3001, 44100, 16000), (250001, 16000, 15999)]
+    for n, orig, new in cases:
+        x = rng.standard_normal((2, n)) if n < 100000 else rng.standard_normal(n)
+        out, ref = ma.resample(x, orig, new), R.resample(x, orig, new)
+        assert out.shape == ref.shape and out.dtype == ref.dtype == np.float64
+        assert np.max(np.abs(out - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref))), (n, orig, new)
+    x32 = synth(29, (3, 2, 7000))
+    out, ref = ma.resample(x32, 16000, 11025), R.resample(x32, 16000, 11025)      # scipy works in float32 for float32 input
+    assert out.shape == ref.shape == (3, 2, 4824) and out.dtype == ref.dtype == np.float32
+    assert np.max(np.abs(out - ref)) <= 1e-5 * np.max(np.abs(ref))
+    assert ma.resample(x32, 16000, 16000) is x32
+    with pytest.raises(NotImplementedError):
+        ma.resample(x32, 16000, 8000, res_type="minddata")
+
+    x = synth(13, (2, 6000))
+    for n_steps in (4, -3, 0.5):
+        y, yr = ma.pitch_shift(x, 16000, n_steps), R.pitch_shift(x, 16000, n_steps)
+        assert y.shape == yr.shape and y.dtype == yr.dtype
+        assert np.max(np.abs(y - yr)) <= 3e-3 * np.max(np.abs(yr)), n_steps     # the phase vocoder's tolerance (see above)
+    y1 = ma.pitch_shift(x[0].astype(np.float64), 16000, 2, bins_per_octave=24)
+    assert y1.shape == R.pitch_shift(x[0].astype(np.float64), 16000, 2, bins_per_octave=24).shape

@@ -115,3 +115,21 @@ def test_hpss_matches_reference(ref):
     # the reference's istft runs numpy >= 2's single-precision irfft on complex64 here; the oracle transforms in float64
     assert ya.shape == yb.shape and np.max(np.abs(ya - yb)) <= 1e-6 * max(1.0, np.max(np.abs(ya)))
 
+
+
+def test_pitch_shift_matches_reference(ref):
+    """Restated resample / pitch_shift == the reference's own functions (both call scipy.signal.resample), including the
+    crop / pad to the STRETCHED length (augment.py:901)."""
+    ps = ref_loader.load_pitch_shift()
+    from tests.util import synth
+    x = synth(19, (2, 5000)).astype(np.float64)
+    for orig, new in ((16000, 8000), (16000, 22050), (12700.3, 16000), (16000, 16000)):
+        a, b = ps.resample(x, orig, new), R.resample(x, orig, new)
+        assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b)
+    a32 = ps.resample(x.astype(np.float32), 16000, 11025)
+    assert a32.dtype == np.float32 and np.array_equal(a32, R.resample(x.astype(np.float32), 16000, 11025))
+    for n_steps in (4, -3, 0.5):
+        a, b = ps.pitch_shift(x, 16000, n_steps), R.pitch_shift(x, 16000, n_steps)
+        assert a.shape == b.shape and a.dtype == b.dtype
+        assert np.max(np.abs(a - b)) <= 1e-6 * max(1.0, np.max(np.abs(a)))
+        assert a.shape[-1] == int(round(x.shape[-1] / 2.0 ** (-n_steps / 12)))
