@@ -315,7 +315,8 @@ enum {  /* mafe_wav_info.warnings: the reference's WavFileWarning cases */
   MAFE_WAV_WARN_INCOMPLETE_ID = 4   /* "Incomplete chunk ID ... ignoring it." (io.py:697-700) */
 };
 enum {  /* mafe_wav_info.error_kind when mafe_wav_parse fails: the exception class the reference raises */
-  MAFE_WAV_ERR_VALUE = 1, MAFE_WAV_ERR_TYPE = 2, MAFE_WAV_ERR_UNBOUND = 3, MAFE_WAV_ERR_ZERODIV = 4
+  MAFE_WAV_ERR_VALUE = 1, MAFE_WAV_ERR_TYPE = 2, MAFE_WAV_ERR_UNBOUND = 3, MAFE_WAV_ERR_ZERODIV = 4,
+  MAFE_WAV_ERR_STRUCT = 5   /* struct.error: a size / header field cut short by the end of the file */
 };
 typedef struct mafe_wav_info {
   int32_t format_tag;        /* 1 PCM, 3 IEEE float (WAVE_FORMAT_EXTENSIBLE resolved through its GUID, io.py:364-382) */

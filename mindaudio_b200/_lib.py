@@ -113,7 +113,7 @@ class WavInfo(C.Structure):
 WAV_U8, WAV_I8, WAV_I16, WAV_I24, WAV_I32, WAV_I40, WAV_I48, WAV_I56, WAV_I64, WAV_F32, WAV_F64 = range(1, 12)
 WAV_OUT_F32, WAV_OUT_F64, WAV_OUT_I16 = 0, 1, 2
 WAV_WARN_UNKNOWN_CHUNK, WAV_WARN_EOF, WAV_WARN_INCOMPLETE_ID = 1, 2, 4
-WAV_ERR_VALUE, WAV_ERR_TYPE, WAV_ERR_UNBOUND, WAV_ERR_ZERODIV = 1, 2, 3, 4
+WAV_ERR_VALUE, WAV_ERR_TYPE, WAV_ERR_UNBOUND, WAV_ERR_ZERODIV, WAV_ERR_STRUCT = 1, 2, 3, 4, 5
 
 _lib = None
 

@@ -34,14 +34,16 @@ int fail(mafe_wav_info* info, int kind) { info->error_kind = kind; return MAFE_E
 
 const char* kSupported = "PCM, IEEE_FLOAT";
 
-// io.py:520-538
-void skip_unknown_chunk(ByteFile& f, bool be) {
+// io.py:520-538; false = the size field is cut short (struct.error in the reference)
+bool skip_unknown_chunk(ByteFile& f, bool be) {
   uint8_t b[4];
-  if (f.read(b, 4) == 4) {     // struct.unpack on a short read raises in the reference; a short size field ends the file anyway
-    uint32_t size = rd_u32(b, be);
-    f.seek_rel(size);
-    if (size & 1) f.seek_rel(1);
-  }
+  const int64_t got = f.read(b, 4);
+  if (got == 0) return true;                     // `if data:` -- nothing left, nothing to skip
+  if (got < 4) return false;
+  const uint32_t size = rd_u32(b, be);
+  f.seek_rel(size);
+  if (size & 1) f.seek_rel(1);
+  return true;
 }
 
 }  // namespace
@@ -67,7 +69,7 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
     return fail(info, MAFE_WAV_ERR_VALUE);
   }
   info->big_endian = be;
-  if (f.read(b, 4) != 4) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_VALUE); }
+  if (f.read(b, 4) != 4) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
   const int64_t file_size = (int64_t)rd_u32(b, be) + 8;
   got = f.read(b, 4);
   if (!(got == 4 && memcmp(b, "WAVE", 4) == 0)) {
@@ -93,11 +95,11 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
     if (got == 4 && memcmp(id, "fmt ", 4) == 0) {
       // ---- io.py:347-424
       have_fmt = true;
-      if (f.read(b, 4) != 4) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_VALUE); }
+      if (f.read(b, 4) != 4) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
       const uint32_t chunk_size = rd_u32(b, be);
       if (chunk_size < 16) { set_error("Binary structure of wave file is not compliant"); return fail(info, MAFE_WAV_ERR_VALUE); }
       int64_t bytes_read = 16;
-      if (f.read(b, 16) != 16) { set_error("unpack requires a buffer of 16 bytes"); return fail(info, MAFE_WAV_ERR_VALUE); }
+      if (f.read(b, 16) != 16) { set_error("unpack requires a buffer of 16 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
       uint32_t format_tag = rd_u16(b, be);
       info->channels = rd_u16(b + 2, be);
       info->sample_rate = (int32_t)rd_u32(b + 4, be);
@@ -105,7 +107,7 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
       info->block_align = rd_u16(b + 12, be);
       info->bit_depth = rd_u16(b + 14, be);
       if (format_tag == 0xFFFE && chunk_size >= (uint32_t)(bytes_read + 2)) {
-        if (f.read(b, 2) != 2) { set_error("unpack requires a buffer of 2 bytes"); return fail(info, MAFE_WAV_ERR_VALUE); }
+        if (f.read(b, 2) != 2) { set_error("unpack requires a buffer of 2 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
         const uint16_t ext = rd_u16(b, be);
         bytes_read += 2;
         if (ext >= 22) {
@@ -137,7 +139,7 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
       // ---- io.py:427-517
       have_data = true;
       if (!have_fmt) { set_error("No fmt chunk before data"); return fail(info, MAFE_WAV_ERR_VALUE); }
-      if (f.read(b, 4) != 4) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_VALUE); }
+      if (f.read(b, 4) != 4) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
       const int64_t size = rd_u32(b, be);
       if (info->channels == 0) { set_error("integer division or modulo by zero"); return fail(info, MAFE_WAV_ERR_ZERODIV); }
       const int bps = info->block_align / info->channels;
@@ -172,7 +174,8 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
       info->data_chunk_bytes = size;
       int64_t ignore = 0;
       if (offset_s > 0) {
-        ignore = (int64_t)(offset_s * (double)(uint32_t)info->sample_rate);   // int() truncates
+        const double want = offset_s * (double)(uint32_t)info->sample_rate;
+        ignore = want < 4.0e18 ? (int64_t)want : (int64_t)4000000000000000000LL;   // int() truncates; beyond any file anyway
         f.skip_read(ignore);                                                  // the reference reads `ignore` BYTES
       }
       const int64_t start = f.pos;
@@ -211,10 +214,10 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
       }
     } else if (got == 4 && (memcmp(id, "fact", 4) == 0 || memcmp(id, "LIST", 4) == 0 || memcmp(id, "JUNK", 4) == 0 ||
                             memcmp(id, "Fake", 4) == 0)) {
-      skip_unknown_chunk(f, be);
+      if (!skip_unknown_chunk(f, be)) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
     } else {
       info->warnings |= MAFE_WAV_WARN_UNKNOWN_CHUNK;
-      skip_unknown_chunk(f, be);
+      if (!skip_unknown_chunk(f, be)) { set_error("unpack requires a buffer of 4 bytes"); return fail(info, MAFE_WAV_ERR_STRUCT); }
     }
   }
   if (!have_data) {

@@ -13,6 +13,7 @@ dtype view of the file's bytes exactly as the reference returns them (no arithme
 from __future__ import annotations
 
 import ctypes as C
+import struct
 import warnings
 
 import numpy as np
@@ -28,7 +29,7 @@ class WavFileWarning(UserWarning):
 
 
 _ERRORS = {L.WAV_ERR_VALUE: ValueError, L.WAV_ERR_TYPE: TypeError, L.WAV_ERR_UNBOUND: UnboundLocalError,
-           L.WAV_ERR_ZERODIV: ZeroDivisionError}
+           L.WAV_ERR_ZERODIV: ZeroDivisionError, L.WAV_ERR_STRUCT: struct.error}
 _DTYPES = {L.WAV_U8: "u1", L.WAV_I8: "i1", L.WAV_I16: "i2", L.WAV_I32: "i4", L.WAV_I64: "i8", L.WAV_F32: "f4", L.WAV_F64: "f8"}
 
 
