@@ -21,7 +21,7 @@ import numpy as np
 from .. import _lib as L
 from .._engine import get_engine
 
-__all__ = ["read", "wav_info", "WavFileWarning", "load_batch", "WavBatch"]
+__all__ = ["read", "wav_info", "WavFileWarning", "load_batch", "WavBatch", "resampled_length"]
 
 
 class WavFileWarning(UserWarning):
@@ -136,13 +136,24 @@ class WavBatch:
         return np.diff(self.sample_offsets)
 
 
-def load_batch(files, int16_scaled=True, buffer_name="wavbatch"):
+def resampled_length(n_in, orig_freq, new_freq):
+    """Output length of ``processing.resample`` (processing.py:170-172), with its float arithmetic."""
+    ratio = float(new_freq) / orig_freq
+    return int(np.ceil(n_in * ratio))
+
+
+def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
     """Decode mono WAV files straight into one device-resident waveform batch (no host-side float pass).
 
     ``int16_scaled=True`` produces what the conformer pipeline feeds its front-end, ``read(path) * (1 << 15)``
     (examples/conformer/dataset.py:389-390): PCM16 files are uploaded as they are (2 bytes / sample) and consumed by
     the front-end's int16 input path; every other format is decoded on the device to float32 with the factor folded
     into the decode.  ``int16_scaled=False`` gives ``read(path)`` as float32.
+
+    ``speeds``: optional per-file speed factors -- the conformer pipeline's speed perturbation
+    (examples/conformer/dataset.py:391-404: ``resample(waveform, sample_rate * speed, sample_rate)`` for
+    ``speed != 1.0``, the Fourier method of ``processing.resample``), run on the device in float64 between the
+    decode and the float32 batch; the caller draws the factors (the reference: ``random.choice([0.9, 1.0, 1.1])``).
 
     Returns a :class:`WavBatch`; its device buffer belongs to the engine (name ``buffer_name``) and stays valid until
     the next ``load_batch`` with the same name."""
@@ -157,17 +168,37 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch"):
         raws.append(np.frombuffer(raw, dtype=np.uint8))
         infos.append(info)
     n = len(infos)
+    rates = [int(np.uint32(i.sample_rate)) for i in infos]
+    if speeds is None:
+        speeds = [1.0] * n
+    speeds = [float(v) for v in speeds]
+    if len(speeds) != n:
+        raise ValueError("load_batch: %d speed factors for %d files" % (len(speeds), n))
+    if any(v <= 0 for v in speeds):
+        raise ValueError("load_batch: speed factors must be positive")
+    n_in = [int(i.n_items) for i in infos]
+    n_out = [m if v == 1.0 or m == 0 else resampled_length(m, rates[k] * v, rates[k]) for k, (m, v) in enumerate(zip(n_in, speeds))]
     so = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum([int(i.n_items) for i in infos], out=so[1:])
+    np.cumsum(n_out, out=so[1:])
     total = int(so[-1])
     scale = 32768.0 if int16_scaled else 1.0
-    all_pcm16 = int16_scaled and n > 0 and all(i.sample_kind == L.WAV_I16 and not i.big_endian for i in infos)
+    perturbed = [v != 1.0 and m > 0 for v, m in zip(speeds, n_in)]
+    all_pcm16 = (int16_scaled and n > 0 and not any(perturbed)
+                 and all(i.sample_kind == L.WAV_I16 and not i.big_endian for i in infos))
     eng = get_engine()
     item_out = 2 if all_pcm16 else 4
+
+    def factor(i):
+        # read() leaves RIFX integer PCM unscaled (io.py:741-746 never matches a big-endian dtype)
+        undo = 1.0
+        if i.big_endian:
+            undo = {L.WAV_I16: 32768.0, L.WAV_I24: 2147483648.0, L.WAV_I32: 2147483648.0}.get(i.sample_kind, 1.0)
+        return scale * undo
+
     with eng.lock:
         d_wave = eng.buf(buffer_name, max(total * item_out, 16))
         # one staging buffer for all payloads (a single H2D), decoded per run of files sharing a format
-        sizes = [int(i.n_items) * L_BYTES[i.sample_kind] for i in infos]
+        sizes = [m * L_BYTES[i.sample_kind] for m, i in zip(n_in, infos)]
         bo = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(sizes, out=bo[1:])
         stage = np.empty(max(int(bo[-1]), 1), dtype=np.uint8)
@@ -180,23 +211,32 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch"):
             keep = eng.h2d(d_stage, stage)
             k = 0
             while k < n:
+                src = C.c_void_p(d_stage.value + int(bo[k]))
+                dst = C.c_void_p(d_wave.value + int(so[k]) * item_out)
+                if perturbed[k]:
+                    # decode -> float64, Fourier resampling in float64 (mafe_resample_fft), -> float32 into the batch
+                    need = C.c_size_t()
+                    L.check(eng.lib.mafe_resample_workspace(1, n_in[k], n_out[k], C.byref(need)))
+                    d_x, d_y = eng.buf("rs_in", n_in[k] * 8), eng.buf("rs_out", n_out[k] * 8)
+                    d_w = eng.buf("work", need.value)
+                    L.check(eng.lib.mafe_wav_decode(eng.ctx, src, n_in[k], infos[k].sample_kind, infos[k].big_endian,
+                                                    L.WAV_OUT_F64, factor(infos[k]), d_x))
+                    L.check(eng.lib.mafe_resample_fft(eng.ctx, d_x, 1, n_in[k], n_out[k], d_y, d_w, need.value))
+                    L.check(eng.lib.mafe_wav_decode(eng.ctx, d_y, n_out[k], L.WAV_F64, 0, L.WAV_OUT_F32, 1.0, dst))
+                    k += 1
+                    continue
                 j = k
-                while j + 1 < n and (infos[j + 1].sample_kind, infos[j + 1].big_endian) == (infos[k].sample_kind, infos[k].big_endian):
+                while (j + 1 < n and not perturbed[j + 1]
+                       and (infos[j + 1].sample_kind, infos[j + 1].big_endian) == (infos[k].sample_kind, infos[k].big_endian)):
                     j += 1
                 items = int(so[j + 1] - so[k])
                 if items:
-                    # read() leaves RIFX integer PCM unscaled (io.py:741-746 never matches a big-endian dtype)
-                    undo = 1.0
-                    if infos[k].big_endian:
-                        undo = {L.WAV_I16: 32768.0, L.WAV_I24: 2147483648.0, L.WAV_I32: 2147483648.0}.get(infos[k].sample_kind, 1.0)
-                    L.check(eng.lib.mafe_wav_decode(
-                        eng.ctx, C.c_void_p(d_stage.value + int(bo[k])), items, infos[k].sample_kind, infos[k].big_endian,
-                        L.WAV_OUT_F32, scale * undo,
-                        C.c_void_p(d_wave.value + int(so[k]) * item_out)))
+                    L.check(eng.lib.mafe_wav_decode(eng.ctx, src, items, infos[k].sample_kind, infos[k].big_endian,
+                                                    L.WAV_OUT_F32, factor(infos[k]), dst))
                 k = j + 1
         eng.sync()
         del keep
-    return WavBatch(d_wave, L.WAVE_I16 if all_pcm16 else L.WAVE_F32, so, [int(np.uint32(i.sample_rate)) for i in infos], 1.0)
+    return WavBatch(d_wave, L.WAVE_I16 if all_pcm16 else L.WAVE_F32, so, rates, 1.0)
 
 
 L_BYTES = {L.WAV_U8: 1, L.WAV_I8: 1, L.WAV_I16: 2, L.WAV_I24: 3, L.WAV_I32: 4, L.WAV_F32: 4, L.WAV_F64: 8}

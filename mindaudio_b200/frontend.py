@@ -163,17 +163,18 @@ class FbankPipeline:
             del keep
         return res
 
-    def features_from_wav(self, files, max_len=None, padding_value=0.0, spec_aug_conf=None, rng=None):
+    def features_from_wav(self, files, max_len=None, padding_value=0.0, spec_aug_conf=None, rng=None, speeds=None):
         """WAV files -> padded feature batch, the whole ``read -> * (1 << 15) -> compute_fbank_feats -> CMVN ->
         spec_aug -> pad_sequence`` chain of the conformer input pipeline (examples/conformer/dataset.py:384-395,
         456-534, 563-621) with one upload (the files' PCM payloads, 2 bytes / sample for PCM16) and one download (the
         padded batch + mask).  ``files``: paths or binary file objects of mono WAV files
-        (:func:`mindaudio_b200.data.io.load_batch`).  Returns ``(xs_pad, xs_lengths, xs_masks)`` like
+        (:func:`mindaudio_b200.data.io.load_batch`); ``speeds``: optional per-file speed-perturbation factors
+        (dataset.py:391-404, Fourier resampling on the device).  Returns ``(xs_pad, xs_lengths, xs_masks)`` like
         :meth:`features_padded`."""
         from .data.io import load_batch
         eng = self.eng
         with eng.lock:
-            wb = load_batch(files, int16_scaled=True)
+            wb = load_batch(files, int16_scaled=True, speeds=speeds)
             for sr in wb.sample_rates:
                 if sr != self.sample_rate:
                     raise ValueError("features_from_wav: file sampled at %d Hz, pipeline built for %d Hz" % (sr, self.sample_rate))

@@ -166,3 +166,33 @@ def test_wav_files_to_padded_batch(ma):
     for i, f in enumerate(feats):
         if f.shape[0] > 1:                                 # one frame: std = 0, no eps in the reference (a11)
             assert mixed_err(c_pad[i, :f.shape[0]], f) <= 1e-3, i
+
+
+def test_speed_perturbed_wav_batch(ma):
+    """dataset.py:384-404: read() * (1 << 15) -> resample(waveform, sample_rate * speed, sample_rate) for speed != 1
+    -> compute_fbank_feats, the resampling done on the device between the PCM decode and the front-end."""
+    from mindaudio_b200.data import io as P
+    lens, speeds = [16000, 9000, 5361, 12001], [0.9, 1.0, 1.1, 1.1]
+    pcm = [np.round(synth(40 + i, (n,)) * 32768).clip(-32768, 32767).astype(np.int16) for i, n in enumerate(lens)]
+    blobs = [W.make_wav(p) for p in pcm]
+    feats, waves = [], []
+    for b, v in zip(blobs, speeds):
+        audio, sr, _ = R.wav_read(b)
+        w = audio * (1 << 15)
+        if v != 1.0:
+            w = R.resample(w, sr * v, sr)
+        waves.append(w)
+        feats.append(R.conformer_fbank(w).astype(np.float32))
+    wb = P.load_batch([io.BytesIO(b) for b in blobs], speeds=speeds)
+    assert list(wb.lengths) == [len(w) for w in waves] and wb.dtype == 0 + __import__("mindaudio_b200")._lib.WAVE_F32
+    pipe = ma.FbankPipeline(cmvn=None)
+    xs_pad, xs_len, xs_mask = pipe.features_from_wav([io.BytesIO(b) for b in blobs], speeds=speeds)
+    assert list(xs_len) == [f.shape[0] for f in feats]
+    for i, f in enumerate(feats):
+        assert logmel_err(xs_pad[i, :f.shape[0]], f.astype(np.float64)) <= 1.0, i
+    # no perturbation drawn: the int16 path, identical to the un-perturbed call
+    a = pipe.features_from_wav([io.BytesIO(b) for b in blobs], speeds=[1.0] * 4)
+    b = pipe.features_from_wav([io.BytesIO(b) for b in blobs])
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    with pytest.raises(ValueError):
+        pipe.features_from_wav([io.BytesIO(blobs[0])], speeds=[0.9, 1.1])
