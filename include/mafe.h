@@ -339,6 +339,14 @@ typedef struct mafe_wav_info {
  * duration)` does (duration_s = 0 stands for None).  filelike != 0 selects the reference's path for file objects
  * without a C-level descriptor (io.BytesIO: read(size) of the whole chunk, `duration` ignored, io.py:500-503). */
 int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_s, double duration_s, int32_t filelike, mafe_wav_info* info);
+/* Host only: walk n_files containers (blobs[k], blob_bytes[k]: the files' contents; path-like semantics, offset 0,
+ * no duration) on n_threads host threads (<= 0: up to 16), fill infos[n_files] and the prefix sums of the payload sizes
+ * payload_offsets[n_files + 1]; when stage != NULL also pack the payloads back to back into it (a pinned buffer of the
+ * caller; stage_bytes >= payload_offsets[n_files]), so that one copy moves the whole batch to the device.  On a
+ * malformed file: returns MAFE_E_INVALID_ARG, *failed_index = the first such file, infos[*failed_index].error_kind and
+ * mafe_last_error() describe it. */
+int mafe_wav_stage(const void* const* blobs, const int64_t* blob_bytes, int32_t n_files, int32_t n_threads,
+                   mafe_wav_info* infos, int64_t* payload_offsets, void* stage, int64_t stage_bytes, int32_t* failed_index);
 /* Device: n_items items of kind sample_kind at payload_dev (byte pointer, any alignment) -> out_dev as float32 / float64
  * in `read`'s unified output format (int16 / 32768, int32 and 24-bit / 2^31, everything else unchanged; io.py:741-746)
  * times `scale` (the conformer pipeline's `* (1 << 15)`, examples/conformer/dataset.py:389-390), or as raw int16 in

@@ -45,6 +45,7 @@ class Engine:
         self.lock = threading.RLock()
         self._plans = {}
         self._bufs = {}
+        self._pinned = {}
 
     # ---- plumbing ----
     def sync(self):
@@ -92,6 +93,24 @@ class Engine:
         L.check(self.lib.mafe_device_malloc(self.ctx, cap, C.byref(p)))
         self._bufs[name] = (p, cap)
         return p
+
+    def pinned(self, name, nbytes):
+        """Grow-only named pinned host buffer (``(address, capacity)``): staging for asynchronous copies."""
+        cur = self._pinned.get(name)
+        if cur is not None and cur[1] >= nbytes:
+            return cur
+        if cur is not None:
+            L.check(self.lib.mafe_pinned_free(self.ctx, cur[0]))
+            del self._pinned[name]
+        p = C.c_void_p()
+        cap = max(int(nbytes * 1.25), 1 << 16)
+        L.check(self.lib.mafe_pinned_malloc(self.ctx, cap, C.byref(p)))
+        self._pinned[name] = (p, cap)
+        return self._pinned[name]
+
+    def h2d_raw(self, dev, host_ptr, nbytes):
+        """Asynchronous copy from a raw host address (pinned memory keeps it asynchronous)."""
+        L.check(self.lib.mafe_memcpy_h2d(self.ctx, dev, host_ptr, int(nbytes)))
 
     def h2d(self, dev, arr):
         arr = np.ascontiguousarray(arr)

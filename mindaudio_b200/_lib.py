@@ -96,6 +96,7 @@ _PROTOS = {
     "mafe_median_filter": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32]),
     "mafe_hpss_masks": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _I32, _P, _P]),
     "mafe_wav_parse": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, _I32, _P]),
+    "mafe_wav_stage": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, C.c_int64, C.POINTER(_I32)]),
     "mafe_wav_decode": (C.c_int, [_P, _P, C.c_int64, _I32, _I32, _I32, C.c_double, _P]),
     "mafe_resample_workspace": (C.c_int, [_I32, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
     "mafe_resample_fft": (C.c_int, [_P, _P, _I32, C.c_int64, C.c_int64, _P, _P, C.c_size_t]),

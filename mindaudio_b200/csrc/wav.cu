@@ -7,6 +7,9 @@
 
 #include <string.h>
 
+#include <atomic>
+#include <thread>
+
 namespace mafe {
 namespace {
 
@@ -223,6 +226,80 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
   if (!have_data) {
     set_error("cannot access local variable 'audio' where it is not associated with a value");
     return fail(info, MAFE_WAV_ERR_UNBOUND);
+  }
+  return MAFE_OK;
+}
+
+// ---- batch staging: many files -> one contiguous payload buffer (pinned by the caller), parsed and copied by a few
+// host threads.  This is the host half of load_batch: Python hands over the file contents, the library finds the
+// payloads and packs them so that one cudaMemcpyAsync moves the whole batch.
+namespace mafe {
+namespace {
+inline int64_t payload_bytes(const mafe_wav_info& i) {
+  static const int kItem[] = {0, 1, 1, 2, 3, 4, 5, 6, 7, 8, 4, 8};
+  return i.n_items * kItem[i.sample_kind];
+}
+}  // namespace
+}  // namespace mafe
+
+extern "C" int mafe_wav_stage(const void* const* blobs, const int64_t* blob_bytes, int32_t n_files, int32_t n_threads,
+                              mafe_wav_info* infos, int64_t* payload_offsets, void* stage, int64_t stage_bytes,
+                              int32_t* failed_index) {
+  MAFE_REQUIRE(n_files >= 0, "mafe_wav_stage: negative file count");
+  MAFE_REQUIRE(n_files == 0 || (blobs && blob_bytes && infos), "mafe_wav_stage: NULL argument");
+  MAFE_REQUIRE(payload_offsets != nullptr, "mafe_wav_stage: payload_offsets is NULL");
+  if (failed_index) *failed_index = -1;
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw < 1) hw = 1;
+  int nt = n_threads > 0 ? n_threads : (hw < 16 ? hw : 16);
+  if (nt > n_files) nt = n_files > 0 ? n_files : 1;
+
+  // pass 1: walk every container
+  std::atomic<int32_t> next{0}, first_bad{INT32_MAX};
+  std::vector<std::string> msgs((size_t)nt);
+  std::vector<int32_t> bad_of((size_t)nt, INT32_MAX);
+  auto walk = [&](int t) {
+    for (;;) {
+      const int32_t k = next.fetch_add(1);
+      if (k >= n_files) break;
+      const int rc = mafe_wav_parse(blobs[k], blob_bytes[k], 0.0, 0.0, 0, &infos[k]);
+      if (rc != MAFE_OK && k < bad_of[(size_t)t]) { bad_of[(size_t)t] = k; msgs[(size_t)t] = mafe_last_error(); }
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(walk, t);
+    walk(0);
+    for (auto& th : pool) th.join();
+  }
+  int32_t bad = INT32_MAX, bad_t = -1;
+  for (int t = 0; t < nt; ++t) if (bad_of[(size_t)t] < bad) { bad = bad_of[(size_t)t]; bad_t = t; }
+  if (bad_t >= 0) {   // the first failing file, with the exception class of the reference in infos[bad].error_kind
+    if (failed_index) *failed_index = bad;
+    set_error("%s", msgs[(size_t)bad_t].c_str());
+    return MAFE_E_INVALID_ARG;
+  }
+  payload_offsets[0] = 0;
+  for (int32_t k = 0; k < n_files; ++k) payload_offsets[k + 1] = payload_offsets[k] + payload_bytes(infos[k]);
+  if (!stage) return MAFE_OK;
+  MAFE_REQUIRE(stage_bytes >= payload_offsets[n_files], "mafe_wav_stage: staging buffer of %lld bytes, %lld needed",
+               (long long)stage_bytes, (long long)payload_offsets[n_files]);
+
+  // pass 2: pack the payloads
+  next.store(0);
+  auto pack = [&]() {
+    for (;;) {
+      const int32_t k = next.fetch_add(1);
+      if (k >= n_files) break;
+      const int64_t nb = payload_offsets[k + 1] - payload_offsets[k];
+      if (nb > 0) memcpy((char*)stage + payload_offsets[k], (const char*)blobs[k] + infos[k].data_offset, (size_t)nb);
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(pack);
+    pack();
+    for (auto& th : pool) th.join();
   }
   return MAFE_OK;
 }

@@ -55,6 +55,8 @@ def wav_info(raw, offset=0.0, duration=None, filelike=False):
 
 def _file_bytes(file):
     """(bytes of the file from its current position, filelike flag) -- io.py:644-647, 500-503."""
+    if isinstance(file, (bytes, bytearray, memoryview)):
+        return file, False                    # the contents of a file, already read
     if hasattr(file, "read"):
         try:
             file.fileno()
@@ -136,6 +138,49 @@ class WavBatch:
         return np.diff(self.sample_offsets)
 
 
+def _name(f):
+    return "<%d bytes>" % len(f) if isinstance(f, (bytes, bytearray, memoryview)) else f
+
+
+class _BatchWalk:
+    """``mafe_wav_stage`` over the contents of many files: ``walk()`` parses all containers on the library's host
+    threads (path-like semantics, offset 0, no duration), ``pack(ptr, nbytes)`` copies their payloads back to back into
+    a pinned buffer.  ``infos[k]`` / ``offsets`` (payload byte offsets, ``[n + 1]``) are valid after ``walk()``."""
+
+    def __init__(self, raws, files):
+        self.n, self.files = len(raws), files
+        self._views = [np.frombuffer(r, dtype=np.uint8) for r in raws]          # keeps the buffers alive
+        self._ptrs = (C.c_void_p * max(self.n, 1))(*[v.ctypes.data for v in self._views])
+        self._sizes = np.array([v.size for v in self._views], dtype=np.int64)
+        self._infos = (L.WavInfo * max(self.n, 1))()
+        self.offsets = np.zeros(self.n + 1, dtype=np.int64)
+        self.infos = []
+
+    def _call(self, stage_ptr, stage_bytes):
+        lib = L.load()
+        failed = C.c_int32(-1)
+        rc = lib.mafe_wav_stage(self._ptrs, self._sizes.ctypes.data_as(C.c_void_p), self.n, 0, self._infos,
+                                self.offsets.ctypes.data_as(C.c_void_p), stage_ptr, int(stage_bytes), C.byref(failed))
+        if rc != L.OK:
+            msg = lib.mafe_last_error().decode("utf-8", "replace")
+            if failed.value >= 0:
+                exc = _ERRORS.get(self._infos[failed.value].error_kind, L.MafeError)
+                raise exc("%s (file %r)" % (msg, _name(self.files[failed.value])))
+            L.check(rc)
+
+    def walk(self):
+        self._call(None, 0)
+        self.infos = [self._infos[k] for k in range(self.n)]
+        for k, i in enumerate(self.infos):
+            if i.warnings:
+                warnings.warn("%r: WAV container with unknown chunks or a short data chunk" % (_name(self.files[k]),),
+                              WavFileWarning, stacklevel=4)
+        return self
+
+    def pack(self, stage_ptr, stage_bytes):
+        self._call(stage_ptr, stage_bytes)
+
+
 def resampled_length(n_in, orig_freq, new_freq):
     """Output length of ``processing.resample`` (processing.py:170-172), with its float arithmetic."""
     ratio = float(new_freq) / orig_freq
@@ -157,16 +202,14 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
 
     Returns a :class:`WavBatch`; its device buffer belongs to the engine (name ``buffer_name``) and stays valid until
     the next ``load_batch`` with the same name."""
-    raws, infos = [], []
-    for f in files:
-        raw, filelike = _file_bytes(f)
-        info = wav_info(raw, 0.0, None, filelike)
+    files = list(files)
+    walk = _BatchWalk([_file_bytes(f)[0] for f in files], files).walk()
+    infos, bo = walk.infos, walk.offsets
+    for f, info in zip(files, infos):
         if info.channels != 1:
-            raise ValueError("load_batch: %r has %d channels; the feature front-end takes mono waveforms" % (f, info.channels))
+            raise ValueError("load_batch: %r has %d channels; the feature front-end takes mono waveforms" % (_name(f), info.channels))
         if info.sample_kind in (L.WAV_I40, L.WAV_I48, L.WAV_I56, L.WAV_I64):
-            raise ValueError("load_batch: %r holds 64-bit integer samples, which have no unit-range scaling in read()" % (f,))
-        raws.append(np.frombuffer(raw, dtype=np.uint8))
-        infos.append(info)
+            raise ValueError("load_batch: %r holds 64-bit integer samples, which have no unit-range scaling in read()" % (_name(f),))
     n = len(infos)
     rates = [int(np.uint32(i.sample_rate)) for i in infos]
     if speeds is None:
@@ -197,18 +240,15 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
 
     with eng.lock:
         d_wave = eng.buf(buffer_name, max(total * item_out, 16))
-        # one staging buffer for all payloads (a single H2D), decoded per run of files sharing a format
-        sizes = [m * L_BYTES[i.sample_kind] for m, i in zip(n_in, infos)]
-        bo = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(sizes, out=bo[1:])
-        stage = np.empty(max(int(bo[-1]), 1), dtype=np.uint8)
-        for k, (u8, i) in enumerate(zip(raws, infos)):
-            stage[bo[k]: bo[k + 1]] = u8[i.data_offset: i.data_offset + sizes[k]]
+        # one pinned staging buffer for all payloads, packed by the library's host threads: a single H2D
+        n_stage = int(bo[-1])
+        stage_ptr, _ = eng.pinned("wavstage", max(n_stage, 16))
+        walk.pack(stage_ptr, n_stage)
         if all_pcm16:
-            keep = eng.h2d(d_wave, stage[: int(bo[-1])]) if total else None          # the payload IS the int16 batch
+            eng.h2d_raw(d_wave, stage_ptr, n_stage)                                  # the payload IS the int16 batch
         else:
-            d_stage = eng.buf("wavstage", max(stage.nbytes, 16))
-            keep = eng.h2d(d_stage, stage)
+            d_stage = eng.buf("wavstage", max(n_stage, 16))
+            eng.h2d_raw(d_stage, stage_ptr, n_stage)
             k = 0
             while k < n:
                 src = C.c_void_p(d_stage.value + int(bo[k]))
@@ -235,7 +275,6 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
                                                     L.WAV_OUT_F32, factor(infos[k]), dst))
                 k = j + 1
         eng.sync()
-        del keep
     return WavBatch(d_wave, L.WAVE_I16 if all_pcm16 else L.WAVE_F32, so, rates, 1.0)
 
 

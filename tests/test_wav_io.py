@@ -177,3 +177,34 @@ def test_fuzz_native_walk_vs_oracle(filelike):
             have = np.frombuffer(b, dtype=np.uint8, count=raw.nbytes, offset=int(info.data_offset)) if raw.nbytes else b""
             assert bytes(have) == raw.tobytes(), it
     assert n_ok > 200
+
+
+def test_batch_walk_packs_payloads():
+    """mafe_wav_stage (host threads): infos / payload offsets of many files, payloads packed back to back; the first
+    malformed file is reported with the reference's exception class."""
+    import ctypes as C
+    from mindaudio_b200.data import io as P
+    names = ["pcm16", "pcm24", "float32", "pcm16_chunks", "pcm8", "pcm16_empty", "pcm32_be", "pcm16_truncated"]
+    blobs = [W.corpus()[n][0] for n in names] * 5
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        walk = P._BatchWalk(blobs, list(range(len(blobs)))).walk()
+    assert len(w) == 10 and all(issubclass(x.category, P.WavFileWarning) for x in w)      # chunks + truncated, x5
+    total = int(walk.offsets[-1])
+    stage = np.full(total + 8, 0xAB, dtype=np.uint8)
+    walk.pack(C.c_void_p(stage.ctypes.data), total)
+    assert (stage[total:] == 0xAB).all()
+    for k, (b, i) in enumerate(zip(blobs, walk.infos)):
+        audio, sr, _ = R.wav_read(b)
+        assert i.n_items == audio.size and i.sample_rate == sr
+        nb = int(walk.offsets[k + 1] - walk.offsets[k])
+        assert nb == audio.size * {"pcm24": 3}.get(names[k % len(names)], GOLD[names[k % len(names)]].dtype.itemsize if names[k % len(names)] not in ("pcm16", "pcm16_chunks", "pcm16_empty", "pcm16_truncated") else 2)
+        assert bytes(stage[walk.offsets[k]: walk.offsets[k + 1]]) == b[i.data_offset: i.data_offset + nb]
+    with pytest.raises(ValueError):
+        walk.pack(C.c_void_p(stage.ctypes.data), total - 1)                               # staging buffer too small
+    bad = list(blobs[:6])
+    bad[4] = W.bad_corpus()["not_wave"][0]
+    bad[5] = W.bad_corpus()["mulaw"][0]
+    with pytest.raises(TypeError, match="file 4"):
+        P._BatchWalk(bad, list(range(6))).walk()
+    assert P._BatchWalk([], []).walk().offsets.tolist() == [0]
