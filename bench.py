@@ -252,8 +252,7 @@ def main():
     p_ms, p_n = eng.profile_read(L.PROF_FRAME_MEAN)
     c_ms, c_n = eng.profile_read(L.PROF_CMVN)
     eng.profile(False)
-    # the tile kernel may run as several launches per step (chunks of whole utterances): its time per
-    # step is the sum over the step's launches, and the "launch" of the roofline is the step's worth of frames
+    # kernel time per step = sum over the step's launches (one today); the roofline's unit is the step's worth of frames
     k_avg_s = k_ms / args.steps / 1e3
     hbm_peak, peak_src = measured_peaks()
     achieved_gbs = BYTES_PER_FRAME * n_frames / k_avg_s / 1e9
@@ -286,8 +285,8 @@ def main():
                 "step_share": {"fbank512_v3_kernel_ms": k_ms / args.steps, "frame_mean_prepass_ms": p_ms / args.steps,
                                "cmvn_apply_ms": c_ms / args.steps, "step_ms": ms / args.steps,
                                "launches_per_step": [k_n // args.steps, p_n // args.steps, c_n // args.steps],
-                               "note": "per-kernel times are event brackets on each kernel's own stream; with the "
-                                       "chunked overlap they run concurrently, so they add up to more than step_ms"}}
+                               "note": "per-kernel times are CUDA-event brackets around each kernel's launches, "
+                                       "summed per step"}}
 
     # ---- end to end through the host-facing call: pinned host buffers, copies inside the timed region ----
     e2e = None
