@@ -67,7 +67,7 @@ def resample(waveform, orig_freq=16000, new_freq=16000, res_type="fft", lowpass_
         M = 1
         while M < 2 * max(n_in, n_out) - 1:
             M <<= 1
-        step = max(1, min(rows, (1 << 25) // M))
+        step = max(1, min(rows, (1 << 25) // M, 65535))     # scratch bound; grid.y limit of the kernels
         with eng.lock:
             for r0 in range(0, rows, step):
                 r1 = min(rows, r0 + step)
