@@ -47,3 +47,38 @@ def test_enums_accept_strings_and_members():
     assert ma.WindowType("hann") is ma.WindowType.HANN and ma.BorderType("reflect") is ma.BorderType.REFLECT
     with pytest.raises(ValueError):
         ma.WindowType("nope")
+
+
+def test_resample_host_side_contract():
+    """processing.resample / io.load_batch: everything decided on the host (lengths, argument errors) without a GPU."""
+    import io as _io
+    import mindaudio_b200 as ma
+    from mindaudio_b200.data import io as P
+    from oracle import restated as R
+    from tests import wav_util as W
+    rng = np.random.default_rng(2)
+    for n in [1, 2, 9000, 9001, 16000, 31999, 44100] + [int(v) for v in rng.integers(1, 400000, 40)]:
+        for speed in (0.9, 1.1):
+            x = np.zeros(n)
+            assert P.resampled_length(n, 16000 * speed, 16000) == R.resample(x, 16000 * speed, 16000).shape[-1], (n, speed)
+        assert P.resampled_length(n, 44100, 16000) == R.resample(np.zeros(n), 44100, 16000).shape[-1]
+    x = np.zeros((2, 100), dtype=np.float32)
+    assert ma.resample(x, 8000, 8000) is x                                       # processing.py:167-168
+    with pytest.raises(NotImplementedError):
+        ma.resample(x, 16000, 8000, res_type="minddata")
+    with pytest.raises(NotImplementedError):
+        ma.resample(x.astype(np.complex64), 16000, 8000)
+    stereo = W.make_wav(np.arange(20), channels=2)
+    mono = W.make_wav(np.arange(20))
+    with pytest.raises(ValueError, match="channels"):
+        P.load_batch([_io.BytesIO(stereo)])
+    with pytest.raises(ValueError, match="speed factors"):
+        P.load_batch([mono], speeds=[0.9, 1.1])
+    with pytest.raises(ValueError, match="positive"):
+        P.load_batch([mono], speeds=[0.0])
+    with pytest.raises(ValueError, match="64-bit"):
+        P.load_batch([W.make_wav(np.arange(8), width=8)])
+    with pytest.raises(UnboundLocalError):      # a container without chunks: what the reference's read() raises (io.py:741)
+        P.load_batch([b"RIFF\x00\x00\x00\x00WAVE"])
+    with pytest.raises(ValueError, match="file"):
+        P.load_batch([mono, b"JUNKJUNKJUNK"])
