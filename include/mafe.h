@@ -316,7 +316,8 @@ enum {  /* mafe_wav_info.warnings: the reference's WavFileWarning cases */
 };
 enum {  /* mafe_wav_info.error_kind when mafe_wav_parse fails: the exception class the reference raises */
   MAFE_WAV_ERR_VALUE = 1, MAFE_WAV_ERR_TYPE = 2, MAFE_WAV_ERR_UNBOUND = 3, MAFE_WAV_ERR_ZERODIV = 4,
-  MAFE_WAV_ERR_STRUCT = 5   /* struct.error: a size / header field cut short by the end of the file */
+  MAFE_WAV_ERR_STRUCT = 5,  /* struct.error: a size / header field cut short by the end of the file */
+  MAFE_WAV_ERR_OS = 6       /* OSError: the file could not be opened / mapped (mafe_wav_files_open) */
 };
 typedef struct mafe_wav_info {
   int32_t format_tag;        /* 1 PCM, 3 IEEE float (WAVE_FORMAT_EXTENSIBLE resolved through its GUID, io.py:364-382) */
@@ -347,6 +348,14 @@ int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_s, double d
  * mafe_last_error() describe it. */
 int mafe_wav_stage(const void* const* blobs, const int64_t* blob_bytes, int32_t n_files, int32_t n_threads,
                    mafe_wav_info* infos, int64_t* payload_offsets, void* stage, int64_t stage_bytes, int32_t* failed_index);
+/* The same from paths (io.read's `open(file, "rb")` branch, io.py:646-647): the files are memory-mapped by the host
+ * threads, walked like mafe_wav_stage (infos, payload_offsets as there), and kept mapped in *out until
+ * mafe_wav_files_close; mafe_wav_files_pack copies the payloads from the page cache into the caller's pinned buffer. */
+typedef struct mafe_wav_files mafe_wav_files;
+int mafe_wav_files_open(const char* const* paths, int32_t n_files, int32_t n_threads, mafe_wav_files** out,
+                        mafe_wav_info* infos, int64_t* payload_offsets, int32_t* failed_index);
+int mafe_wav_files_pack(mafe_wav_files* files, void* stage, int64_t stage_bytes);
+int mafe_wav_files_close(mafe_wav_files* files);
 /* Device: n_items items of kind sample_kind at payload_dev (byte pointer, any alignment) -> out_dev as float32 / float64
  * in `read`'s unified output format (int16 / 32768, int32 and 24-bit / 2^31, everything else unchanged; io.py:741-746)
  * times `scale` (the conformer pipeline's `* (1 << 15)`, examples/conformer/dataset.py:389-390), or as raw int16 in

@@ -97,6 +97,9 @@ _PROTOS = {
     "mafe_hpss_masks": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, _I32, _P, _P]),
     "mafe_wav_parse": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, _I32, _P]),
     "mafe_wav_stage": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, C.c_int64, C.POINTER(_I32)]),
+    "mafe_wav_files_open": (C.c_int, [_P, _I32, _I32, C.POINTER(_P), _P, _P, C.POINTER(_I32)]),
+    "mafe_wav_files_pack": (C.c_int, [_P, _P, C.c_int64]),
+    "mafe_wav_files_close": (C.c_int, [_P]),
     "mafe_wav_decode": (C.c_int, [_P, _P, C.c_int64, _I32, _I32, _I32, C.c_double, _P]),
     "mafe_resample_workspace": (C.c_int, [_I32, C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]),
     "mafe_resample_fft": (C.c_int, [_P, _P, _I32, C.c_int64, C.c_int64, _P, _P, C.c_size_t]),
@@ -114,7 +117,7 @@ class WavInfo(C.Structure):
 WAV_U8, WAV_I8, WAV_I16, WAV_I24, WAV_I32, WAV_I40, WAV_I48, WAV_I56, WAV_I64, WAV_F32, WAV_F64 = range(1, 12)
 WAV_OUT_F32, WAV_OUT_F64, WAV_OUT_I16 = 0, 1, 2
 WAV_WARN_UNKNOWN_CHUNK, WAV_WARN_EOF, WAV_WARN_INCOMPLETE_ID = 1, 2, 4
-WAV_ERR_VALUE, WAV_ERR_TYPE, WAV_ERR_UNBOUND, WAV_ERR_ZERODIV, WAV_ERR_STRUCT = 1, 2, 3, 4, 5
+WAV_ERR_VALUE, WAV_ERR_TYPE, WAV_ERR_UNBOUND, WAV_ERR_ZERODIV, WAV_ERR_STRUCT, WAV_ERR_OS = 1, 2, 3, 4, 5, 6
 
 _lib = None
 

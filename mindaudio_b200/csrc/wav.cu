@@ -5,7 +5,12 @@
 // items that were read).  The arithmetic of the "unified output format" (io.py:741-746) runs on the device.
 #include "common.cuh"
 
+#include <errno.h>
+#include <fcntl.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <thread>
@@ -301,6 +306,145 @@ extern "C" int mafe_wav_stage(const void* const* blobs, const int64_t* blob_byte
     pack();
     for (auto& th : pool) th.join();
   }
+  return MAFE_OK;
+}
+
+// ---- the same, from paths: the files are mapped (not read) by the host threads, so the only copy of a payload is the
+// one from the page cache into the caller's pinned staging buffer.
+struct mafe_wav_files {
+  struct Map { void* p = nullptr; size_t n = 0; };
+  std::vector<Map> maps;
+  std::vector<const void*> ptrs;
+  std::vector<int64_t> sizes;
+  std::vector<mafe_wav_info> infos;
+  std::vector<int64_t> offsets;
+  std::vector<std::string> paths;
+  int n_threads = 0;
+  ~mafe_wav_files() {
+    for (auto& m : maps) if (m.p && m.n) munmap(m.p, m.n);
+  }
+};
+
+extern "C" int mafe_wav_files_open(const char* const* paths, int32_t n_files, int32_t n_threads, mafe_wav_files** out,
+                                   mafe_wav_info* infos, int64_t* payload_offsets, int32_t* failed_index) {
+  MAFE_REQUIRE(out != nullptr, "mafe_wav_files_open: out is NULL");
+  *out = nullptr;
+  MAFE_REQUIRE(n_files >= 0 && (n_files == 0 || (paths && infos)) && payload_offsets, "mafe_wav_files_open: bad argument");
+  if (failed_index) *failed_index = -1;
+  mafe_wav_files* h = new (std::nothrow) mafe_wav_files();
+  if (!h) { set_error("out of host memory"); return MAFE_E_OOM; }
+  h->maps.resize((size_t)n_files);
+  h->ptrs.assign((size_t)n_files, nullptr);
+  h->sizes.assign((size_t)n_files, 0);
+  h->n_threads = n_threads;
+  for (int32_t k = 0; k < n_files; ++k) h->paths.emplace_back(paths[k]);
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw < 1) hw = 1;
+  int nt = n_threads > 0 ? n_threads : (hw < 16 ? hw : 16);
+  if (nt > n_files) nt = n_files > 0 ? n_files : 1;
+  std::atomic<int32_t> next{0};
+  std::vector<int32_t> bad_of((size_t)nt, INT32_MAX);
+  std::vector<std::string> msgs((size_t)nt);
+  static const char kEmpty = 0;
+  auto map_all = [&](int t) {
+    for (;;) {
+      const int32_t k = next.fetch_add(1);
+      if (k >= n_files) break;
+      const int fd = open(paths[k], O_RDONLY | O_CLOEXEC);
+      struct stat st;
+      if (fd < 0 || fstat(fd, &st) != 0) {
+        if (k < bad_of[(size_t)t]) { bad_of[(size_t)t] = k; msgs[(size_t)t] = std::string(paths[k]) + ": " + strerror(errno); }
+        if (fd >= 0) close(fd);
+        continue;
+      }
+      if (st.st_size > 0) {
+        void* p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED) {
+          if (k < bad_of[(size_t)t]) { bad_of[(size_t)t] = k; msgs[(size_t)t] = std::string(paths[k]) + ": mmap: " + strerror(errno); }
+          close(fd);
+          continue;
+        }
+        h->maps[(size_t)k].p = p;
+        h->maps[(size_t)k].n = (size_t)st.st_size;
+        h->ptrs[(size_t)k] = p;
+      } else {
+        h->ptrs[(size_t)k] = &kEmpty;
+      }
+      h->sizes[(size_t)k] = (int64_t)st.st_size;
+      close(fd);
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(map_all, t);
+    map_all(0);
+    for (auto& th : pool) th.join();
+  }
+  int32_t bad = INT32_MAX, bad_t = -1;
+  for (int t = 0; t < nt; ++t) if (bad_of[(size_t)t] < bad) { bad = bad_of[(size_t)t]; bad_t = t; }
+  if (bad_t >= 0) {
+    if (failed_index) *failed_index = bad;
+    if (infos) { memset(&infos[bad], 0, sizeof(mafe_wav_info)); infos[bad].error_kind = MAFE_WAV_ERR_OS; }
+    set_error("%s", msgs[(size_t)bad_t].c_str());
+    delete h;
+    return MAFE_E_INVALID_ARG;
+  }
+  const int rc = mafe_wav_stage(h->ptrs.data(), h->sizes.data(), n_files, n_threads, infos, payload_offsets, nullptr, 0, failed_index);
+  if (rc != MAFE_OK) { delete h; return rc; }
+  h->infos.assign(infos, infos + n_files);
+  h->offsets.assign(payload_offsets, payload_offsets + n_files + 1);
+  *out = h;
+  return MAFE_OK;
+}
+
+extern "C" int mafe_wav_files_pack(mafe_wav_files* h, void* stage, int64_t stage_bytes) {
+  MAFE_REQUIRE(h != nullptr && stage != nullptr, "mafe_wav_files_pack: NULL argument");
+  const int32_t n = (int32_t)h->ptrs.size();
+  MAFE_REQUIRE(stage_bytes >= h->offsets[(size_t)n], "mafe_wav_files_pack: staging buffer of %lld bytes, %lld needed",
+               (long long)stage_bytes, (long long)h->offsets[(size_t)n]);
+  // pread straight into the staging buffer: one kernel copy from the page cache, no page faults on a mapping
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw < 1) hw = 1;
+  int nt = h->n_threads > 0 ? h->n_threads : (hw < 16 ? hw : 16);
+  if (nt > n) nt = n > 0 ? n : 1;
+  std::atomic<int32_t> next{0}, bad{INT32_MAX};
+  auto pack = [&]() {
+    for (;;) {
+      const int32_t k = next.fetch_add(1);
+      if (k >= n) break;
+      int64_t nb = h->offsets[(size_t)k + 1] - h->offsets[(size_t)k];
+      if (nb <= 0) continue;
+      char* dst = (char*)stage + h->offsets[(size_t)k];
+      const int fd = open(h->paths[(size_t)k].c_str(), O_RDONLY | O_CLOEXEC);
+      int64_t pos = h->infos[(size_t)k].data_offset;
+      bool ok = fd >= 0;
+      while (ok && nb > 0) {
+        const ssize_t got = pread(fd, dst, (size_t)nb, (off_t)pos);
+        if (got <= 0) { if (got < 0 && errno == EINTR) continue; ok = false; break; }
+        dst += got; pos += got; nb -= got;
+      }
+      if (fd >= 0) close(fd);
+      if (!ok) {   // the file changed under us since it was walked
+        int32_t cur = bad.load();
+        while (k < cur && !bad.compare_exchange_weak(cur, k)) {}
+      }
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(pack);
+    pack();
+    for (auto& th : pool) th.join();
+  }
+  if (bad.load() != INT32_MAX) {
+    set_error("%s: short read while packing the payload", h->paths[(size_t)bad.load()].c_str());
+    return MAFE_E_INVALID_ARG;
+  }
+  return MAFE_OK;
+}
+
+extern "C" int mafe_wav_files_close(mafe_wav_files* h) {
+  delete h;
   return MAFE_OK;
 }
 

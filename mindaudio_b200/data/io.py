@@ -13,6 +13,7 @@ dtype view of the file's bytes exactly as the reference returns them (no arithme
 from __future__ import annotations
 
 import ctypes as C
+import os
 import struct
 import warnings
 
@@ -29,7 +30,7 @@ class WavFileWarning(UserWarning):
 
 
 _ERRORS = {L.WAV_ERR_VALUE: ValueError, L.WAV_ERR_TYPE: TypeError, L.WAV_ERR_UNBOUND: UnboundLocalError,
-           L.WAV_ERR_ZERODIV: ZeroDivisionError, L.WAV_ERR_STRUCT: struct.error}
+           L.WAV_ERR_ZERODIV: ZeroDivisionError, L.WAV_ERR_STRUCT: struct.error, L.WAV_ERR_OS: OSError}
 _DTYPES = {L.WAV_U8: "u1", L.WAV_I8: "i1", L.WAV_I16: "i2", L.WAV_I32: "i4", L.WAV_I64: "i8", L.WAV_F32: "f4", L.WAV_F64: "f8"}
 
 
@@ -180,6 +181,58 @@ class _BatchWalk:
     def pack(self, stage_ptr, stage_bytes):
         self._call(stage_ptr, stage_bytes)
 
+    def close(self):
+        pass
+
+
+class _FileWalk:
+    """``mafe_wav_files_*``: the same as :class:`_BatchWalk` for paths -- the library's host threads map the files,
+    walk the containers and later copy the payloads from the page cache straight into the pinned staging buffer (no
+    Python-side ``read()``, no intermediate copy)."""
+
+    def __init__(self, paths):
+        self.n, self.files = len(paths), list(paths)
+        enc = [os.fsencode(p) for p in self.files]
+        self._paths = (C.c_char_p * max(self.n, 1))(*enc)
+        self._infos = (L.WavInfo * max(self.n, 1))()
+        self.offsets = np.zeros(self.n + 1, dtype=np.int64)
+        self.infos = []
+        self._h = C.c_void_p()
+
+    def walk(self):
+        lib = L.load()
+        failed = C.c_int32(-1)
+        rc = lib.mafe_wav_files_open(self._paths, self.n, 0, C.byref(self._h), self._infos,
+                                     self.offsets.ctypes.data_as(C.c_void_p), C.byref(failed))
+        if rc != L.OK:
+            msg = lib.mafe_last_error().decode("utf-8", "replace")
+            if failed.value >= 0:
+                kind = self._infos[failed.value].error_kind
+                if kind == L.WAV_ERR_OS:
+                    raise OSError(msg)
+                raise _ERRORS.get(kind, L.MafeError)("%s (file %r)" % (msg, self.files[failed.value]))
+            L.check(rc)
+        self.infos = [self._infos[k] for k in range(self.n)]
+        for k, i in enumerate(self.infos):
+            if i.warnings:
+                warnings.warn("%r: WAV container with unknown chunks or a short data chunk" % (self.files[k],),
+                              WavFileWarning, stacklevel=4)
+        return self
+
+    def pack(self, stage_ptr, stage_bytes):
+        L.check(L.load().mafe_wav_files_pack(self._h, stage_ptr, int(stage_bytes)))
+
+    def close(self):
+        if self._h:
+            L.load().mafe_wav_files_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001 -- interpreter shutdown
+            pass
+
 
 def resampled_length(n_in, orig_freq, new_freq):
     """Output length of ``processing.resample`` (processing.py:170-172), with its float arithmetic."""
@@ -203,7 +256,10 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
     Returns a :class:`WavBatch`; its device buffer belongs to the engine (name ``buffer_name``) and stays valid until
     the next ``load_batch`` with the same name."""
     files = list(files)
-    walk = _BatchWalk([_file_bytes(f)[0] for f in files], files).walk()
+    if files and all(isinstance(f, (str, os.PathLike)) for f in files):
+        walk = _FileWalk(files).walk()              # paths: mapped, walked and packed by the library's host threads
+    else:
+        walk = _BatchWalk([_file_bytes(f)[0] for f in files], files).walk()
     infos, bo = walk.infos, walk.offsets
     for f, info in zip(files, infos):
         if info.channels != 1:
@@ -244,6 +300,7 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
         n_stage = int(bo[-1])
         stage_ptr, _ = eng.pinned("wavstage", max(n_stage, 16))
         walk.pack(stage_ptr, n_stage)
+        walk.close()                                  # the files' mappings are no longer needed
         if all_pcm16:
             eng.h2d_raw(d_wave, stage_ptr, n_stage)                                  # the payload IS the int16 batch
         else:

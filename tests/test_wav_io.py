@@ -208,3 +208,43 @@ def test_batch_walk_packs_payloads():
     with pytest.raises(TypeError, match="file 4"):
         P._BatchWalk(bad, list(range(6))).walk()
     assert P._BatchWalk([], []).walk().offsets.tolist() == [0]
+
+
+def test_file_walk_matches_bytes_walk(tmp_path):
+    """mafe_wav_files_*: paths are mapped / walked / packed (pread) by the library's host threads -- same infos, same
+    payload offsets, same packed bytes as handing over the files' contents; OS and format errors name the file."""
+    import ctypes as C
+    from mindaudio_b200.data import io as P
+    names = ["pcm16", "pcm24", "float32", "pcm16_chunks", "pcm8", "pcm16_empty", "pcm32_be", "pcm16_odd_payload"]
+    blobs = [W.corpus()[n][0] for n in names] * 3
+    paths = []
+    for k, b in enumerate(blobs):
+        paths.append(str(tmp_path / ("%d.wav" % k)))
+        with open(paths[-1], "wb") as fh:
+            fh.write(b)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = P._BatchWalk(blobs, paths).walk()
+        f = P._FileWalk([paths[0], tmp_path / "1.wav"] + paths[2:]).walk()        # str and PathLike
+    assert np.array_equal(a.offsets, f.offsets)
+    assert all(bytes(x) == bytes(y) for x, y in zip(a.infos, f.infos))
+    total = int(a.offsets[-1])
+    s1, s2 = np.zeros(total, np.uint8), np.full(total + 4, 0xCD, np.uint8)
+    a.pack(C.c_void_p(s1.ctypes.data), total)
+    f.pack(C.c_void_p(s2.ctypes.data), total)
+    assert np.array_equal(s1, s2[:total]) and (s2[total:] == 0xCD).all()
+    with pytest.raises(ValueError):
+        f.pack(C.c_void_p(s2.ctypes.data), total - 1)
+    f.close()
+    f.close()                                                                      # idempotent
+    with pytest.raises(OSError, match="nonexistent"):
+        P._FileWalk(paths[:2] + [str(tmp_path / "nonexistent.wav")]).walk()
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(W.bad_corpus()["mulaw"][0])
+    with pytest.raises(ValueError, match="bad.wav"):
+        P._FileWalk(paths[:2] + [str(bad)]).walk()
+    empty = tmp_path / "empty.wav"
+    empty.write_bytes(b"")
+    with pytest.raises(ValueError, match="empty.wav"):
+        P._FileWalk([str(empty)]).walk()
+    assert P._FileWalk([]).walk().offsets.tolist() == [0]

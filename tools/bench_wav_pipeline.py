@@ -29,11 +29,22 @@ def main():
     ap.add_argument("--utts", type=int, default=2048)
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--files", action="store_true", help="write the WAVs to a temporary directory and pass PATHS "
+                    "(mapped / walked / packed by the library's host threads) instead of the files' contents")
     args = ap.parse_args()
     rng = np.random.default_rng(8)
     lens = np.sort(rng.integers(16000, 320001, size=args.utts))            # length-bucketed batches, as the reference sorts
     blobs = [make_wav(np.clip(np.round(0.05 * 32768 * rng.standard_normal(n)), -32768, 32767).astype(np.int16)) for n in lens]
     hours = float(lens.sum()) / 16000.0 / 3600.0
+    if args.files:
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="mafe_wav_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        paths = []
+        for k, b in enumerate(blobs):
+            paths.append(os.path.join(tmp, "%05d.wav" % k))
+            with open(paths[-1], "wb") as fh:
+                fh.write(b)
+        blobs = paths
     pipe = ma.FbankPipeline(cmvn="utt")
     batches = [blobs[i:i + args.batch] for i in range(0, args.utts, args.batch)]
 
@@ -55,7 +66,10 @@ def main():
     dt = (time.perf_counter() - t0) / args.steps
     split = [0.0]
     epoch(split)
-    print(json.dumps({"workload": "WAV contents (PCM16, 1-20 s, %d utterances in length-sorted batches of %d) -> padded "
+    if args.files:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps({"input": "paths" if args.files else "file contents (bytes)", "workload": "WAV contents (PCM16, 1-20 s, %d utterances in length-sorted batches of %d) -> padded "
                                   "fbank80 + utterance CMVN batches (features_from_wav)" % (args.utts, args.batch),
                       "audio_hours_per_s": hours / dt, "ms_per_batch": dt / len(batches) * 1e3, "frames": frames,
                       "load_batch_ms_per_batch": split[0] / len(batches) * 1e3,
