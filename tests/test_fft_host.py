@@ -50,6 +50,19 @@ def test_sweep_program_replayed_on_host(tmp_path):
         fb.tofile(path)
         res = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=60)
         assert res.returncode == 0, name + ": " + res.stdout + res.stderr
+    # the one-pass program of fbank400_kernel (n_fft 400: features.fbank / mfcc / melspectrogram defaults)
+    for name, nm, fb in (("f400_htk80", 80, T.hz_triangle_bank(201, 80, 16000, 0.0, 8000.0)),
+                         ("f400_htk40", 40, T.hz_triangle_bank(201, 40, 16000, 0.0, 8000.0)),
+                         ("f400_htk23", 23, T.hz_triangle_bank(201, 23, 16000, 0.0, 8000.0)),
+                         ("f400_slaney128", 128, T.hz_triangle_bank(201, 128, 16000, 0.0, 8000.0, norm="slaney", mel_type="slaney"))):
+        fb = np.ascontiguousarray(fb, dtype=np.float32)
+        assert fb.shape == (nm, 201), name
+        path = tmp_path / (name + ".f32")
+        fb.tofile(path)
+        res = subprocess.run([str(exe), str(path), str(nm)], capture_output=True, text=True, timeout=60)
+        assert res.returncode in (0, 3), name + ": " + res.stdout + res.stderr      # 3 = refused -> generic kernel, never wrong
+        if name in ("f400_htk80", "f400_htk40", "f400_htk23"):
+            assert res.returncode == 0, name + ": " + res.stdout + res.stderr
     wide = np.ascontiguousarray(banks["htk"], dtype=np.float32).copy()
     wide[10, 100] = wide[11, 100] = wide[12, 100] = 0.3                      # three filters on one bin
     path = tmp_path / "wide.f32"
