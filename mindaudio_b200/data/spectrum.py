@@ -421,6 +421,8 @@ def melscale(
     """``spectrum.py:738-774``: ``[..., n_stft, T]`` -> ``[..., n_mels, T]``."""
     spec = np.asarray(spec)
     f_max = f_max if f_max is not None else sample_rate // 2
+    if f_min > f_max:
+        raise ValueError("f_min ({}) should be no more than f_max ({})".format(f_min, f_max))
     if spec.ndim < 2 or spec.shape[-2] != n_stft:
         raise RuntimeError("input tensor is not in shape of <..., freq={}, time>, got {}".format(n_stft, spec.shape))
     bank = np.ascontiguousarray(T.hz_triangle_bank(n_stft, n_mels, sample_rate, f_min, f_max, NormType(norm), MelType(mel_type)),

@@ -61,6 +61,10 @@ def test_feature_argument_errors():
         ma.time_stretch(X, 0.0)
     with pytest.raises(ValueError, match="mask_param should be in"):
         ma.frequencymasking(np.zeros((1, 40, 30), dtype=np.float32), frequency_mask_param=100)
+    with pytest.raises(ValueError, match="f_min"):
+        ma.melscale(np.ones((201, 10), dtype=np.float32), f_min=9000, f_max=8000)
+    with pytest.raises(RuntimeError, match="freq=201"):
+        ma.melscale(np.ones((100, 10), dtype=np.float32))
     with pytest.raises(ValueError, match="Invalid hop_length"):
         ma.stft(X, hop_length=0)
     with pytest.raises(ValueError, match="expected 1 \\+ n_fft//2"):
