@@ -334,5 +334,3 @@ def load_batch(files, int16_scaled=True, buffer_name="wavbatch", speeds=None):
         eng.sync()
     return WavBatch(d_wave, L.WAVE_I16 if all_pcm16 else L.WAVE_F32, so, rates, 1.0)
 
-
-L_BYTES = {L.WAV_U8: 1, L.WAV_I8: 1, L.WAV_I16: 2, L.WAV_I24: 3, L.WAV_I32: 4, L.WAV_F32: 4, L.WAV_F64: 8}
