@@ -260,7 +260,7 @@ extern "C" int mafe_wav_stage(const void* const* blobs, const int64_t* blob_byte
   if (nt > n_files) nt = n_files > 0 ? n_files : 1;
 
   // pass 1: walk every container
-  std::atomic<int32_t> next{0}, first_bad{INT32_MAX};
+  std::atomic<int32_t> next{0};
   std::vector<std::string> msgs((size_t)nt);
   std::vector<int32_t> bad_of((size_t)nt, INT32_MAX);
   auto walk = [&](int t) {
