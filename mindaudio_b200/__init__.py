@@ -7,7 +7,7 @@ Importing this package does not touch CUDA (fork safe); the first op creates the
 from ._enums import BorderType, MelType, NormMode, NormType, WindowType  # noqa: F401
 from ._lib import MafeError  # noqa: F401
 from .data import augment, cmvn, collate, features, io, masking, processing, spectrum  # noqa: F401
-from .data.augment import pitch_shift, time_stretch  # noqa: F401
+from .data.augment import pitch_shift, speed_perturb, time_stretch  # noqa: F401
 from .data.collate import *  # noqa: F401,F403
 from .data.io import *  # noqa: F401,F403
 from .data.masking import *  # noqa: F401,F403

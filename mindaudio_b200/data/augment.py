@@ -18,7 +18,7 @@ from .masking import frequencymasking, timemasking  # noqa: F401
 from .processing import resample
 from .spectrum import _dense_offsets, _flatten_batch, _pad_shape
 
-__all__ = ["time_stretch", "pitch_shift", "_phase_vocoder", "frequencymasking", "timemasking"]
+__all__ = ["time_stretch", "pitch_shift", "speed_perturb", "_phase_vocoder", "frequencymasking", "timemasking"]
 
 
 def _vocoder_tables(n_frames, n_bins, rate, hop_length):
@@ -108,3 +108,15 @@ def pitch_shift(waveforms, sr, n_steps, bins_per_octave=12):
     stretched = time_stretch(waveforms, rate=rate)
     y_shift = resample(stretched, orig_freq=float(sr) / rate, new_freq=sr)
     return _pad_shape(y_shift, data_shape=stretched.shape[-1])
+
+
+def speed_perturb(waveform, orig_freq, speeds=(90, 100, 110), perturb_prob=1.0):
+    """``augment.py:601-638``: with probability ``perturb_prob`` resample the batch from ``orig_freq`` to
+    ``orig_freq * speed // 100`` for a ``speed`` drawn from ``speeds`` (same ``np.random`` call sequence as the
+    reference: ``rand(1)`` then ``randint(0, len(speeds), (1,))``); the Fourier ``resample`` runs on the device."""
+    if np.random.rand(1) > perturb_prob:
+        return np.asarray(waveform).copy()
+    samp_index = np.random.randint(0, len(speeds), (1,))[0]
+    speed = speeds[samp_index]
+    new_freq = orig_freq * speed // 100
+    return resample(waveform, orig_freq, new_freq)

@@ -82,3 +82,34 @@ def test_resample_host_side_contract():
         P.load_batch([b"RIFF\x00\x00\x00\x00WAVE"])
     with pytest.raises(ValueError, match="file"):
         P.load_batch([mono, b"JUNKJUNKJUNK"])
+
+
+def test_speed_perturb_draws_like_the_reference(monkeypatch):
+    """augment.speed_perturb: same np.random call sequence and target frequency as augment.py:629-637 (the resampling
+    itself is the device op checked in test_gpu_spectrum)."""
+    import os
+    from mindaudio_b200.data import augment as A
+    calls = []
+    monkeypatch.setattr(A, "resample", lambda w, o, n: calls.append((o, n)) or w)
+    x = np.zeros((2, 1000), dtype=np.float32)
+    np.random.seed(11)
+    out = A.speed_perturb(x, 16000, perturb_prob=0.0)                 # rand(1) > 0 -> untouched copy
+    assert out is not x and np.array_equal(out, x) and not calls
+    expect = []
+    np.random.seed(12)
+    for _ in range(6):
+        A.speed_perturb(x, 16000, speeds=[90, 100, 110])
+    np.random.seed(12)
+    for _ in range(6):
+        assert not np.random.rand(1) > 1.0
+        expect.append((16000, 16000 * [90, 100, 110][np.random.randint(0, 3, (1,))[0]] // 100))
+    assert calls == expect and len({n for _, n in calls}) > 1
+    if os.path.isfile("/root/reference/mindaudio/data/augment.py"):
+        from oracle import ref_loader
+        g = ref_loader._extract_functions("/root/reference/mindaudio/data/augment.py", ["speed_perturb"],
+                                          {"resample": lambda w, o, n: ref_calls.append((o, n)) or w})
+        ref_calls = []
+        np.random.seed(12)
+        for _ in range(6):
+            g["speed_perturb"](x, 16000, speeds=[90, 100, 110])
+        assert ref_calls == expect
