@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <thread>
 
@@ -272,8 +273,10 @@ extern "C" int mafe_wav_stage(const void* const* blobs, const int64_t* blob_byte
     }
   };
   {
+    // a container walk takes a few microseconds: more than one thread per 64 files costs more than it saves
+    const int nw = std::min(nt, n_files / 64 + 1);
     std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(walk, t);
+    for (int t = 1; t < nw; ++t) pool.emplace_back(walk, t);
     walk(0);
     for (auto& th : pool) th.join();
   }
@@ -375,8 +378,9 @@ extern "C" int mafe_wav_files_open(const char* const* paths, int32_t n_files, in
     }
   };
   {
+    const int nw = std::min(nt, n_files / 64 + 1);   // open + fstat + mmap: a few microseconds per file
     std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(map_all, t);
+    for (int t = 1; t < nw; ++t) pool.emplace_back(map_all, t);
     map_all(0);
     for (auto& th : pool) th.join();
   }
