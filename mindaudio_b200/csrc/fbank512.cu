@@ -341,6 +341,9 @@ struct FastTablesHost {
   V3Sweep sweep;          // sweep program of the v3 kernel (kernel-parameter bank)
   bool v3 = false;        // the v3 kernel's compact planes can hold this filterbank
   int* comb3_dev = nullptr;   // v3: plane rows (A | B << 8) of every filter
+  V5Sweep sweep5;             // half-warp variant (experimental, MAFE_HALFWARP_SWEEP)
+  bool v5 = false;
+  int* comb5_dev = nullptr;
 };
 
 int fast_tile_frames() { return kTileFrames; }
@@ -468,6 +471,71 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
     if (nrow[m] == 0) comb3[m] = rows | (rows << 8);
     else if (nrow[m] == 1) comb3[m] |= rows << 8;
   }
+  return true;
+}
+
+// Half-warp variant: 16 cost-balanced ranges (one per half-warp), a filter may be emitted by up to three of them.
+static bool build_v5_program(const std::vector<BinEntry>& bins, V5Sweep& S, std::vector<int>& comb5) {
+  memset(&S, 0, sizeof(S));
+  comb5.assign(kV2Mels, 0);
+  constexpr int NK = 128, W = kV5Ranges;
+  constexpr int c_bin = 14, c_ret = 8;   // per (pair, bin) step / per retire, relative
+  auto lo_of = [&](int a) { return bins[2 * a].f0; };
+  auto hi_of = [&](int b) { return bins[b == NK ? kBins - 1 : 2 * b - 1].f0 + 1; };
+  auto cost = [&](int a, int b) -> long {
+    const int nret = hi_of(b) - lo_of(a) + 1;
+    if (nret > kV3Runs || b - a + 1 > 32) return -1;
+    return (long)c_bin * (2 * (b - a) + (b == NK ? 1 : 0)) + (long)c_ret * 2 * nret;
+  };
+  const long INF = 1L << 60;
+  std::vector<std::vector<long>> best(W + 1, std::vector<long>(NK + 1, INF));
+  std::vector<std::vector<int>> from(W + 1, std::vector<int>(NK + 1, -1));
+  best[0][0] = 0;
+  for (int w = 1; w <= W; ++w)
+    for (int b = w; b <= NK; ++b)
+      for (int a = w - 1; a < b; ++a) {
+        if (best[w - 1][a] == INF) continue;
+        const long c = cost(a, b);
+        if (c < 0) continue;
+        const long v = std::max(best[w - 1][a], c);
+        if (v < best[w][b]) { best[w][b] = v; from[w][b] = a; }
+      }
+  if (best[W][NK] == INF) return false;
+  int edge[W + 1];
+  edge[W] = NK;
+  for (int w = W; w > 0; --w) edge[w - 1] = from[w][edge[w]];
+  int rows = 0;
+  std::vector<int> nrow(kV2Mels, 0);
+  for (int w = 0; w < W; ++w) {
+    const int a = edge[w], b = edge[w + 1];
+    const int lo = lo_of(a), hi = hi_of(b);
+    S.kk0[w] = (unsigned char)a;
+    S.kk0[w + 1] = (unsigned char)b;
+    S.row0[w] = (unsigned char)rows;
+    for (int m = lo; m <= hi; ++m, ++rows)
+      if (m >= 0 && m < kV2Mels) {
+        if (nrow[m] >= 3) return false;
+        comb5[m] |= rows << (8 * nrow[m]);
+        ++nrow[m];
+      }
+    for (int h = 0; h < 2; ++h) {
+      const int kk_end = b + ((h == 0 && b == NK) ? 1 : 0);
+      int cur = lo;
+      for (int kk = a; kk < kk_end; ++kk) {
+        const BinEntry& e = bins[2 * kk + h];
+        const int nret = e.f0 - cur;
+        if (nret > 3) return false;
+        S.step[h * kV3HalfStride + kk] = V3Step{e.w0, e.w1, nret, 0};
+        S.nret_mask[h * W + w][(kk - a) / 16] |= (uint32_t)nret << (2 * ((kk - a) % 16));
+        cur = e.f0;
+      }
+      S.tail[h][w] = (unsigned char)(hi - cur + 1);
+    }
+  }
+  if (rows >= kV5PlaneRows || rows > 254) return false;
+  S.zero_row = rows;
+  for (int m = 0; m < kV2Mels; ++m)
+    for (int r = nrow[m]; r < 3; ++r) comb5[m] |= rows << (8 * r);
   return true;
 }
 
@@ -696,6 +764,13 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     std::vector<int> comb3;
     th->v3 = build_v3_program(bins, th->sweep, comb3);
     if ((rc = up(&th->comb3_dev, comb3))) return rc;
+    std::vector<int> comb5;
+    th->v5 = th->v3 && build_v5_program(bins, th->sweep5, comb5);
+    if (th->v5) {
+      if ((rc = up(&th->comb5_dev, comb5))) return rc;
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<false, true, V5Sweep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<true, true, V5Sweep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5Smem::kTotal));
+    }
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem::kTotal));
     MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem::kTotal));
   }
@@ -708,6 +783,7 @@ void fast_plan_free(mafe_plan* p) {
   cudaFree(th->dev.window); cudaFree(th->dev.w512); cudaFree(th->dev.w256t);
   cudaFree(th->dev.bins); cudaFree(th->dev.warp_range); cudaFree(th->dev.combine); cudaFree(th->dev.cover);
   cudaFree(th->comb3_dev);
+  cudaFree(th->comb5_dev);
   cudaFree(th->tw400_dev);
   delete th;
   p->fast_tables = nullptr;
@@ -823,7 +899,18 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
-    {
+    static const bool halfwarp = getenv("MAFE_HALFWARP_SWEEP") != nullptr;   // experimental: 16 ranges, two frames per lane
+    if (halfwarp && th->v5) {
+      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
+      V2Params Q5 = Q;
+      Q5.combine = th->comb5_dev;
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      if (wave_dtype == MAFE_WAVE_I16)
+        fbank512_v3_kernel<true, true, V5Sweep><<<grid3, kFastThreads, V5Smem::kTotal, ctx->stream>>>(Q5, th->sweep5);
+      else
+        fbank512_v3_kernel<false, true, V5Sweep><<<grid3, kFastThreads, V5Smem::kTotal, ctx->stream>>>(Q5, th->sweep5);
+      MAFE_LAUNCH_CHECK(ctx);
+    } else {
       const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);   // persistent: 3 CTAs per SM, dynamic tile queue
       ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
       if (wave_dtype == MAFE_WAVE_I16)

@@ -40,6 +40,19 @@ struct V3Sweep {  // kernel-parameter resident (constant bank 0)
   unsigned char row0[kFastWarps];      // first plane row of a warp: it emits filters lo .. hi into consecutive rows
   int zero_row;                        // an all-zero plane row (filters with < 2 contributing warps read it)
 };
+// Half-warp variant (experimental): 16 bin ranges, one per HALF-warp; a lane carries both frames of a pair.  A filter may
+// be emitted by up to three ranges (comb5[m] = rowA | rowB << 8 | rowC << 16).
+constexpr int kV5Ranges = 2 * kFastWarps;
+constexpr int kV5PlaneRows = 116;     // 80 + 2 guards + <= 2 per range boundary + zero row
+struct V5Sweep {
+  V3Step step[2 * kV3HalfStride];
+  uint32_t nret_mask[2 * kV5Ranges][2];   // (half, range): ranges hold <= 32 steps
+  unsigned char tail[2][kV5Ranges];
+  unsigned char kk0[kV5Ranges + 1];
+  unsigned char row0[kV5Ranges];
+  int zero_row;
+};
+static_assert(sizeof(V5Sweep) + sizeof(V2Params) < 8000, "kernel parameters");
 static_assert(sizeof(V3Sweep) + sizeof(V2Params) < 8000, "kernel parameters (large-parameter ABI, <= 32764 B)");
 
 constexpr int kV3PlaneRows = 98;       // sum over warps of emitted filters (80 + 2 guards + <= 2 shared per boundary) + zero row
@@ -48,6 +61,7 @@ struct V3Smem {
   static constexpr size_t kZ = kY + sizeof(float) * 5632;                 // float2[16][273]; upper part = TMA landing zone
   static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
   static constexpr size_t kRawInZ = kZBytes - kV2RawBytes;
+  static constexpr size_t kRaw = kZ + kRawInZ;
   static constexpr size_t kPlanes = kZ + kZBytes;                         // float[98][33]
   static constexpr size_t kWin = kPlanes + ((sizeof(float) * kV3PlaneRows * kPlaneStride + 15) & ~(size_t)15);
   static constexpr size_t kW512 = kWin + sizeof(float) * 400;
@@ -57,6 +71,23 @@ struct V3Smem {
   static constexpr size_t kTotal = kInfo + 2 * 64;
 };
 static_assert(3 * (V3Smem::kTotal + 1024) <= 228 * 1024, "3 CTAs per SM");
+// Half-warp variant: more plane rows (16 ranges), the W512 twiddles stay in global memory (L1) to make room.
+struct V5Smem {
+  static constexpr size_t kY = 0;
+  static constexpr size_t kZ = kY + sizeof(float) * 5632;
+  static constexpr size_t kZBytes = sizeof(float2) * kPairs * kSlotStride;
+  static constexpr size_t kRawInZ = kZBytes - kV2RawBytes;
+  static constexpr size_t kRaw = kZ + kRawInZ;
+  static constexpr size_t kPlanes = kZ + kZBytes;
+  static constexpr size_t kWin = kPlanes + ((sizeof(float) * kV5PlaneRows * kPlaneStride + 15) & ~(size_t)15);
+  static constexpr size_t kW512 = kWin + sizeof(float) * 400;            // (not staged)
+  static constexpr size_t kW256 = kW512;
+  static constexpr size_t kBar = kW256 + sizeof(float2) * 256;
+  static constexpr size_t kInfo = kBar + 32;
+  static constexpr size_t kTotal = kInfo + 2 * 64;
+};
+static_assert(3 * (V5Smem::kTotal + 1024) <= 228 * 1024, "3 CTAs per SM (half-warp variant)");
+static_assert(V5Smem::kRaw % 128 == 0 && V5Smem::kBar % 8 == 0 && V5Smem::kWin % 16 == 0, "smem alignment");
 static_assert(V3Smem::kRawInZ % 128 == 0 && V3Smem::kRawInZ >= 6 * kV2Mels * 4, "landing zone vs the CMVN partial sums");
 static_assert(V3Smem::kZ % 16 == 0 && V3Smem::kBar % 8 == 0 && V3Smem::kWin % 16 == 0, "smem alignment");
 
@@ -116,6 +147,60 @@ __device__ __forceinline__ void sweep_v3(const V3Sweep& S, int g, int warp, cons
   retire(S.tail[g][warp]);   // >= 1: the last filter is always retired after the last bin
 }
 
+// Half-warp sweep: half-warp hw = 2 warp + (lane >> 4) owns the sub-range kk0[hw] .. kk0[hw + 1] - 1 of the current group
+// g; its 16 lanes are the 16 frame pairs and carry BOTH frames (plane columns 2t, 2t + 1), so the two loads, the weights
+// and the loop control of a step serve two frames.  The halves of a warp run their own (cost-balanced) programs: the
+// loops diverge, nothing is shared between them.
+__device__ __forceinline__ void sweep_v5(const V5Sweep& S, int g, int warp, int lane, const float2* __restrict__ Zs,
+                                         float* __restrict__ planes) {
+  const int hw = 2 * warp + (lane >> 4), t = lane & 15;
+  const float2* zp = Zs + t * kSlotStride;
+  const int kk0 = S.kk0[hw];
+  uint32_t ak = smem_u32(zp + kk0);
+  uint32_t an = smem_u32(zp + (256 - g) - kk0);
+  int si = g * kV3HalfStride + kk0;
+  const int si_end = g * kV3HalfStride + S.kk0[hw + 1] + ((g == 0 && hw == kV5Ranges - 1) ? 1 : 0);
+  float* dst = planes + (int)S.row0[hw] * kPlaneStride + 2 * t;
+  float a_lo = 0.f, a_hi = 0.f, b_lo = 0.f, b_hi = 0.f;
+  auto retire = [&](int n) {
+#pragma unroll 1
+    do {
+      float va = a_lo, vb = b_lo;
+      if (g) { va += dst[0]; vb += dst[1]; }
+      dst[0] = va;
+      dst[1] = vb;
+      a_lo = a_hi; a_hi = 0.f; b_lo = b_hi; b_hi = 0.f;
+      dst += kPlaneStride;
+    } while (--n);
+  };
+  const int gw = g * kV5Ranges + hw;
+  int word = 0;
+#pragma unroll 1
+  do {
+    uint32_t m = S.nret_mask[gw][word++];
+    const int chunk_end = min(si + 16, si_end);
+#pragma unroll 1
+    do {
+      const float2 w = *reinterpret_cast<const float2*>(&S.step[si].w0);
+      const int nr = m & 3u;
+      m >>= 2;
+      if (nr) retire(nr);
+      const float2 zk = lds_f2(ak);
+      const float2 zn = lds_f2(an);
+      bump<1>(si); bump<8>(ak); bump<-8>(an);
+      const float ra = zk.x + zn.x, ia = zk.y - zn.y;
+      const float rb = zk.x - zn.x, ib = zk.y + zn.y;
+      const float pa = fmaf(ra, ra, ia * ia);
+      const float pb = fmaf(rb, rb, ib * ib);
+      a_lo = fmaf(w.x, pa, a_lo);
+      a_hi = fmaf(w.y, pa, a_hi);
+      b_lo = fmaf(w.x, pb, b_lo);
+      b_hi = fmaf(w.y, pb, b_hi);
+    } while (si != chunk_end);
+  } while (si != si_end);
+  retire((int)S.tail[g][hw]);
+}
+
 // frame pair -> registers for group g: window, mean removal, radix-2 fold.  g = 0: even bins (lo + hi);
 // g = 1: odd bins ((lo - hi) W512^n).  Pair p starts at padded index 336 p of ybuf; sample n of frame a sits at
 // n + 16 (n >= 320), of frame b (= a + 160) at 160 + n + 16 (n >= 160): with n = t + 16 j the shifts depend on j only.
@@ -173,26 +258,28 @@ __device__ __forceinline__ void pass_p_f32(const float4* __restrict__ r4, float*
   }
 }
 
-template <bool I16>
+template <bool I16, bool HW = false, typename SweepT = V3Sweep>
 __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v3_kernel(const __grid_constant__ V2Params P,
-                                                                      const __grid_constant__ V3Sweep S) {
+                                                                      const __grid_constant__ SweepT S) {
+  using SM = typename std::conditional<HW, V5Smem, V3Smem>::type;
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* rb = smem + V3Smem::kZ + V3Smem::kRawInZ;   // the waveform tile lands in the upper part of Z
-  float* ybuf = reinterpret_cast<float*>(smem + V3Smem::kY);
-  float* planes = reinterpret_cast<float*>(smem + V3Smem::kPlanes);
-  float2* Zs = reinterpret_cast<float2*>(smem + V3Smem::kZ);
-  float* stage = reinterpret_cast<float*>(smem + V3Smem::kZ);
-  float* s_win = reinterpret_cast<float*>(smem + V3Smem::kWin);
-  float2* s_w512 = reinterpret_cast<float2*>(smem + V3Smem::kW512);
-  float2* s_w256 = reinterpret_cast<float2*>(smem + V3Smem::kW256);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + V3Smem::kBar);
-  int* s_work = reinterpret_cast<int*>(smem + V3Smem::kBar) + 4;   // [2] claimed tile index per parity
-  TileInfo* info = reinterpret_cast<TileInfo*>(smem + V3Smem::kInfo);
+  unsigned char* rb = smem + SM::kRaw;   // the waveform tile lands in the upper part of Z
+  float* ybuf = reinterpret_cast<float*>(smem + SM::kY);
+  float* planes = reinterpret_cast<float*>(smem + SM::kPlanes);
+  float2* Zs = reinterpret_cast<float2*>(smem + SM::kZ);
+  float* stage = reinterpret_cast<float*>(smem + SM::kZ);
+  float* s_win = reinterpret_cast<float*>(smem + SM::kWin);
+  float2* s_w512 = reinterpret_cast<float2*>(smem + SM::kW512);
+  float2* s_w256 = reinterpret_cast<float2*>(smem + SM::kW256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
+  int* s_work = reinterpret_cast<int*>(smem + SM::kBar) + 4;   // [2] claimed tile index per parity
+  TileInfo* info = reinterpret_cast<TileInfo*>(smem + SM::kInfo);
   constexpr int ES = I16 ? 2 : 4;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kV2Flen; i += kFastThreads) s_win[i] = P.window[i];
-  for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
+  for (int i = tid; i < 256; i += kFastThreads) { if (!HW) s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
+  const float2* w512 = HW ? P.w512 : s_w512;   // half-warp variant: the W512 twiddles are read through L1
   if (tid < kPlaneStride) planes[S.zero_row * kPlaneStride + tid] = 0.f;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -335,12 +422,13 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v3_kernel(const __gr
 #pragma unroll 1
     for (int g = 0; g < 2; ++g) {
       cpx v[16];
-      load_fold_v3(v, ya, s_win, s_w512, t, neg_mu, g);
+      load_fold_v3(v, ya, s_win, w512, t, neg_mu, g);
       fft256_group(v, slot, s_w256, t);
       __syncthreads();
       // stage 3: offsets + frame-mean sum of the next tile's utterance (consumed after the sweep)
       if (g == 1 && tid == 0 && nx_w < P.n_tiles) load_offsets();
-      sweep_v3(S, g, warp, zp, sgn, plane_dst);
+      if constexpr (HW) sweep_v5(S, g, warp, lane, Zs, planes);
+      else sweep_v3(S, g, warp, zp, sgn, plane_dst);
       __syncthreads();
     }
     // the Z region has been read for the last time -> the next tile's waveform may land in its upper part
@@ -353,7 +441,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v3_kernel(const __gr
     if (tid < 3 * kV2Mels) {
       const int g = cg, m = cm;
       const float* qa = planes + (crow & 0xff) * kPlaneStride + g;
-      const float* qb = planes + (crow >> 8) * kPlaneStride + g;
+      const float* qb = planes + (HW ? ((crow >> 8) & 0xff) : (crow >> 8)) * kPlaneStride + g;
+      const float* qc = planes + (HW ? (crow >> 16) : 0) * kPlaneStride + g;   // half-warp variant: a third contributing range
       float* od = P.out + (cur.out_row + g) * (int64_t)kV2Mels + m;
       const int left = nf - g;
       // one code path for the three log kinds: ln(a == 0 ? eps : a), ln(a + c), a
@@ -364,7 +453,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v3_kernel(const __gr
       // frames g, g + 3, ..., g + 30: fixed trip count, immediate offsets (f = 32 reads the pad column and is discarded)
 #pragma unroll
       for (int i = 0; i < 11; ++i) {
-        const float a = qa[3 * i] + qb[3 * i];
+        const float a = HW ? (qa[3 * i] + qb[3 * i]) + qc[3 * i] : qa[3 * i] + qb[3 * i];
         float x = a + add;
         x = x == 0.f ? zero_sub : x;
         // ln x = lg2 x * ln 2 with the raw MUFU (mel energies are never subnormal: 0 is replaced by DBL_EPSILON)
