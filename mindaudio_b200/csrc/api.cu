@@ -349,6 +349,7 @@ int mafe_batch_destroy(mafe_batch* b) {
   cudaFree(b->scratch_dev);
   cudaFree(b->utt_stats_dev);
   cudaFree(b->queue_dev);
+  cudaFree(b->tile_recs_dev);
   delete b;
   return MAFE_OK;
 }

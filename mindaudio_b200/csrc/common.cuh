@@ -145,6 +145,8 @@ struct mafe_batch {
   size_t scratch_bytes = 0;
   double* utt_stats_dev = nullptr;        // [n_utts][2][dim] fused utterance-CMVN statistics
   int32_t* queue_dev = nullptr;           // persistent-kernel work queue head (1 int)
+  void* tile_recs_dev = nullptr;          // v6 kernel: one 64-byte work record per tile (tile_prepare_kernel)
+  size_t cap_tile_recs = 0;               // in records
 };
 
 namespace mafe {

@@ -319,9 +319,7 @@ __global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, doubl
 }  // namespace mafe
 #include "fbank512_tile.cuh"
 #include "fbank512_v3.cuh"
-namespace mafe {
-
-}  // namespace mafe
+#include "fbank512_v6.cuh"
 #include "stft512.cuh"
 #include "fbank400.cuh"
 #include "stftn16.cuh"
@@ -341,6 +339,8 @@ struct FastTablesHost {
   V3Sweep sweep;          // sweep program of the v3 kernel (kernel-parameter bank)
   bool v3 = false;        // the v3 kernel's compact planes can hold this filterbank
   int* comb3_dev = nullptr;   // v3: plane rows (A | B << 8) of every filter
+  V6Sweep sweep6;             // dense per-filter mel program of the v6 kernel (kernel-parameter bank)
+  bool v6 = false;
   V5Sweep sweep5;             // half-warp variant (experimental, MAFE_HALFWARP_SWEEP)
   bool v5 = false;
   int* comb5_dev = nullptr;
@@ -471,6 +471,76 @@ static bool build_v3_program(const std::vector<BinEntry>& bins, V3Sweep& S, std:
     if (nrow[m] == 0) comb3[m] = rows | (rows << 8);
     else if (nrow[m] == 1) comb3[m] |= rows << 8;
   }
+  return true;
+}
+
+// Mel program of the v6 kernel: every filter = a run of aligned 4-bin chunks of the natural-order power row with
+// zero-padded weights.  The 80 filters are dealt to the 8 warps as contiguous ranges; inside a warp every filter takes the
+// chunk count of the warp's widest one (no per-filter dispatch in the kernel), and the split minimises the largest warp
+// cost  filters x (6 + 5 chunks)  by dynamic programming.
+static bool build_v6_program(const std::vector<BinEntry>& bins, V6Sweep& S) {
+  memset(&S, 0, sizeof(S));
+  constexpr int W = kFastWarps, M = kV2Mels;
+  std::vector<float> dense((size_t)M * kBins, 0.f);
+  for (int k = 0; k < kBins; ++k) {
+    const BinEntry& e = bins[k];
+    if (e.w0 != 0.f && e.f0 >= 0 && e.f0 < M) dense[(size_t)e.f0 * kBins + k] = e.w0;
+    if (e.w1 != 0.f && e.f0 + 1 >= 0 && e.f0 + 1 < M) dense[(size_t)(e.f0 + 1) * kBins + k] = e.w1;
+  }
+  int c0[M], n4[M];
+  for (int m = 0; m < M; ++m) {
+    int k0 = -1, k1 = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (dense[(size_t)m * kBins + k] != 0.f) { if (k0 < 0) k0 = k; k1 = k + 1; }
+    if (k0 < 0) { k0 = 0; k1 = 1; }   // empty filter: one all-zero chunk
+    c0[m] = k0 / 4;
+    n4[m] = (k1 + 3) / 4 - c0[m];
+    if (n4[m] > kV6MaxN4) return false;
+  }
+  auto cost = [&](int a, int b) -> long {   // filters a .. b - 1 in one warp
+    int nw = 0;
+    for (int m = a; m < b; ++m) nw = std::max(nw, n4[m]);
+    return (long)(b - a) * (6 + 5 * nw);
+  };
+  const long INF = 1L << 60;
+  std::vector<std::vector<long>> best(W + 1, std::vector<long>(M + 1, INF));
+  std::vector<std::vector<int>> from(W + 1, std::vector<int>(M + 1, -1));
+  best[0][0] = 0;
+  for (int w = 1; w <= W; ++w)
+    for (int b = w; b <= M; ++b)
+      for (int a = w - 1; a < b; ++a) {
+        if (best[w - 1][a] == INF) continue;
+        const long v = std::max(best[w - 1][a], cost(a, b));
+        if (v < best[w][b]) { best[w][b] = v; from[w][b] = a; }
+      }
+  if (best[W][M] == INF) return false;
+  int edge[W + 1];
+  edge[W] = M;
+  for (int w = W; w > 0; --w) edge[w - 1] = from[w][edge[w]];
+  int chunks = 0;
+  for (int w = 0; w < W; ++w) {
+    const int a = edge[w], b = edge[w + 1];
+    int nw = 0;
+    for (int m = a; m < b; ++m) nw = std::max(nw, n4[m]);
+    S.f0[w] = (unsigned char)a;
+    S.nw[w] = (unsigned char)nw;
+    S.wbase[w] = (unsigned short)chunks;
+    if (chunks + (b - a) * nw > kV6MaxChunks) return false;
+    for (int m = a; m < b; ++m) {
+      int start = c0[m];
+      if (4 * (start + nw) > kV6Row) start = kV6Row / 4 - nw;   // keep the padded run inside the row
+      S.start[m] = (unsigned short)(4 * start);
+      for (int j = 0; j < nw; ++j) {
+        float w4[4];
+        for (int i = 0; i < 4; ++i) {
+          const int k = 4 * (start + j) + i;
+          w4[i] = k < kBins ? dense[(size_t)m * kBins + k] : 0.f;
+        }
+        S.w[chunks++] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+  }
+  S.f0[W] = (unsigned char)M;
   return true;
 }
 
@@ -764,6 +834,13 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     std::vector<int> comb3;
     th->v3 = build_v3_program(bins, th->sweep, comb3);
     if ((rc = up(&th->comb3_dev, comb3))) return rc;
+    th->v6 = th->v3 && build_v6_program(bins, th->sweep6);
+    if (th->v6) {
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+    }
     std::vector<int> comb5;
     th->v5 = th->v3 && build_v5_program(bins, th->sweep5, comb5);
     if (th->v5) {
@@ -879,6 +956,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     Q.window = th->dev.window; Q.w512 = th->dev.w512; Q.w256t = th->dev.w256t; Q.combine = th->comb3_dev;
     Q.out = out;
     Q.queue_head = b->queue_dev;
+    Q.tile_recs = nullptr;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
     if (d.remove_frame_mean) {
       MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
@@ -900,7 +978,39 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
     static const bool halfwarp = getenv("MAFE_HALFWARP_SWEEP") != nullptr;   // experimental: 16 ranges, two frames per lane
-    if (halfwarp && th->v5) {
+    static const bool force_v3 = getenv("MAFE_FBANK_V3") != nullptr;         // A/B switch: the round-1 kernel
+    if (th->v6 && !force_v3 && !halfwarp) {
+      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);   // persistent: 3 CTAs per SM, dynamic tile queue
+      if (b->cap_tile_recs < (size_t)b->n_tiles) {   // grow-only
+        if (b->tile_recs_dev) MAFE_CUDA_CHECK(cudaFree(b->tile_recs_dev));
+        b->tile_recs_dev = nullptr; b->cap_tile_recs = 0;
+        const size_t cap = (size_t)b->n_tiles + (size_t)b->n_tiles / 4 + 16;
+        MAFE_CUDA_CHECK(cudaMalloc(&b->tile_recs_dev, cap * sizeof(TileInfo)));
+        b->cap_tile_recs = cap;
+      }
+      Q.tile_recs = b->tile_recs_dev;
+      {
+        ProfScope ps(ctx, MAFE_PROF_OTHER);
+        const int pg = (b->n_tiles + 255) / 256;
+        if (wave_dtype == MAFE_WAVE_I16) tile_prepare_kernel<true><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev);
+        else tile_prepare_kernel<false><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev);
+        MAFE_LAUNCH_CHECK(ctx);
+      }
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      static const bool no_tmem = getenv("MAFE_NO_TMEM") != nullptr;           // A/B switch: constants from shared memory
+      if (no_tmem) {
+        if (wave_dtype == MAFE_WAVE_I16)
+          fbank512_v6_kernel<true, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+        else
+          fbank512_v6_kernel<false, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+      } else {
+        if (wave_dtype == MAFE_WAVE_I16)
+          fbank512_v6_kernel<true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+        else
+          fbank512_v6_kernel<false, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+      }
+      MAFE_LAUNCH_CHECK(ctx);
+    } else if (halfwarp && th->v5) {
       const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);
       V2Params Q5 = Q;
       Q5.combine = th->comb5_dev;

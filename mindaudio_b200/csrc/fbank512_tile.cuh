@@ -35,6 +35,7 @@ struct V2Params {
   const int* combine;    // [80]
   float* out;
   int* queue_head;               // dynamic work queue: next unclaimed tile index
+  const void* tile_recs;         // v6: TileInfo[n_tiles], prepared per step by tile_prepare_kernel
 };
 
 struct TileInfo {  // geometry of one work item, prepared by thread 0 one iteration ahead
@@ -43,6 +44,7 @@ struct TileInfo {  // geometry of one work item, prepared by thread 0 one iterat
   int64_t cov_end, end_elem, base_elem;  // scalar patch-up range / element index of raw[0]
   int utt, nf, shift;
   float neg_mu;
+  uint32_t bytes;     // size of the bulk copy (multiple of 16; 0: nothing can be bulk-copied)
 };
 static_assert(sizeof(TileInfo) <= 64, "TileInfo slot");
 
@@ -105,6 +107,33 @@ __device__ __forceinline__ TileSrc<I16> tile_src(const V2Params& P, const Tile t
   r.shift = (int)(r.g0 - r.ga_byte / ES);  // -1 only when g0 == -1 (first tile of the first utterance)
   r.cov_end = r.bytes ? gb / ES : first;
   return r;
+}
+
+// Geometry of every work item, computed once per step for the whole batch (one thread per tile) after the frame-mean
+// pre-pass: the persistent kernel's producer thread then only copies a 64-byte record and issues the bulk copy -- the
+// 64-bit address arithmetic and the double division of the frame mean left its critical path.
+template <bool I16>
+__global__ void __launch_bounds__(256) tile_prepare_kernel(const V2Params P, TileInfo* __restrict__ recs) {
+  constexpr int ES = I16 ? 2 : 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_tiles) return;
+  const Tile tile = P.tiles[i];
+  const int64_t off = P.sample_offsets[tile.utt];
+  const int64_t fo0 = P.frame_offsets[tile.utt], fo1 = P.frame_offsets[tile.utt + 1];
+  const int T = (int)(fo1 - fo0);
+  const TileSrc<I16> src = tile_src<I16>(P, tile, off, T);
+  TileInfo r;
+  r.out_row = fo0 + tile.frame0;
+  r.s0 = (int64_t)tile.frame0 * kV2Hop;
+  r.cov_end = src.cov_end;
+  r.end_elem = src.end_elem;
+  r.base_elem = src.ga_byte / ES;
+  r.utt = tile.utt;
+  r.nf = min(kTileFrames, T - tile.frame0);
+  r.shift = src.shift;
+  r.neg_mu = P.remove_mean ? -(float)(P.utt_sum[tile.utt] / ((double)T * (double)kV2Flen)) : 0.f;
+  r.bytes = src.bytes;
+  recs[i] = r;
 }
 
 // 256-point transform of v by the 16-lane group; result (bin 2*(t+16kt)+HALF at slot[t+16kt])
