@@ -79,6 +79,30 @@ __device__ __forceinline__ void tm_wait8(float (&v)[8]) {
                : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 __device__ __forceinline__ void tm_wait1(float& v) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v)); }
+// Warps w and w + 4 share a TMEM lane quarter: the constants are common, the parking space is per warp (h = warp >> 2).
+constexpr int kTmPark = 96;           // columns 96 + 16 h ..: the even-bin powers of a lane wait here while the odd half is transformed
+constexpr int kTmNyq = 26;            // columns 26 + 2 h, 27 + 2 h (unused tail of the window block): powers of bin 256
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const float (&a)[8], const float (&b)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]), "f"(b[0]), "f"(b[1]), "f"(b[2]),
+      "f"(b[3]), "f"(b[4]), "f"(b[5]), "f"(b[6]), "f"(b[7])
+      : "memory");
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, float a, float b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&a)[8], float (&b)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]), "=f"(b[0]), "=f"(b[1]),
+        "=f"(b[2]), "=f"(b[3]), "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tm_ld2(uint32_t taddr, float& a, float& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_wait2(float& a, float& b) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b)); }
 __device__ __forceinline__ void tm_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
                "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -296,6 +320,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
 
+  const uint32_t tpark = tb + kTmPark + 16 * (warp >> 2), tnyq = tb + kTmNyq + 2 * (warp >> 2);
+
   // Thread 0 prepares every work item ONE ITERATION AHEAD, in stages spread over the iteration: claim (atomicAdd) at the
   // top, publish after pass P, copy the tile's 64-byte record (tile_prepare_kernel) into the other info slot with
   // cp.async after the FFT phase, bulk copy of the waveform tile after the sweep.  Tiles are claimed from a global
@@ -445,13 +471,26 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
           pb[kt] = re(qb) + im(qb);
         }
         if (g == 0) {
-#pragma unroll
-          for (int kt = 0; kt < 8; ++kt) { ea[kt] = pa[kt]; eb[kt] = pb[kt]; }
           // bin 256 (kk = 128, lane 0): its own partner: A = 2 re, B = 2 im
           const c2 zq = u[fft16_pos(8)];
           nyq_a = 4.f * re(zq) * re(zq);
           nyq_b = 4.f * im(zq) * im(zq);
+          if (TM) {   // park the even-bin powers in the lane's TMEM columns: 18 registers less through the odd half
+            tm_st16(tpark, pa, pb);
+            tm_st2(tnyq, nyq_a, nyq_b);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          } else {
+#pragma unroll
+            for (int kt = 0; kt < 8; ++kt) { ea[kt] = pa[kt]; eb[kt] = pb[kt]; }
+          }
         } else {
+          if (TM) {
+            tm_ld16(tpark, ea, eb);
+            tm_ld2(tnyq, nyq_a, nyq_b);
+            tm_wait8(ea);
+            tm_wait8(eb);
+            tm_wait2(nyq_a, nyq_b);
+          }
           __syncwarp();   // every lane of the group has read the scratch: the slot becomes the pair's two P rows
 #pragma unroll
           for (int kt = 0; kt < 8; ++kt) {
