@@ -234,7 +234,7 @@ __device__ __forceinline__ void load_fold_v3(cpx (&v)[16], const float* __restri
 
 // pass P, interior tile, float input: each thread owns groups of 4 samples.  The 5 raw values a group needs (4 samples
 // + predecessor) start at raw float 4q + SHIFT: two ALIGNED 16-byte loads and a compile-time pick.
-template <int SHIFT>
+template <int SHIFT, bool UNIT = false>
 __device__ __forceinline__ void pass_p_f32(const float4* __restrict__ r4, float* __restrict__ ybuf, int tid, float scale,
                                            float pre_hi, float pre_lo) {
   int rem80 = tid % 80, gpad = 16 * (tid / 80);   // q mod 80, 16 * (q / 80) for q = tid + 256 k
@@ -246,7 +246,7 @@ __device__ __forceinline__ void pass_p_f32(const float4* __restrict__ r4, float*
     else if (SHIFT == 1) { x0 = A.y; x1 = A.z; x2 = A.w; x3 = B.x; x4 = B.y; }
     else if (SHIFT == 2) { x0 = A.z; x1 = A.w; x2 = B.x; x3 = B.y; x4 = B.z; }
     else { x0 = A.w; x1 = B.x; x2 = B.y; x3 = B.z; x4 = B.w; }
-    x0 *= scale; x1 *= scale; x2 *= scale; x3 *= scale; x4 *= scale;
+    if (!UNIT) { x0 *= scale; x1 *= scale; x2 *= scale; x3 *= scale; x4 *= scale; }
     float4 y;
     y.x = fmaf(-pre_lo, x0, fmaf(-pre_hi, x0, x1));
     y.y = fmaf(-pre_lo, x1, fmaf(-pre_hi, x1, x2));

@@ -370,9 +370,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   const int cg = tid / kV2Mels, cm = tid - cg * kV2Mels;
   const int f_begin = S.f0[warp], f_end = S.f0[warp + 1], nw = S.nw[warp], wbase = S.wbase[warp];
 
-  uint32_t phase0 = 0, phase1 = 0;
-  int buf = 0;
-  for (;; buf ^= 1) {
+  // iteration it uses info / barrier slot it & 1; the slot's mbarrier completes its (it >> 1)-th phase
+  for (uint32_t it = 0;; ++it) {
+    const int buf = it & 1;
     if (s_work[buf] >= P.n_tiles) break;
     if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1 (issue): claim the next tile
     const TileInfo cur = info[buf];
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     const int nf = cur.nf;
 
     // wait for this tile's bytes
-    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    mbar_wait(&bars[buf], (it >> 1) & 1);
     // scalar patch-up of what the 16 B-granular bulk copy could not cover (end of the flat array)
     if (cur.cov_end < cur.end_elem) {
       for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
@@ -398,11 +398,20 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
       const bool interior = nf == kTileFrames && s0 > 0 && P.dither == 0.f && P.preemph_on;
       if (!I16 && interior) {
         const float4* r4 = reinterpret_cast<const float4*>(rb);
-        switch (cur.shift) {   // 0..3 here (s0 > 0), tile uniform
-          case 0: pass_p_f32<0>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
-          case 1: pass_p_f32<1>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
-          case 2: pass_p_f32<2>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
-          default: pass_p_f32<3>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
+        if (P.wave_scale == 1.0f) {
+          switch (cur.shift) {   // 0..3 here (s0 > 0), tile uniform
+            case 0: pass_p_f32<0, true>(r4, ybuf, tid, 1.0f, P.pre_hi, P.pre_lo); break;
+            case 1: pass_p_f32<1, true>(r4, ybuf, tid, 1.0f, P.pre_hi, P.pre_lo); break;
+            case 2: pass_p_f32<2, true>(r4, ybuf, tid, 1.0f, P.pre_hi, P.pre_lo); break;
+            default: pass_p_f32<3, true>(r4, ybuf, tid, 1.0f, P.pre_hi, P.pre_lo); break;
+          }
+        } else {
+          switch (cur.shift) {
+            case 0: pass_p_f32<0>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
+            case 1: pass_p_f32<1>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
+            case 2: pass_p_f32<2>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
+            default: pass_p_f32<3>(r4, ybuf, tid, P.wave_scale, P.pre_hi, P.pre_lo); break;
+          }
         }
       } else if (interior) {
         int rem = tid, pad = 0;        // i mod 320, 16 * (i / 320)  (tid < 256 < 320)
@@ -532,6 +541,22 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
       const float add = P.log_kind == MAFE_LOG_LN_PLUS ? P.log_arg : 0.f;
       const float zero_sub = P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO ? 2.220446049250313e-16f : 0.f;
       float s1 = 0.f, s2 = 0.f;
+      if (nf == kTileFrames && P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) {
+        // full tile, conformer log: frames g + 3 i, i < 11 (g < 2) or 10; no per-element predicates
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          if (i < 10 || g < 2) {
+            const float a = q[3 * i];
+            const float x = a == 0.f ? 2.220446049250313e-16f : a;
+            float l;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+            const float o = l * 0.69314718055994530942f;
+            od[3 * i * kV2Mels] = o;
+            s1 += o;
+            s2 = fmaf(o, o, s2);
+          }
+        }
+      } else {
       // frames g, g + 3, ..., g + 30: fixed trip count (f = 32 reads the pad column and is discarded)
 #pragma unroll
       for (int i = 0; i < 11; ++i) {
@@ -546,6 +571,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
         const float ov = in ? o : 0.f;
         s1 += ov;
         s2 = fmaf(ov, ov, s2);
+      }
       }
       if (P.utt_stats != nullptr) {
         part[(g * 2) * kV2Mels + m] = s1;
