@@ -59,6 +59,34 @@ def thin(d, stride=8, min_frames=64):
     return out
 
 
+def features_goldens(sp, ft, x, msop):
+    """The entries of ``features_msop.npz``: the reference's python wrappers (``sp`` = spectrum.py, ``ft`` = features.py)
+    around the ``mindspore.dataset.audio`` ops -- restated ones here (``msop=1``), the real MindSpore 2.3.0 binary in
+    ``oracle/make_goldens_with_mindspore.py`` (``msop=0``).  ``x``: BAC009S0002W0122 as ``io.read`` returns it."""
+    f = {"msop": np.int32(msop)}
+    f["spectrogram_default"] = sp.spectrogram(x)                                # (201, 480)
+    f["spectrogram_512_mag"] = sp.spectrogram(x.astype(np.float32), n_fft=512, hop_length=128, power=1.0,
+                                              normalized=True, window="hamming")
+    f["melspectrogram_default"] = sp.melspectrogram(x)                         # (128, 480)
+    f["melspectrogram_slaney"] = sp.melspectrogram(x, n_fft=512, n_mels=40, norm="slaney", mel_type="slaney",
+                                                   f_min=50.0, f_max=7600.0)
+    f["melscale_1024"] = sp.melscale(sp.spectrogram(x, n_fft=1024), n_stft=1024 // 2 + 1)
+    f["fbank_cfg1"] = ft.fbank(x, n_mels=80, n_fft=400, hop_length=160)        # (80, 600)
+    assert f["fbank_cfg1"].shape == (80, 600)
+    xe = synth(4, (4, 48000))
+    f["fbank_ecapa_syn4"] = ft.fbank(xe, deltas=False, n_mels=80, left_frames=0, right_frames=0,
+                                     n_fft=400, hop_length=160)                  # ECAPA call, (4, 80, 301)
+    xm = synth(11, (2, 16000))
+    f["fbank_default_dc_syn11"] = ft.fbank(xm, deltas=True, context=True)
+    f["mfcc_default_syn11"] = ft.mfcc(xm)                                      # (2, 660, 81)
+    f["mfcc_cfg4"] = ft.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160)
+    f["mfcc_cfg4_logmels"] = ft.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160,
+                                     log_mels=True)
+    f["deltas_syn"] = ft.compute_deltas(f["fbank_cfg1"][:, :100], win_length=7, pad_mode="reflect")
+    f["context_3_5"] = ft.context_window(f["fbank_cfg1"][:10, :60].astype(np.float32), 3, 5)
+    return f
+
+
 def main():
     sys.path.insert(0, REPO)
     from oracle import ref_loader
@@ -110,27 +138,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "spectrum.npz"), **thin(g))
 
     # ---------------- features via ms-op shim (msop=1: unpinned vs MindSpore binary) ----------
-    f = {"msop": np.int32(1)}
-    f["spectrogram_default"] = sp.spectrogram(x)                                # (201, 480)
-    f["spectrogram_512_mag"] = sp.spectrogram(x.astype(np.float32), n_fft=512, hop_length=128, power=1.0,
-                                              normalized=True, window="hamming")
-    f["melspectrogram_default"] = sp.melspectrogram(x)                         # (128, 480)
-    f["melspectrogram_slaney"] = sp.melspectrogram(x, n_fft=512, n_mels=40, norm="slaney", mel_type="slaney",
-                                                   f_min=50.0, f_max=7600.0)
-    f["melscale_1024"] = sp.melscale(sp.spectrogram(x, n_fft=1024), n_stft=1024 // 2 + 1)
-    f["fbank_cfg1"] = ft.fbank(x, n_mels=80, n_fft=400, hop_length=160)        # (80, 600)
-    assert f["fbank_cfg1"].shape == (80, 600)
-    xe = synth(4, (4, 48000))
-    f["fbank_ecapa_syn4"] = ft.fbank(xe, deltas=False, n_mels=80, left_frames=0, right_frames=0,
-                                     n_fft=400, hop_length=160)                  # ECAPA call, (4, 80, 301)
-    xm = synth(11, (2, 16000))
-    f["fbank_default_dc_syn11"] = ft.fbank(xm, deltas=True, context=True)
-    f["mfcc_default_syn11"] = ft.mfcc(xm)                                      # (2, 660, 81)
-    f["mfcc_cfg4"] = ft.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160)
-    f["mfcc_cfg4_logmels"] = ft.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160,
-                                     log_mels=True)
-    f["deltas_syn"] = ft.compute_deltas(f["fbank_cfg1"][:, :100], win_length=7, pad_mode="reflect")
-    f["context_3_5"] = ft.context_window(f["fbank_cfg1"][:10, :60].astype(np.float32), 3, 5)
+    f = features_goldens(sp, ft, x, msop=1)
     np.savez_compressed(os.path.join(OUT, "features_msop.npz"), **thin(f))
 
     # ---------------- conformer front-end + CMVN (in-repo python: pinned) --------------

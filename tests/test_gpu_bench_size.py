@@ -1,0 +1,87 @@
+"""GPU parity AT THE MEASURED SIZES (missing #6): the bench workload (8192 ragged utterances, one launch) and
+BASELINE.json configs[1] ([1024, 160000] stft + magphase) are compared with the float64 oracle on a seeded SAMPLE of the
+full-size output -- not with a sub-batch of the same kernel."""
+import numpy as np
+import pytest
+
+from oracle import restated as R
+from tests.util import TOL_STFT, record_parity, stft_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ma():
+    import __graft_entry__ as entry
+    entry.build()
+    import mindaudio_b200
+    return mindaudio_b200
+
+
+def test_bench_config_sample_vs_oracle(ma):
+    """bench.py's step: 8192 utterances of 1-20 s (seed 3), fbank + utterance CMVN in one launch; 64 utterances of the
+    output against the oracle chain (conformer fbank, examples/conformer/dataset.py:117-168; mean / std normalisation,
+    examples/ECAPA-TDNN/spec_augment.py:43-70).  Criterion: the de-normalised log-mel meets the PLAIN
+    |d| <= 1e-4 max(1, |ref|) on all but <= 1e-4 of the elements; the normalised values agree to 2e-3 absolute."""
+    torch = pytest.importorskip("torch")
+    import bench
+    from mindaudio_b200 import _lib as L
+    n = 8192
+    lens = bench.chunk_lengths(3, n)
+    total = int(lens.sum())
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    wave = torch.empty(total, dtype=torch.float32, device=dev)
+    for s in range(0, total, 1 << 26):
+        e = min(total, s + (1 << 26))
+        wave[s:e] = torch.round(torch.clamp(0.05 * torch.randn(e - s, generator=gen, device=dev), -1.0, 1.0) * 32768.0)
+    pipe = ma.FbankPipeline(cmvn="utt", mean_norm=True, std_norm=True)
+    assert pipe.plan.is_fast
+    pipe.use_torch_stream()
+    batch = pipe.layout(lens)
+    out = torch.empty((batch.total_frames, 80), dtype=torch.float32, device=dev)
+    pipe.run(wave.data_ptr(), batch, out.data_ptr(), L.WAVE_F32, 1.0)
+    # the same batch staged as PCM16 (the e2e default): bit-identical input values, must give the same features
+    out16 = torch.empty_like(out)
+    pipe.run(wave.to(torch.int16).data_ptr(), batch, out16.data_ptr(), L.WAVE_I16, 1.0)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all())
+    assert float((out - out16).abs().max()) <= 1e-5
+    fo = batch.frame_offsets
+    so = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=so[1:])
+    picks = np.random.default_rng(64).choice(n, size=64, replace=False)
+    gots, refs = [], []
+    for u in picks:
+        w = wave[int(so[u]):int(so[u + 1])].cpu().numpy().astype(np.float64)
+        ref = R.conformer_fbank(w)
+        got = out[int(fo[u]):int(fo[u + 1])].cpu().numpy().astype(np.float64)
+        assert got.shape == ref.shape, u
+        mu, sd = ref.mean(axis=0), ref.std(axis=0)
+        assert np.max(np.abs(got - (ref - mu) / sd)) <= 2e-3, u
+        gots.append((got * sd + mu).ravel())
+        refs.append(ref.ravel())
+    frac, worst = record_parity("bench cfg3 sample (64 of 8192 utterances)", np.concatenate(gots), np.concatenate(refs))
+    assert frac <= 1e-4, (frac, worst)
+    batch.close()
+
+
+def test_cfg2_stft_magphase_sample_vs_oracle(ma):
+    """BASELINE.json configs[1]: spectrum.stft (n_fft 512, hop 256, hann) + magphase on [1024, 160000]; a seeded sample of
+    48 utterances of the full-size result against the oracle (spectrum.py:125-278, 701-735)."""
+    rng = np.random.default_rng(2)
+    x = np.clip(0.05 * rng.standard_normal((1024, 160000), dtype=np.float32), -1.0, 1.0)
+    spec = ma.stft(x, n_fft=512, hop_length=256)
+    assert spec.shape == (1024, 257, 626) and spec.dtype == np.complex64
+    worst = 0.0
+    for u in np.random.default_rng(48).choice(1024, size=48, replace=False):
+        ref = R.stft(x[u], n_fft=512, hop_length=256)
+        worst = max(worst, stft_err(spec[u], ref))
+        assert stft_err(spec[u], ref) <= TOL_STFT, u
+        mag, phase = ma.magphase(spec[u], 1.0)
+        rmag, rphase = R.magphase(ref, 1.0)
+        assert np.max(np.abs(mag - rmag)) <= TOL_STFT * np.max(rmag), u
+        big = rmag > 1e-3 * np.max(rmag)                  # the unit phase of a near-zero bin is ill-conditioned
+        assert np.max(np.abs(phase[big] - rphase[big])) <= 1e-3, u
+    record_parity("cfg2 stft sample (48 of 1024 utterances; value = worst max|dX| / max|X|)", [worst], [0.0], tol=TOL_STFT)

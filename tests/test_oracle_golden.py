@@ -180,3 +180,24 @@ def test_dither_is_deterministic_and_normal():
     assert [int(v) for v in w] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     w = R.philox4x32_10(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
     assert [int(v) for v in w] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+def test_mindspore_golden_script_self_test(tmp_path):
+    """oracle/make_goldens_with_mindspore.py (the script that closes the 'unpinned vs the MindSpore binary' gap where
+    mindspore==2.3.0 exists): its --self-test path runs the same recipe on the restated shim and must reproduce the
+    committed features_msop.npz exactly; without MindSpore the real path refuses with a clear message."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle import make_goldens_with_mindspore as mm
+    rep = mm.main(["--self-test", "--out", str(tmp_path)])
+    assert len(rep) >= 13 and all(v["pins_restatement"] and v["max_abs"] == 0.0 for v in rep.values())
+    assert (tmp_path / "features_selftest.npz").is_file() and (tmp_path / "features_selftest_diff.json").is_file()
+    try:
+        import mindspore  # noqa: F401
+        has_ms = not getattr(mindspore, "__file__", "").startswith(mm.HERE)
+    except ImportError:
+        has_ms = False
+    if not has_ms:
+        with pytest.raises(SystemExit):
+            mm.main(["--out", str(tmp_path)])

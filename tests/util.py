@@ -24,6 +24,30 @@ def mixed_err(got, ref):
     return float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref)))) if ref.size else 0.0
 
 
+# every log-mel comparison of a test session: (test id, elements, fraction outside the PLAIN north-star bound, max mixed error);
+# tests/conftest.py writes it to gpurun_out/parity_report.json at the end of a GPU session
+PARITY_REPORT = []
+MAX_FRAC_OUTSIDE_PLAIN = 1e-4
+
+
+def plain_violations(got, ref, tol=TOL_LOGMEL):
+    """(fraction of elements with |d| > tol * max(1, |ref|), largest |d| / max(1, |ref|)): the north-star bound as written."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if not ref.size:
+        return 0.0, 0.0
+    e = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+    return float(np.mean(e > tol)), float(e.max())
+
+
+def record_parity(kind, got, ref, tol=TOL_LOGMEL):
+    frac, worst = plain_violations(got, ref, tol)
+    PARITY_REPORT.append({"test": os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], "kind": kind,
+                          "elements": int(np.asarray(ref).size), "frac_outside_plain_bound": frac, "max_mixed_err": worst,
+                          "bound": tol})
+    return frac, worst
+
+
 def logmel_err(got, ref, to_ln=1.0):
     """Log-mel criterion, returned as a ratio (pass when <= 1):
 
@@ -39,6 +63,9 @@ def logmel_err(got, ref, to_ln=1.0):
     ref = np.asarray(ref, dtype=np.float64)
     if not ref.size:
         return 0.0
+    # the plain bound first: at most MAX_FRAC_OUTSIDE_PLAIN of the elements may need the floor term at all
+    frac, worst = record_parity("logmel", got, ref)
+    assert frac <= MAX_FRAC_OUTSIDE_PLAIN, "%.3g of %d elements are outside |d| <= 1e-4 max(1, |ref|) (worst %.3g)" % (frac, ref.size, worst)
     ln_ref = ref * to_ln
     peak = np.max(ln_ref, axis=-1, keepdims=True)
     floor = 2e-7 * np.exp(0.5 * (peak - ln_ref)) / to_ln
