@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=8192, help="utterances per step per GPU")
-    ap.add_argument("--cpu-utts", type=int, default=768, help="utterances in the bounded CPU sample")
+    ap.add_argument("--cpu-utts", type=int, default=2048, help="utterances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk-utts", type=int, default=512, help="utterances per chunk of the pipelined host path")
