@@ -195,6 +195,7 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
  * Utterances are processed in chunks of chunk_utts (<= 0: 512) on three internal streams, so the H2D copy of
  * chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap.  Synchronous: returns when out_host
  * is complete.  frame_offsets_host_out: int64[n_utts+1] or NULL.  db_group: MAFE_DBGROUP_NONE / _UTT only.
+ * On an error the call still waits for the chunks it has enqueued; the contents of out_host are then unspecified.
  */
 int mafe_frontend_run_host(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
                            const void* wave_host, int32_t wave_dtype, float wave_scale, float* out_host,

@@ -278,6 +278,7 @@ static int batch_fill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* b, const
   b->tiles_host.clear();
   const int tf = plan->tile_frames;
   int32_t max_group = -1;
+  int64_t max_frames = 0;
   b->so_host[0] = n_utts ? so[0] - rebase : 0;
   for (int32_t u = 0; u < n_utts; ++u) {
     int64_t len = so[u + 1] - so[u];
@@ -286,10 +287,12 @@ static int batch_fill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* b, const
     int64_t t = mafe_plan_num_frames(plan, len);
     MAFE_REQUIRE(t <= INT32_MAX - tf, "utterance %d has too many frames", u);
     b->frame_offsets_host[u + 1] = b->frame_offsets_host[u] + t;
+    max_frames = std::max(max_frames, t);
     for (int64_t f0 = 0; f0 < t; f0 += tf) b->tiles_host.push_back(Tile{u, (int32_t)f0});
     if (utt_group) max_group = std::max(max_group, utt_group[u]);
   }
   b->total_frames = b->frame_offsets_host[n_utts];
+  b->max_utt_frames = max_frames;
   b->total_samples = n_utts ? so[n_utts] - so[0] : 0;
   b->wave_len = n_utts ? so[n_utts] - rebase : 0;
   b->n_tiles = (int32_t)b->tiles_host.size();
@@ -350,6 +353,7 @@ int mafe_batch_destroy(mafe_batch* b) {
   cudaFree(b->utt_stats_dev);
   cudaFree(b->queue_dev);
   cudaFree(b->tile_recs_dev);
+  cudaFree(b->utt_done_dev);
   delete b;
   return MAFE_OK;
 }
@@ -427,7 +431,11 @@ int mafe_frontend_run_host(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* 
     const int64_t n_frames = fo[u1] - fo[u0];
     if (n_frames == 0) continue;
     // stream order protects the lane's buffers: the previous chunk of this lane has been enqueued before
-    if (!l.batch) { l.batch = new (std::nothrow) mafe_batch(); l.batch->device = ctx->device; }
+    if (!l.batch) {
+      l.batch = new (std::nothrow) mafe_batch();
+      if (!l.batch) { set_error("out of host memory"); rc = MAFE_E_OOM; break; }
+      l.batch->device = ctx->device;
+    }
     cudaError_t e;
     if ((size_t)n_samp * es + 64 > l.wave_cap) {
       cudaStreamSynchronize(l.stream);

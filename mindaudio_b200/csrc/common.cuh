@@ -147,6 +147,9 @@ struct mafe_batch {
   int32_t* queue_dev = nullptr;           // persistent-kernel work queue head (1 int)
   void* tile_recs_dev = nullptr;          // v6 kernel: one 64-byte work record per tile (tile_prepare_kernel)
   size_t cap_tile_recs = 0;               // in records
+  int32_t* utt_done_dev = nullptr;        // v6 kernel, fused CMVN: completed tiles per utterance
+  size_t cap_utt_done = 0;
+  int64_t max_utt_frames = 0;             // longest utterance of the batch in frames
 };
 
 namespace mafe {

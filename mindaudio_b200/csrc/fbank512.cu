@@ -836,10 +836,12 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     if ((rc = up(&th->comb3_dev, comb3))) return rc;
     th->v6 = th->v3 && build_v6_program(bins, th->sweep6);
     if (th->v6) {
-      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
-      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
-      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
-      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
     }
     std::vector<int> comb5;
     th->v5 = th->v3 && build_v5_program(bins, th->sweep5, comb5);
@@ -957,6 +959,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     Q.out = out;
     Q.queue_head = b->queue_dev;
     Q.tile_recs = nullptr;
+    Q.utt_done = nullptr; Q.lag = 0; Q.mean_norm = 0; Q.std_norm = 0;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
     if (d.remove_frame_mean) {
       MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
@@ -996,18 +999,44 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
         else tile_prepare_kernel<false><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev);
         MAFE_LAUNCH_CHECK(ctx);
       }
-      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
       static const bool no_tmem = getenv("MAFE_NO_TMEM") != nullptr;           // A/B switch: constants from shared memory
+      static const bool no_fuse = getenv("MAFE_NO_FUSED_CMVN") != nullptr;     // A/B switch: separate CMVN apply kernel
+      const bool fuse = cmvn && !no_tmem && !no_fuse;
+      if (fuse) {
+        if (b->cap_utt_done < (size_t)b->n_utts) {   // grow-only
+          if (b->utt_done_dev) MAFE_CUDA_CHECK(cudaFree(b->utt_done_dev));
+          b->utt_done_dev = nullptr; b->cap_utt_done = 0;
+          const size_t cap = (size_t)b->n_utts + (size_t)b->n_utts / 4 + 16;
+          MAFE_CUDA_CHECK(cudaMalloc((void**)&b->utt_done_dev, cap * sizeof(int32_t)));
+          b->cap_utt_done = cap;
+        }
+        MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_done_dev, 0, sizeof(int32_t) * b->n_utts, ctx->stream));
+        Q.utt_done = b->utt_done_dev;
+        // the normalisation of a tile trails its computation by `lag` queue items: at least the longest utterance in tiles
+        // (deadlock freedom), plus three rounds of the resident CTAs (a finished tile is published one iteration later; the
+        // wait is then almost never entered).  ~1.4 k tiles = 14 MB of features + 28 MB of waveform in between: L2 resident
+        Q.lag = (int)((b->max_utt_frames + kTileFrames - 1) / kTileFrames) + 3 * grid3 + 64;
+        Q.mean_norm = d.utt_cmvn_mean; Q.std_norm = d.utt_cmvn_std;
+      }
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      if (fuse) {
+        if (wave_dtype == MAFE_WAVE_I16)
+          fbank512_v6_kernel<true, true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+        else
+          fbank512_v6_kernel<false, true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+        MAFE_LAUNCH_CHECK(ctx);
+        return MAFE_OK;   // features are final: no apply kernel
+      }
       if (no_tmem) {
         if (wave_dtype == MAFE_WAVE_I16)
-          fbank512_v6_kernel<true, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+          fbank512_v6_kernel<true, false, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
         else
-          fbank512_v6_kernel<false, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+          fbank512_v6_kernel<false, false, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
       } else {
         if (wave_dtype == MAFE_WAVE_I16)
-          fbank512_v6_kernel<true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+          fbank512_v6_kernel<true, true, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
         else
-          fbank512_v6_kernel<false, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+          fbank512_v6_kernel<false, true, false><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
       }
       MAFE_LAUNCH_CHECK(ctx);
     } else if (halfwarp && th->v5) {

@@ -36,6 +36,10 @@ struct V2Params {
   float* out;
   int* queue_head;               // dynamic work queue: next unclaimed tile index
   const void* tile_recs;         // v6: TileInfo[n_tiles], prepared per step by tile_prepare_kernel
+  // v6 with the utterance CMVN applied inside the persistent kernel (fbank512_v6.cuh, FUSE):
+  int* utt_done;                 // [n_utts] tiles of the utterance whose features and statistics are complete (zeroed per step)
+  int lag;                       // the CTA that claims tile w also normalises tile w - lag; >= the longest utterance in tiles
+  int mean_norm, std_norm;
 };
 
 struct TileInfo {  // geometry of one work item, prepared by thread 0 one iteration ahead
@@ -45,6 +49,7 @@ struct TileInfo {  // geometry of one work item, prepared by thread 0 one iterat
   int utt, nf, shift;
   float neg_mu;
   uint32_t bytes;     // size of the bulk copy (multiple of 16; 0: nothing can be bulk-copied)
+  int T;              // frames of the tile's utterance
 };
 static_assert(sizeof(TileInfo) <= 64, "TileInfo slot");
 
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(256) tile_prepare_kernel(const V2Params P, Til
   r.shift = src.shift;
   r.neg_mu = P.remove_mean ? -(float)(P.utt_sum[tile.utt] / ((double)T * (double)kV2Flen)) : 0.f;
   r.bytes = src.bytes;
+  r.T = T;
   recs[i] = r;
 }
 

@@ -46,10 +46,13 @@ struct V6Smem {
   static constexpr size_t kW512 = kWin + sizeof(float) * 400;
   static constexpr size_t kW256 = kW512 + sizeof(float2) * 256;
   static constexpr size_t kBar = kW256 + sizeof(float2) * 256;            // 2 mbarriers + 2 claimed indices
-  static constexpr size_t kInfo = kBar + 32;                              // 2 x TileInfo
-  static constexpr size_t kTotal = kInfo + 2 * 64;
+  static constexpr size_t kInfo = kBar + 32;                              // 2 x TileInfo + the record of the tile being normalised
+  static constexpr size_t kNorm = kInfo + 3 * 64;                         // float[2][80]: mean, 1 / std of that tile's utterance
+  static constexpr size_t kABar = kNorm + sizeof(float) * 2 * kV2Mels;    // mbarrier of its bulk copy
+  static constexpr size_t kTotal = kABar + 16;
 };
 static_assert(3 * (V6Smem::kTotal + 1024) <= 228 * 1024, "3 CTAs per SM");
+static_assert(V6Smem::kInfo % 16 == 0 && V6Smem::kNorm % 16 == 0 && V6Smem::kABar % 8 == 0, "smem alignment (cp.async / float4 / mbarrier)");
 static_assert(V6Smem::kRaw % 128 == 0 && V6Smem::kRawInZ >= 6 * kV2Mels * 4, "landing zone vs the CMVN partial sums");
 static_assert(V6Smem::kZ % 16 == 0 && V6Smem::kBar % 8 == 0 && V6Smem::kWin % 16 == 0 && V6Smem::kPlanes % 16 == 0, "smem alignment");
 static_assert(15 * kRowStride + 15 < kV6Slot, "the 16 x 17 transpose scratch fits the slot");
@@ -245,7 +248,27 @@ __device__ __forceinline__ void v6_mel(const V6Sweep& S, const float* __restrict
   if (m < m1) plane_col[m * kPlaneStride] = v6_dot<N>(my_row + S.start[m], w);
 }
 
-template <bool I16, bool TM>
+// FUSE: the utterance CMVN is applied INSIDE this kernel.  The tile queue runs lag items past the last tile; the CTA that
+// claims item w also owns the normalisation of tile w - lag: by then that tile's utterance is (almost always) complete --
+// every finished tile bumps utt_done[utt] with release semantics, the normalising CTA acquires it (and spins in the rare
+// case it is early; lag >= the longest utterance in tiles makes the wait deadlock free: everything it waits for has been
+// claimed by a resident CTA).  The tile's 10 KB of raw log-mel come back from L2 (written ~lag tiles = 20 MB ago) by one
+// bulk copy into the then idle waveform buffer, are normalised with the utterance's mean / inverse deviation and stored
+// for good: the separate apply kernel -- a second read and write of the whole feature matrix through HBM -- is gone.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_relaxed_inc(int* p) { asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory"); }
+
+
+template <bool I16, bool TM, bool FUSE>
 __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __grid_constant__ V2Params P,
                                                                       const __grid_constant__ V6Sweep S) {
   using SM = V6Smem;
@@ -262,6 +285,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
   int* s_work = reinterpret_cast<int*>(smem + SM::kBar) + 4;   // [2] claimed tile index per parity
   TileInfo* info = reinterpret_cast<TileInfo*>(smem + SM::kInfo);
+  TileInfo* ainfo = info + 2;                                       // FUSE: record of the tile being normalised
+  float* s_norm = reinterpret_cast<float*>(smem + SM::kNorm);
+  uint64_t* abar = reinterpret_cast<uint64_t*>(smem + SM::kABar);
   constexpr int ES = I16 ? 2 : 4;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,6 +299,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(abar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (TM && warp == 0) {
@@ -349,12 +376,23 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     }
   };
 
+  const int n_items = FUSE ? P.n_tiles + P.lag : P.n_tiles;   // queue length: lag normalisation-only items at the end
   if (tid == 0) {   // prologue: the first tile, all stages back to back
     nx_w = atomicAdd(P.queue_head, 1);
     s_work[0] = nx_w;
     if (nx_w < P.n_tiles) { fetch_rec(0); issue_tile(0); }
   }
   __syncthreads();
+  // service thread (the last thread of the CTA: its warp has only half a share of phase C): utterance of the tile this CTA
+  // finished last and not yet published; state of the current duty
+  const bool svc = tid == kFastThreads - 1;
+  int prev_utt = -1, a_flag = 0, a_need = 0;
+  auto publish = [&]() {   // the fence orders everything this CTA wrote so far before the counter bump (cumulative over barriers)
+    __threadfence();
+    red_relaxed_inc(P.utt_done + prev_utt);
+    prev_utt = -1;
+  };
+  uint32_t a_cnt = 0;                          // normalisation duties done by this CTA (parity of abar)
 
   const int t = lane & 15;
   const int pair = warp * 2 + (lane >> 4);
@@ -373,12 +411,26 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   // iteration it uses info / barrier slot it & 1; the slot's mbarrier completes its (it >> 1)-th phase
   for (uint32_t it = 0;; ++it) {
     const int buf = it & 1;
-    if (s_work[buf] >= P.n_tiles) break;
-    if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1 (issue): claim the next tile
+    const int w = s_work[buf];
+    if (w >= n_items) break;
+    const bool main_tile = !FUSE || w < P.n_tiles;
+    const bool duty = FUSE && w >= P.lag;              // normalise tile w - lag
+    if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1 (issue): claim the next item
+    if (FUSE && svc) {
+      if (duty) {                          // the duty tile's record -> ainfo (asynchronous)
+        const uint32_t dst = smem_u32(ainfo);
+        const unsigned char* srcp = reinterpret_cast<const unsigned char*>(recs + (w - P.lag));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * q), "l"(srcp + 16 * q) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
     const TileInfo cur = info[buf];
     const uint32_t utt = (uint32_t)cur.utt;
     const int nf = cur.nf;
-
+    float neg_mu = 0.f;
+    if (main_tile) {
     // wait for this tile's bytes
     mbar_wait(&bars[buf], (it >> 1) & 1);
     // scalar patch-up of what the 16 B-granular bulk copy could not cover (end of the flat array)
@@ -445,9 +497,19 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
         }
       }
     }
-    const float neg_mu = cur.neg_mu;
+    neg_mu = cur.neg_mu;
+    }   // main_tile (pass P)
     __syncthreads();
     if (tid == 0) s_work[buf ^ 1] = nx_w;   // stage 2: the claim has arrived during pass P -> publish it
+    if (FUSE && svc && duty) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      a_need = (ainfo->T + kTileFrames - 1) / kTileFrames;
+      // Relaxed (L2) load, consumed after the FFT phase.  The data reads that depend on it -- the bulk copy and the .cg
+      // loads of the statistics -- are issued after the branch on its value and go to L2, where the writer's fence put
+      // the data before the counter: no acquire fence on the fast path (the slow path spins with ld.acquire).
+      a_flag = ld_relaxed(P.utt_done + ainfo->utt);
+    }
+    if (main_tile) {
 
     // ---- FFT phase: both 256-point halves of the pair, powers of the lane's bins, P rows ----
     {
@@ -510,10 +572,32 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
         }
       }
     }
+    }   // main_tile (FFT phase)
+    if (FUSE && svc && duty && a_flag != a_need) {
+      // early (rare): first publish what this CTA still holds back -- the utterance may be waiting for exactly that -- then
+      // spin; every tile waited for has been claimed by a resident CTA (lag >= the longest utterance), which publishes it
+      // within one iteration or before it waits itself
+      if (prev_utt >= 0) publish();
+      do { a_flag = ld_acquire(P.utt_done + ainfo->utt); } while (a_flag != a_need);
+    }
     __syncthreads();
     // stage 3: the next tile's record travels to the other info slot during the mel projection
     if (tid == 0 && nx_w < P.n_tiles) fetch_rec(buf ^ 1);
+    double st_s1 = 0.0, st_s2 = 0.0;
+    if (FUSE && duty) {
+      if (svc) {   // the duty tile's raw log-mel rows come back from L2 into the (now idle) waveform buffer
+        const uint32_t bytes = (uint32_t)ainfo->nf * (kV2Mels * 4);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(abar, bytes);
+        tma_bulk_g2s(ybuf, P.out + ainfo->out_row * (int64_t)kV2Mels, bytes, abar);
+      }
+      if (tid < kV2Mels) {   // moments of its utterance: loaded now, used after the mel projection (L2 latency hidden)
+        st_s1 = __ldcg(&P.utt_stats[((size_t)ainfo->utt * 2) * kV2Mels + tid]);
+        st_s2 = __ldcg(&P.utt_stats[((size_t)ainfo->utt * 2 + 1) * kV2Mels + tid]);
+      }
+    }
 
+    if (main_tile) {
     // ---- mel projection: lane = frame, this warp's filters ----
     switch (nw) {   // warp uniform
       case 1: v6_mel<1>(S, my_row, planes + lane, f_begin, f_end, wbase); break;
@@ -525,13 +609,34 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
       case 7: v6_mel<7>(S, my_row, planes + lane, f_begin, f_end, wbase); break;
       default: v6_mel<8>(S, my_row, planes + lane, f_begin, f_end, wbase); break;
     }
+    }   // main_tile (mel projection)
+    if (FUSE && duty && tid < kV2Mels) {
+      // mean / inverse deviation of the duty tile's utterance.  The moments are double (cancellation in s2 / T - mean^2);
+      // the double DIVISIONS and the square root of cmvn_utt_apply_kernel would sit on the critical path of three warps
+      // in every tile, so: 1 / T by one Newton step on the float reciprocal (exact to ~1e-14), 1 / sqrt(var) by MUFU.RSQ
+      // + one Newton step in float (<= 1 ulp of the float that is stored anyway).
+      const int T = ainfo->T;
+      const double dT = (double)T;
+      double r = (double)(1.0f / (float)T);
+      r = r * (2.0 - dT * r);
+      const double mean = st_s1 * r;
+      const float var = (float)fmax(fma(st_s2, r, -mean * mean), 0.0);
+      float y = rsqrtf(var);
+      if (var > 0.f) y = y * (1.5f - 0.5f * var * y * y);
+      s_norm[tid] = P.mean_norm ? (float)mean : 0.f;
+      s_norm[kV2Mels + tid] = P.std_norm ? y : 1.f;
+    }
     __syncthreads();
     // the Z region has been read for the last time -> the next tile's waveform may land in its upper part
     if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
+    // the tile this CTA finished in the previous iteration: its feature stores and statistics atomics were issued before
+    // barriers passed since -> publish it (here, where the service thread's warp has slack)
+    if (FUSE && svc && prev_utt >= 0) publish();
+    float* part = stage;  // [3][2][80] per-group CMVN partial sums (lower part of the Z region, free after the sweep)
+    if (main_tile) {
 
     // ---- phase C: log, store; thread = (frame group g, filter m).  For one frame the 80 threads of a group write
     // 320 contiguous bytes straight to global memory. ----
-    float* part = stage;  // [3][2][80] per-group CMVN partial sums (lower part of the Z region, free after the sweep)
     if (tid < 3 * kV2Mels) {
       const int g = cg, m = cm;
       const float* q = planes + m * kPlaneStride + g;
@@ -578,14 +683,33 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
         part[(g * 2 + 1) * kV2Mels + m] = s2;
       }
     }
+    }   // main_tile (phase C)
+    if (FUSE && duty) {   // normalise the duty tile: y -> (y - mean) / std, 16 bytes per thread and step
+      mbar_wait(abar, a_cnt & 1);
+      ++a_cnt;
+      const int n4 = ainfo->nf * (kV2Mels / 4);
+      const float4* y4 = reinterpret_cast<const float4*>(ybuf);
+      const float4* nm4 = reinterpret_cast<const float4*>(s_norm);
+      float4* o4 = reinterpret_cast<float4*>(P.out + ainfo->out_row * (int64_t)kV2Mels);
+      for (int q = tid; q < n4; q += kFastThreads) {
+        const int m4 = q % (kV2Mels / 4);
+        const float4 v = y4[q], mu = nm4[m4], iv = nm4[kV2Mels / 4 + m4];
+        o4[q] = make_float4((v.x - mu.x) * iv.x, (v.y - mu.y) * iv.y, (v.z - mu.z) * iv.z, (v.w - mu.w) * iv.w);
+      }
+    }
     __syncthreads();   // the next tile's geometry (thread 0, above) and the partial sums are visible
+    if (FUSE && svc && main_tile) prev_utt = cur.utt;
     // per-utterance CMVN statistics: one double atomic per (filter, moment)
-    if (P.utt_stats != nullptr && tid < 2 * kV2Mels) {
+    if (main_tile && P.utt_stats != nullptr && tid < 2 * kV2Mels) {
       const int m = tid % kV2Mels, which = tid / kV2Mels;
       const double sum = (double)part[which * kV2Mels + m] + (double)part[(2 + which) * kV2Mels + m] +
                          (double)part[(4 + which) * kV2Mels + m];
       atomicAdd(&P.utt_stats[((size_t)utt * 2 + which) * kV2Mels + m], sum);
     }
+  }
+  if (FUSE) {   // the last tile of this CTA
+    __syncthreads();
+    if (svc && prev_utt >= 0) publish();
   }
   if (TM) {
     __syncthreads();   // every warp has issued its last TMEM load
