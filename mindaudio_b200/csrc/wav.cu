@@ -193,8 +193,9 @@ extern "C" int mafe_wav_parse(const void* bytes, int64_t n_bytes, double offset_
         int64_t count = raw ? size : n_samples;
         if (ignore <= count) count -= ignore;
         if (duration_s != 0.0 && duration_s * (double)(uint32_t)info->sample_rate < (double)count) {
-          if (duration_s < 0) { set_error("mafe_wav_parse: negative duration"); return fail(info, MAFE_WAV_ERR_VALUE); }
-          count = (int64_t)(duration_s * (double)(uint32_t)info->sample_rate);
+          // a negative duration makes the reference's count negative and np.fromfile(count < 0) reads to the end of the
+          // file (io.py:500-503): keep the full count
+          if (duration_s > 0) count = (int64_t)(duration_s * (double)(uint32_t)info->sample_rate);
         }
         const int64_t avail = start < f.n ? (f.n - start) / item : 0;
         items = count < avail ? count : avail;                               // np.fromfile stops at EOF
@@ -322,6 +323,8 @@ struct mafe_wav_files {
   std::vector<mafe_wav_info> infos;
   std::vector<int64_t> offsets;
   std::vector<std::string> paths;
+  struct Ident { dev_t dev = 0; ino_t ino = 0; off_t size = 0; struct timespec mtime = {0, 0}; };
+  std::vector<Ident> idents;   // identity of every file at walk time: the pack refuses a file replaced or rewritten since
   int n_threads = 0;
   ~mafe_wav_files() {
     for (auto& m : maps) if (m.p && m.n) munmap(m.p, m.n);
@@ -339,6 +342,7 @@ extern "C" int mafe_wav_files_open(const char* const* paths, int32_t n_files, in
   h->maps.resize((size_t)n_files);
   h->ptrs.assign((size_t)n_files, nullptr);
   h->sizes.assign((size_t)n_files, 0);
+  h->idents.resize((size_t)n_files);
   h->n_threads = n_threads;
   for (int32_t k = 0; k < n_files; ++k) h->paths.emplace_back(paths[k]);
   int hw = (int)std::thread::hardware_concurrency();
@@ -374,6 +378,8 @@ extern "C" int mafe_wav_files_open(const char* const* paths, int32_t n_files, in
         h->ptrs[(size_t)k] = &kEmpty;
       }
       h->sizes[(size_t)k] = (int64_t)st.st_size;
+      h->idents[(size_t)k].dev = st.st_dev; h->idents[(size_t)k].ino = st.st_ino;
+      h->idents[(size_t)k].size = st.st_size; h->idents[(size_t)k].mtime = st.st_mtim;
       close(fd);
     }
   };
@@ -422,6 +428,12 @@ extern "C" int mafe_wav_files_pack(mafe_wav_files* h, void* stage, int64_t stage
       const int fd = open(h->paths[(size_t)k].c_str(), O_RDONLY | O_CLOEXEC);
       int64_t pos = h->infos[(size_t)k].data_offset;
       bool ok = fd >= 0;
+      if (ok) {   // the same file as the one that was walked? (a path can be replaced or rewritten between open and pack)
+        struct stat st;
+        const mafe_wav_files::Ident& id = h->idents[(size_t)k];
+        ok = fstat(fd, &st) == 0 && st.st_dev == id.dev && st.st_ino == id.ino && st.st_size == id.size &&
+             st.st_mtim.tv_sec == id.mtime.tv_sec && st.st_mtim.tv_nsec == id.mtime.tv_nsec;
+      }
       while (ok && nb > 0) {
         const ssize_t got = pread(fd, dst, (size_t)nb, (off_t)pos);
         if (got <= 0) { if (got < 0 && errno == EINTR) continue; ok = false; break; }

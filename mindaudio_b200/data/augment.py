@@ -63,8 +63,8 @@ def time_stretch(waveforms, rate=None):
     waveforms = np.asarray(waveforms)
     n_fft, hop = 512, 128
     x, lead = _flatten_batch(waveforms)
-    if x.shape[-1] < n_fft // 2 + 1:
-        raise ValueError("n_fft={} is too large for input signal of length={}".format(n_fft, x.shape[-1]))
+    if n_fft > x.shape[-1]:   # the reference goes through stft(center=True), which refuses these (spectrum.py:182-187)
+        raise ValueError("n_fft={} is too small for input signal of length={}".format(n_fft, x.shape[-1]))
     length_stretch = int(round(waveforms.shape[-1] / rate))
     eng = get_engine()
     win = T.analysis_window("hann", n_fft, n_fft)

@@ -140,7 +140,8 @@ class FbankPipeline:
                            wave_scale, chunk_utts)
         return out, fo
 
-    def features_padded(self, waves, max_len=None, padding_value=0.0, wave_scale=1.0, spec_aug_conf=None, rng=None):
+    def features_padded(self, waves, max_len=None, padding_value=0.0, wave_scale=1.0, spec_aug_conf=None, rng=None,
+                        sort_by_length=False):
         """Front-end + collate in one device round trip (examples/conformer/dataset.py:456-491, 563-569, 616-621):
         list of 1-D waveforms -> ``(xs_pad [B, max_len, mel_bin] float32, xs_lengths [B] int32, xs_masks [B, 1, max_len]
         float32)``.  The ragged feature matrix never leaves the GPU: the padded batch and the mask are written by
@@ -148,7 +149,13 @@ class FbankPipeline:
         ``pad_sequence`` does; ``xs_lengths`` are the untruncated frame counts, as in the reference.
         ``spec_aug_conf`` (dataset.py:493-534) masks time / frequency rectangles of the ragged features on the device
         before the padding; the positions come from ``rng`` (a ``random.Random``; default the ``random`` module) with
-        the reference's call sequence."""
+        the reference's call sequence.
+
+        ``sort_by_length=True`` reproduces the reference collate to the letter: ``extract_feature`` sorts the utterances by
+        frame count, longest first (``np.argsort(lengths)[::-1]``, dataset.py:483-489), BEFORE ``spec_aug`` and
+        ``pad_sequence`` -- so the random draws land on the utterances in that order and the batch rows come out in it.
+        A fourth value, ``order`` (row i = input utterance ``order[i]``), is then returned.  With the default ``False`` rows
+        and draws follow the input order (callers that pre-sort get the reference's result either way)."""
         lens = [len(w) for w in waves]
         dt = np.int16 if waves and all(np.asarray(w).dtype == np.int16 for w in waves) else np.float32
         flat = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=dt) for w in waves])) if waves else np.zeros(0, dt)
@@ -159,18 +166,19 @@ class FbankPipeline:
             d_w = eng.buf("wave", max(flat.nbytes, 16))
             keep = eng.h2d(d_w, flat)
             res = self._padded_from_device(d_w, L.WAVE_I16 if dt == np.int16 else L.WAVE_F32, so, max_len, padding_value,
-                                           wave_scale, spec_aug_conf, rng)
+                                           wave_scale, spec_aug_conf, rng, sort_by_length)
             del keep
         return res
 
-    def features_from_wav(self, files, max_len=None, padding_value=0.0, spec_aug_conf=None, rng=None, speeds=None):
+    def features_from_wav(self, files, max_len=None, padding_value=0.0, spec_aug_conf=None, rng=None, speeds=None,
+                          sort_by_length=False):
         """WAV files -> padded feature batch, the whole ``read -> * (1 << 15) -> compute_fbank_feats -> CMVN ->
         spec_aug -> pad_sequence`` chain of the conformer input pipeline (examples/conformer/dataset.py:384-395,
         456-534, 563-621) with one upload (the files' PCM payloads, 2 bytes / sample for PCM16) and one download (the
         padded batch + mask).  ``files``: paths or binary file objects of mono WAV files
         (:func:`mindaudio_b200.data.io.load_batch`); ``speeds``: optional per-file speed-perturbation factors
         (dataset.py:391-404, Fourier resampling on the device).  Returns ``(xs_pad, xs_lengths, xs_masks)`` like
-        :meth:`features_padded`."""
+        :meth:`features_padded` (``sort_by_length=True``: the reference's longest-first order, plus ``order``)."""
         from .data.io import load_batch
         eng = self.eng
         with eng.lock:
@@ -179,9 +187,10 @@ class FbankPipeline:
                 if sr != self.sample_rate:
                     raise ValueError("features_from_wav: file sampled at %d Hz, pipeline built for %d Hz" % (sr, self.sample_rate))
             return self._padded_from_device(wb.wave_dev, wb.dtype, wb.sample_offsets, max_len, padding_value, wb.wave_scale,
-                                            spec_aug_conf, rng)
+                                            spec_aug_conf, rng, sort_by_length)
 
-    def _padded_from_device(self, d_w, wave_dtype, so, max_len, padding_value, wave_scale, spec_aug_conf, rng):
+    def _padded_from_device(self, d_w, wave_dtype, so, max_len, padding_value, wave_scale, spec_aug_conf, rng,
+                            sort_by_length=False):
         """front-end + spec_aug + pad_sequence on a device-resident flat waveform batch (engine lock held)."""
         eng = self.eng
         n = len(so) - 1
@@ -189,6 +198,9 @@ class FbankPipeline:
             b = eng.batch(self.plan, so)
             try:
                 xs_lengths = np.diff(b.frame_offsets).astype(np.int32)
+                # the reference's batch order (dataset.py:483-489); the device works in input order, the draws of spec_aug
+                # are dealt in `order` and the rows are permuted on the way out
+                order = np.argsort(xs_lengths)[::-1] if sort_by_length else None
                 if max_len is None:
                     max_len = int(xs_lengths.max()) if n else 0
                 xs_pad = np.empty((n, max_len, self.mel_bin), dtype=np.float32)
@@ -202,7 +214,10 @@ class FbankPipeline:
                     keep_r = None
                     if spec_aug_conf:
                         from .data.masking import spec_aug_rects
-                        rects = spec_aug_rects([(int(t), self.mel_bin) for t in xs_lengths], spec_aug_conf, rng)
+                        seq = xs_lengths if order is None else xs_lengths[order]
+                        rects = spec_aug_rects([(int(t), self.mel_bin) for t in seq], spec_aug_conf, rng)
+                        if order is not None and len(rects):
+                            rects[:, 0] = order[rects[:, 0]].astype(rects.dtype)
                         if len(rects):
                             d_r = eng.buf("rects", rects.nbytes)
                             keep_r = eng.h2d(d_r, rects)
@@ -214,6 +229,8 @@ class FbankPipeline:
                     eng.d2h(xs_masks, d_m)
                     eng.sync()
                     del keep_r
+                if order is not None:
+                    return xs_pad[order], xs_lengths[order], xs_masks[order], order
                 return xs_pad, xs_lengths, xs_masks
             finally:
                 b.close()

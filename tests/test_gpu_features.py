@@ -353,3 +353,19 @@ def test_hpss_harmonic(ma):
     with pytest.raises(TypeError):
         ma.hpss(spec, margin=0.5)
 
+
+
+def test_padded_pipeline_reference_order(ma):
+    """the reference collate sorts by frame count, longest first, BEFORE spec_aug / pad_sequence
+    (examples/conformer/dataset.py:483-489).  sort_by_length=True must equal a call on the pre-sorted list (same seed),
+    and return the order."""
+    import random
+    rng = np.random.default_rng(21)
+    waves = [np.round(synth(100 + i, (int(n),)) * 32768).astype(np.float32) for i, n in enumerate(rng.integers(4000, 30000, size=6))]
+    conf = {"num_t_mask": 2, "num_f_mask": 2, "max_t": 20, "max_f": 10}
+    pipe = ma.FbankPipeline(cmvn="utt")
+    xs, ln, mk, order = pipe.features_padded(waves, spec_aug_conf=conf, rng=random.Random(5), sort_by_length=True)
+    frames = np.array([(len(w) - 400) // 160 + 1 for w in waves])
+    assert np.array_equal(order, np.argsort(frames)[::-1]) and np.array_equal(ln, frames[order])
+    xs2, ln2, mk2 = pipe.features_padded([waves[i] for i in order], spec_aug_conf=conf, rng=random.Random(5))
+    assert np.array_equal(ln, ln2) and np.array_equal(mk, mk2) and np.allclose(xs, xs2, atol=2e-5)

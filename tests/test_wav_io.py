@@ -248,3 +248,12 @@ def test_file_walk_matches_bytes_walk(tmp_path):
     with pytest.raises(ValueError, match="empty.wav"):
         P._FileWalk([str(empty)]).walk()
     assert P._FileWalk([]).walk().offsets.tolist() == [0]
+
+
+def test_negative_duration_reads_to_the_end():
+    """the reference does not raise on duration < 0 -- ``count = int(duration * samplerate)`` goes negative and
+    ``np.fromfile`` reads the whole chunk (io.py:500-503).  The native walk mirrors that."""
+    from mindaudio_b200.data import io as P
+    blob = W.corpus()["pcm16"][0]
+    full = P.wav_info(blob, 0.0, None, False).n_items
+    assert P.wav_info(blob, 0.0, -0.5, False).n_items == full == R.wav_read(blob, 0, -0.5, False)[0].size
