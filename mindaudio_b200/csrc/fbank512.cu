@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(256) frame_sum_fast_kernel(FastParams P, doubl
 #include "stft512.cuh"
 #include "fbank400.cuh"
 #include "stftn16.cuh"
+#include "front2048.cuh"
 namespace mafe {
 
 struct FastTablesHost {
@@ -339,6 +340,11 @@ struct FastTablesHost {
   V3Sweep sweep;          // sweep program of the v3 kernel (kernel-parameter bank)
   bool v3 = false;        // the v3 kernel's compact planes can hold this filterbank
   int* comb3_dev = nullptr;   // v3: plane rows (A | B << 8) of every filter
+  bool f2048 = false;         // n_fft = 2048 front-end (front2048_kernel)
+  int j0_2048 = 0, j1_2048 = 16, mw_floats_2048 = 0;
+  float2* tw2048_dev = nullptr;
+  int *mstart_dev = nullptr, *mcount_dev = nullptr, *moff_dev = nullptr;
+  float* mweights_dev = nullptr;
   V6Sweep sweep6;             // dense per-filter mel program of the v6 kernel (kernel-parameter bank)
   bool v6 = false;
   V5Sweep sweep5;             // half-warp variant (experimental, MAFE_HALFWARP_SWEEP)
@@ -704,7 +710,17 @@ static bool f400_plan_supported(const mafe_frontend_desc* d) {
   return build_bins_n(d, kBins400, 1.0f, bins) && build_f400_program(bins, d->n_mels, sw, comb);
 }
 
+// n_fft = 2048: every output kind, hop <= 512, no pre-emphasis / frame-mean removal / dither (front2048.cuh)
+static bool f2048_plan_supported(const mafe_frontend_desc* d) {
+  if (d->n_fft != kN2048 || d->frame_len != kN2048 || d->hop < 1 || d->hop > kMaxHop2048) return false;
+  if (d->preemph != 0.0 || d->remove_frame_mean || d->dither != 0.f) return false;
+  if (d->out_kind == MAFE_OUT_POWER && !(d->power > 0.f)) return false;
+  if (d->out_kind >= MAFE_OUT_MEL && (!(d->power > 0.f) || d->n_mels < 1)) return false;
+  return true;
+}
+
 bool fast_plan_supported(const mafe_frontend_desc* d) {
+  if (f2048_plan_supported(d)) return true;
   if (stft_plan_supported(d)) return true;
   if (stftn_plan_supported(d)) return true;
   if (f400_plan_supported(d)) return true;
@@ -735,7 +751,7 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
   th->ylen = (kTileFrames - 1) * d->hop + d->frame_len;
   p->fast_tables = th;
   th->stft = stft_plan_supported(d);
-  std::vector<float> win(kNfft, 0.f);
+  std::vector<float> win(std::max(kNfft, d->frame_len), 0.f);
   for (int i = 0; i < d->frame_len; ++i) win[i] = th->stft ? 0.5f * d->spec_scale * d->window[i] : d->window[i];
   std::vector<float2> w512(256), w256(256);
   for (int n = 0; n < 256; ++n) {
@@ -748,6 +764,46 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       w256[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
     }
   int rc;
+  th->f2048 = f2048_plan_supported(d);
+  if (th->f2048) {
+    std::vector<float> w2(kN2048);
+    int lo = kN2048, hi = 0;
+    for (int i = 0; i < kN2048; ++i) {
+      w2[i] = 0.5f * d->spec_scale * d->window[i];   // 1/2: the pair separation leaves 2X
+      if (d->window[i] != 0.f) { lo = std::min(lo, i); hi = std::max(hi, i + 1); }
+    }
+    th->j0_2048 = lo < hi ? lo / 128 : 0;
+    th->j1_2048 = lo < hi ? (hi + 127) / 128 : 0;
+    std::vector<float2> tw(kN2048);
+    for (int j = 0; j < kN2048; ++j) {
+      const double a = -2.0 * M_PI * (double)j / (double)kN2048;
+      tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if ((rc = up(&th->dev.window, w2))) return rc;
+    if ((rc = up(&th->tw2048_dev, tw))) return rc;
+    if (d->out_kind >= MAFE_OUT_MEL) {
+      std::vector<int> ms(d->n_mels, 0), mc(d->n_mels, 0), mo(d->n_mels, 0);
+      std::vector<float> mw;
+      for (int m = 0; m < d->n_mels; ++m) {
+        int k0 = -1, k1 = -1;
+        for (int k = 0; k < kBins2048; ++k)
+          if (d->mel_fb[(size_t)m * kBins2048 + k] != 0.f) { if (k0 < 0) k0 = k; k1 = k + 1; }
+        if (k0 < 0) { k0 = 0; k1 = 0; }
+        // the support in whole groups of 4 bins (16-byte weight loads), zero weights pad it; rows have kPRow2048 >= 1028 floats
+        int cnt = (k1 - k0 + 3) & ~3;
+        if (k0 + cnt > kPRow2048) k0 = kPRow2048 - cnt;
+        ms[m] = k0; mc[m] = cnt; mo[m] = (int)mw.size();
+        for (int k = k0; k < k0 + cnt; ++k) mw.push_back(k < kBins2048 ? d->mel_fb[(size_t)m * kBins2048 + k] : 0.f);
+      }
+      th->mw_floats_2048 = (int)mw.size();
+      if ((rc = up(&th->mstart_dev, ms))) return rc;
+      if ((rc = up(&th->mcount_dev, mc))) return rc;
+      if ((rc = up(&th->moff_dev, mo))) return rc;
+      if ((rc = up(&th->mweights_dev, mw))) return rc;
+    }
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(front2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2048SmemBudget));
+    return MAFE_OK;
+  }
   th->stftn = stftn_plan_supported(d);
   if (th->stftn) {
     const int N1 = th->stftn, N = 16 * N1, B = N1 == 25 ? 5 : 4;   // N1 = 5 x B: twiddles W_N1^(j1 k1), j1 = 1..4, k1 = 1..B-1
@@ -864,6 +920,7 @@ void fast_plan_free(mafe_plan* p) {
   cudaFree(th->comb3_dev);
   cudaFree(th->comb5_dev);
   cudaFree(th->tw400_dev);
+  cudaFree(th->tw2048_dev); cudaFree(th->mstart_dev); cudaFree(th->mcount_dev); cudaFree(th->moff_dev); cudaFree(th->mweights_dev);
   delete th;
   p->fast_tables = nullptr;
 }
@@ -878,6 +935,39 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
   if (b->n_tiles == 0) return MAFE_OK;
   const FastTablesHost* th = static_cast<const FastTablesHost*>(p->fast_tables);
   const mafe_frontend_desc& d = p->d;
+  if (th->f2048) {
+    F2048Params F;
+    F.wave = wave; F.wave_dtype = wave_dtype; F.wave_scale = wave_scale;
+    F.sample_offsets = b->sample_offsets_dev; F.frame_offsets = b->frame_offsets_dev; F.tiles = b->tiles_dev;
+    F.n_tiles = b->n_tiles; F.hop = d.hop; F.center = d.center; F.pad_mode = d.pad_mode;
+    F.j0 = th->j0_2048; F.j1 = th->j1_2048;
+    F.window = th->dev.window; F.tw = th->tw2048_dev;
+    F.out_kind = d.out_kind == MAFE_OUT_MFCC ? MAFE_OUT_LOGMEL : d.out_kind;
+    F.power = d.power; F.n_mels = d.n_mels;
+    F.mstart = th->mstart_dev; F.mcount = th->mcount_dev; F.moff = th->moff_dev; F.mweights = th->mweights_dev;
+    F.log_kind = d.out_kind == MAFE_OUT_MEL ? MAFE_LOG_NONE : d.log_kind;
+    F.log_arg = d.log_arg; F.log_mult = d.log_mult; F.log_offset = d.log_offset;
+    F.out = out; F.out_dim = d.out_kind >= MAFE_OUT_MEL ? d.n_mels : p->out_dim;
+    F.queue_head = b->queue_dev;
+    F.db_group = (d.out_kind >= MAFE_OUT_LOGMEL && d.log_kind == MAFE_LOG_DB && d.top_db >= 0.f) ? db_group : MAFE_DBGROUP_NONE;
+    F.group_max = b->group_max_dev; F.utt_group = b->utt_group_dev;
+    // staging buffers for this hop: (16 - 1) hop + 2048 samples, rounded to 16 bytes; two when they fit 2 CTAs per SM
+    F.stage_floats = (((kHalfFrames2048 - 1) * d.hop + kN2048) + 3) & ~3;
+    F.mw_floats = d.out_kind >= MAFE_OUT_MEL ? ((th->mw_floats_2048 + 3) & ~3) : 0;
+    F.n_stage = f2048_smem_total(F.stage_floats, 2, F.mw_floats) <= kF2048SmemBudget ? 2 : 1;
+    const size_t smem_bytes = f2048_smem_total(F.stage_floats, F.n_stage, F.mw_floats);
+    if (smem_bytes > kF2048SmemBudget) return MAFE_E_UNSUPPORTED;   // (a filterbank with an enormous support): generic route
+    MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
+    if (F.db_group != MAFE_DBGROUP_NONE) {
+      const int n = std::max(b->n_groups, 1);
+      fill_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->group_max_dev, n, (int)0x80000000);
+      MAFE_LAUNCH_CHECK(ctx);
+    }
+    ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+    front2048_kernel<<<std::min(2 * b->n_tiles, 2 * ctx->sm_count), 256, smem_bytes, ctx->stream>>>(F);
+    MAFE_LAUNCH_CHECK(ctx);
+    return d.out_kind >= MAFE_OUT_MEL ? kFastNeedsPost : MAFE_OK;
+  }
   if (th->f400) {
     if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
     F400Params F;
