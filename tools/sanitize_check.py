@@ -31,4 +31,14 @@ ma.hpss(np.abs(spec[0]).astype(np.float32), power=np.inf, mask=True)
 ma.harmonic(x[0, :6000])
 ma.time_stretch(x[:, :6000], 1.3)
 ma.augment._phase_vocoder(spec, 0.8)
+# round 2: the 2048-point front-end (every output kind, edge tiles, odd frame counts) and the fused-CMVN path with
+# several utterances per CTA
+x22 = synth(9, (2, 9001))
+ma.stft(x22, n_fft=2048, hop_length=300, win_length=1200)
+ma.spectrogram(x22, n_fft=2048, hop_length=512)
+ma.melspectrogram(x22, n_fft=2048, win_length=1200, hop_length=300, n_mels=128, sample_rate=22050)
+ma.mfcc(x22, n_fft=2048, n_mels=128, n_mfcc=64, hop_length=256, deltas=False, context=False)
+many = [np.round(synth(200 + i, (int(n),)) * 32768).astype(np.float32) for i, n in enumerate(rng.integers(400, 9000, size=96))]
+pipe = ma.FbankPipeline(cmvn="utt")
+pipe.features(many, chunk_utts=40)
 print("sanitize script ok")
