@@ -72,14 +72,58 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
-  for (int i = tid; i < kNfft; i += kFastThreads) s_win[i] = P.window[i];
-  for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
+  (void)s_win; (void)s_w512; (void)s_w256;   // round 1 staged the tables here; they live in TMEM now
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // Per-lane constants in tensor memory (round 2, see fbank512_v6.cuh): the window entries w[t + 16 j], w[t + 16 j + 256], the
+  // W512 twiddles of the fold and the W256 twiddles of the transform depend on t = lane & 15 only.  From shared memory they
+  // were 7 of the 11 loads per point of the fold on the kernel's busiest unit (the L1 / shared data pipe); from the lane's TMEM
+  // columns they are 12 eight-word loads per pair.  Columns: 0..15 w[n], 16..31 w[n + 256], 32..63 W512^n, 64..93 W256^(t kj).
+  uint32_t* s_tm = reinterpret_cast<uint32_t*>(smem + StftSmem::kBar) + 6;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(s_tm)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = *s_tm + ((uint32_t)(32 * (warp & 3)) << 16);
+  if (warp < 4) {
+    const int tt = lane & 15;
+    float c8[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c8[i] = P.window[tt + 16 * ((8 * c + i) & 15) + ((8 * c + i) >> 4) * 256];
+      tm_st8(tb + 8 * c, c8);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 w = P.w512[tt + 16 * (4 * c + i)];
+        c8[2 * i] = w.x; c8[2 * i + 1] = w.y;
+      }
+      tm_st8(tb + 32 + 8 * c, c8);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kj = 4 * c + 1 + i;
+        const float2 w = kj < 16 ? P.w256t[kj * 16 + tt] : make_float2(0.f, 0.f);
+        c8[2 * i] = w.x; c8[2 * i + 1] = w.y;
+      }
+      tm_st8(tb + 64 + 8 * c, c8);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh) ----
   // Centre padding: the first tile of an utterance lands `pad` floats into the buffer and the last one leaves room
@@ -188,21 +232,29 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
 
     float2 hA[2][4], hB[2][4];   // even bins of the warp's two pairs, held until the odd bins exist
     // ---- fold: frame pair -> registers (window only; a = frame 2*pair, b = frame 2*pair+1), both halves at once ----
-    cpx v0[16], v1[16];
+    c2 v0[16], v1[16];
     {
       auto fold = [&](auto H256) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = t + 16 * j;
-          const float a0 = fa_ok ? xa[16 * j] : 0.f, a1 = fa_ok ? xa[16 * j + 256] : 0.f;
-          // hop 256: frame b starts where the second half of frame a starts
-          const float b0 = decltype(H256)::value ? (fb_ok ? a1 : 0.f) : (fb_ok ? xb[16 * j] : 0.f);
-          const float b1 = fb_ok ? xb[16 * j + 256] : 0.f;
-          const float w0 = s_win[n], w1 = s_win[n + 256];
-          const cpx lo = cx(a0 * w0, b0 * w0), hi = cx(a1 * w1, b1 * w1);
-          const float2 tw = s_w512[n];
-          v0[j] = lo + hi;
-          v1[j] = cmulf(lo - hi, cx(tw.x, tw.y));
+        for (int c = 0; c < 2; ++c) {          // 8 points per round: their window entries and twiddles, 4 TMEM loads
+          float w0[8], w1[8], ta[8], tc[8];
+          tm_ld8(tb + 8 * c, w0);
+          tm_ld8(tb + 16 + 8 * c, w1);
+          tm_ld8(tb + 32 + 16 * c, ta);
+          tm_ld8(tb + 40 + 16 * c, tc);
+          tm_wait8(w0); tm_wait8(w1); tm_wait8(ta); tm_wait8(tc);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j = 8 * c + jj;
+            const float a0 = fa_ok ? xa[16 * j] : 0.f, a1 = fa_ok ? xa[16 * j + 256] : 0.f;
+            // hop 256: frame b starts where the second half of frame a starts
+            const float b0 = decltype(H256)::value ? (fb_ok ? a1 : 0.f) : (fb_ok ? xb[16 * j] : 0.f);
+            const float b1 = fb_ok ? xb[16 * j + 256] : 0.f;
+            const c2 lo = mul2(pk(a0, b0), bc(w0[jj])), hi = mul2(pk(a1, b1), bc(w1[jj]));
+            v0[j] = add2(lo, hi);
+            const float* tw = jj < 4 ? ta : tc;
+            v1[j] = cmul(sub2(lo, hi), tw[2 * (jj & 3)], tw[2 * (jj & 3) + 1]);
+          }
         }
       };
       if (hop == 256) fold(std::true_type{}); else fold(std::false_type{});
@@ -214,8 +266,31 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      cpx (&v)[16] = half ? v1 : v0;
-      fft256_group(v, slot, s_w256, t);
+      c2 (&v)[16] = half ? v1 : v0;
+      {   // 256-point transform of the 16-lane group, packed arithmetic; outputs to the slot (bin 2 (t + 16 kt) + half)
+        fft16p(v);
+        sts_c2(slot + t, v[fft16_pos(0)]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float tw[8];
+          tm_ld8(tb + 64 + 8 * c, tw);
+          tm_wait8(tw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kj = 4 * c + 1 + i;
+            if (kj < 16) sts_c2(slot + kj * kRowStride + t, cmul(v[fft16_pos(kj)], tw[2 * i], tw[2 * i + 1]));
+          }
+        }
+        __syncwarp();
+        c2 u[16];
+#pragma unroll
+        for (int tt = 0; tt < 16; ++tt) u[tt] = lds_c2(slot + t * kRowStride + tt);
+        __syncwarp();
+        fft16p(u);
+#pragma unroll
+        for (int kt = 0; kt < 16; ++kt) sts_c2(slot + t + 16 * kt, u[fft16_pos(kt)]);
+        if (t == 0) sts_c2(slot + 256, u[fft16_pos(0)]);   // output 0 again: partner of itself
+      }
       __syncwarp();
       if (half == 0 && tid == 0 && nx_w < P.n_tiles) load_offsets();   // stage 3
       // ---- emit: this warp's two pairs.  Lane l owns sub-indices kk = l + 32 i: the even bins 2kk (half 0) wait in
@@ -313,6 +388,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
     }
     __syncthreads();   // s_work / info of the next tile are visible; the Z slots may be overwritten
   }
+  __syncthreads();   // every warp has issued its last TMEM load
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*s_tm) : "memory");
 }
 
 }  // namespace mafe
