@@ -59,7 +59,9 @@ extern "C" {
 /* log applied to mel energies */
 #define MAFE_LOG_NONE 0
 #define MAFE_LOG_LN_EPS_IF_ZERO 1 /* ln(x == 0 ? DBL_EPSILON : x)  conformer/dataset.py:154-155 */
-#define MAFE_LOG_LN_PLUS 2        /* ln(x + log_arg)               features.py:349-350 (log_mels) */
+#define MAFE_LOG_LN_PLUS 2        /* ln(x + log_arg)               features.py:349-350 (log_mels); also valid on
+                                   * MAFE_OUT_POWER: ln(|X|^power + log_arg) -- deepspeech2's log1p(magnitude),
+                                   * examples/deepspeech2/dataset.py:42-43, written by the transform itself */
 #define MAFE_LOG_DB 3             /* mult*log10(max(x, amin)) - mult*log10(max(amin, ref)) spectrum.py:73-76 */
 
 /* waveform element types */
@@ -114,6 +116,10 @@ typedef struct mafe_frontend_desc {
   int32_t utt_cmvn_std;
 
   int32_t allow_fast_path; /* 1: use a specialised kernel when the configuration has one        */
+
+  /* fused per-utterance SCALAR normalisation of the output (examples/deepspeech2/dataset.py:44-47):
+   * (x - mean) / std over ALL elements of the utterance's [T, out_dim] matrix; excludes utt_cmvn_*. */
+  int32_t utt_scalar_norm;
 } mafe_frontend_desc;
 
 /* ---- library / errors ---- */

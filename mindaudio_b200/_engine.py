@@ -125,7 +125,7 @@ class Engine:
     def plan(self, *, n_fft, frame_len=None, hop, center, pad_mode="constant", out_kind, window, preemph=0.0,
              remove_frame_mean=False, dither=0.0, dither_seed=0, power=2.0, spec_scale=1.0, mel_fb=None,
              log_kind=L.LOG_NONE, log_arg=0.0, log_mult=10.0, log_offset=0.0, top_db=-1.0, dct=None,
-             utt_cmvn_mean=False, utt_cmvn_std=False, allow_fast_path=True):
+             utt_cmvn_mean=False, utt_cmvn_std=False, allow_fast_path=True, utt_scalar_norm=False):
         frame_len = n_fft if frame_len is None else frame_len
         window = np.ascontiguousarray(window, dtype=np.float32)
         mel_fb = None if mel_fb is None else np.ascontiguousarray(mel_fb, dtype=np.float32)
@@ -134,7 +134,7 @@ class Engine:
                bool(remove_frame_mean), float(dither), int(dither_seed), float(power), float(spec_scale),
                None if mel_fb is None else (mel_fb.shape, mel_fb.tobytes()), log_kind, float(log_arg),
                float(log_mult), float(log_offset), float(top_db), None if dct is None else (dct.shape, dct.tobytes()),
-               bool(allow_fast_path), bool(utt_cmvn_mean), bool(utt_cmvn_std))
+               bool(allow_fast_path), bool(utt_cmvn_mean), bool(utt_cmvn_std), bool(utt_scalar_norm))
         with self.lock:
             p = self._plans.get(key)
             if p is not None:
@@ -159,6 +159,7 @@ class Engine:
                 d.n_mfcc, d.dct = dct.shape[1], _fptr(dct)
             d.utt_cmvn_mean, d.utt_cmvn_std = int(bool(utt_cmvn_mean)), int(bool(utt_cmvn_std))
             d.allow_fast_path = int(bool(allow_fast_path))
+            d.utt_scalar_norm = int(bool(utt_scalar_norm))
             h = C.c_void_p()
             L.check(self.lib.mafe_plan_create(self.ctx, C.byref(d), C.byref(h)))
             p = Plan(self, h, dict(n_fft=n_fft, frame_len=frame_len, hop=hop, center=center, out_kind=out_kind))

@@ -39,6 +39,7 @@ class FrontendDesc(C.Structure):
         ("n_mfcc", C.c_int32), ("dct", C.POINTER(C.c_float)),
         ("utt_cmvn_mean", C.c_int32), ("utt_cmvn_std", C.c_int32),
         ("allow_fast_path", C.c_int32),
+        ("utt_scalar_norm", C.c_int32),
     ]
 
 

@@ -315,7 +315,7 @@ static int batch_fill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* b, const
   } else if (!utt_group && b->utt_group_dev) {
     cudaFree(b->utt_group_dev); b->utt_group_dev = nullptr; b->cap_utt_group = 0;
   }
-  if ((plan->d.utt_cmvn_mean || plan->d.utt_cmvn_std) && n_utts > 0)
+  if ((plan->d.utt_cmvn_mean || plan->d.utt_cmvn_std || plan->d.utt_scalar_norm) && n_utts > 0)
     MAFE_CUDA_CHECK(ensure_cap(&b->utt_stats_dev, &b->cap_utt_stats, (size_t)n_utts * 2 * plan->out_dim));
   if (plan->d.out_kind == MAFE_OUT_MFCC && b->total_frames > 0) {
     MAFE_CUDA_CHECK(ensure_cap(&b->scratch_dev, &b->cap_scratch, (size_t)b->total_frames * plan->d.n_mels));
@@ -380,7 +380,8 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   DeviceGuard g(ctx->device);
   const mafe_frontend_desc& d = plan->d;
   const bool cmvn = d.utt_cmvn_mean || d.utt_cmvn_std;
-  MAFE_REQUIRE(!(cmvn && d.out_kind == MAFE_OUT_COMPLEX), "utterance CMVN needs a real-valued output kind");
+  MAFE_REQUIRE(!((cmvn || d.utt_scalar_norm) && d.out_kind == MAFE_OUT_COMPLEX), "utterance normalisation needs a real-valued output kind");
+  MAFE_REQUIRE(!(cmvn && d.utt_scalar_norm), "utt_scalar_norm excludes utt_cmvn_mean / utt_cmvn_std");
   int rc = MAFE_E_UNSUPPORTED;
   float* const feat_target = d.out_kind == MAFE_OUT_MFCC ? batch->scratch_dev : out_dev;
   if (plan->fast) {
@@ -399,6 +400,8 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   if (rc) return rc;
   if (cmvn)
     return mafe_cmvn_utt(ctx, out_dev, batch->frame_offsets_dev, batch->n_utts, plan->out_dim, d.utt_cmvn_mean, d.utt_cmvn_std);
+  if (d.utt_scalar_norm)   // (the specialised transform that accumulates the moments itself returned MAFE_OK above)
+    return mafe_cmvn_scalar(ctx, out_dev, batch->frame_offsets_dev, batch->n_utts, plan->out_dim, 0);
   return MAFE_OK;
 }
 

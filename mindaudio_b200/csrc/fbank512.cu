@@ -945,7 +945,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     F.out_kind = d.out_kind == MAFE_OUT_MFCC ? MAFE_OUT_LOGMEL : d.out_kind;
     F.power = d.power; F.n_mels = d.n_mels;
     F.mstart = th->mstart_dev; F.mcount = th->mcount_dev; F.moff = th->moff_dev; F.mweights = th->mweights_dev;
-    F.log_kind = d.out_kind == MAFE_OUT_MEL ? MAFE_LOG_NONE : d.log_kind;
+    F.log_kind = (d.out_kind == MAFE_OUT_MEL || d.out_kind == MAFE_OUT_COMPLEX) ? MAFE_LOG_NONE : d.log_kind;
     F.log_arg = d.log_arg; F.log_mult = d.log_mult; F.log_offset = d.log_offset;
     F.out = out; F.out_dim = d.out_kind >= MAFE_OUT_MEL ? d.n_mels : p->out_dim;
     F.queue_head = b->queue_dev;
@@ -966,7 +966,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
     front2048_kernel<<<std::min(2 * b->n_tiles, 2 * ctx->sm_count), 256, smem_bytes, ctx->stream>>>(F);
     MAFE_LAUNCH_CHECK(ctx);
-    return d.out_kind >= MAFE_OUT_MEL ? kFastNeedsPost : MAFE_OK;
+    return (d.out_kind >= MAFE_OUT_MEL || d.utt_scalar_norm) ? kFastNeedsPost : MAFE_OK;
   }
   if (th->f400) {
     if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
@@ -1000,14 +1000,27 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     S.n_tiles = b->n_tiles; S.hop = d.hop; S.center = d.center; S.pad_mode = d.pad_mode;
     S.window = th->dev.window; S.twn = th->tw400_dev; S.out = out; S.queue_head = b->queue_dev;
     S.out_power = d.out_kind == MAFE_OUT_POWER; S.power = d.power;
+    S.log_kind = d.out_kind == MAFE_OUT_POWER ? d.log_kind : MAFE_LOG_NONE; S.log_arg = d.log_arg;
     for (int i = 0; i < 16; ++i) S.tws[i] = th->tws[i];
+    const bool scalar_norm = d.utt_scalar_norm && d.out_kind == MAFE_OUT_POWER && b->utt_stats_dev != nullptr;
+    S.utt_stats = scalar_norm ? b->utt_stats_dev : nullptr;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
-    ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-    const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
-    if (th->stftn == 20) stftn16_kernel<20><<<grid, kFastThreads, StftN<20>::kTotal, ctx->stream>>>(S);
-    else stftn16_kernel<25><<<grid, kFastThreads, StftN<25>::kTotal, ctx->stream>>>(S);
-    MAFE_LAUNCH_CHECK(ctx);
-    return MAFE_OK;
+    if (scalar_norm) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * b->n_utts, ctx->stream));
+    {
+      ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
+      if (th->stftn == 20) stftn16_kernel<20><<<grid, kFastThreads, StftN<20>::kTotal, ctx->stream>>>(S);
+      else stftn16_kernel<25><<<grid, kFastThreads, StftN<25>::kTotal, ctx->stream>>>(S);
+      MAFE_LAUNCH_CHECK(ctx);
+    }
+    if (scalar_norm) {   // the transform accumulated sum x, sum x^2 per utterance: one streaming pass normalises
+      ProfScope ps(ctx, MAFE_PROF_CMVN);
+      scalar_norm_apply_kernel<<<std::min(b->n_tiles, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(
+          out, b->tiles_dev, b->n_tiles, b->frame_offsets_dev, b->utt_stats_dev, p->out_dim, p->tile_frames);
+      MAFE_LAUNCH_CHECK(ctx);
+      return MAFE_OK;
+    }
+    return d.utt_scalar_norm ? kFastNeedsPost : MAFE_OK;
   }
   if (th->stft) {
     if (wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave & 15) != 0) return MAFE_E_UNSUPPORTED;
@@ -1018,12 +1031,13 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     S.window = th->dev.window; S.w512 = th->dev.w512; S.w256t = th->dev.w256t;
     S.out = out; S.queue_head = b->queue_dev;
     S.out_power = d.out_kind == MAFE_OUT_POWER; S.power = d.power;
+    S.log_kind = d.out_kind == MAFE_OUT_POWER ? d.log_kind : MAFE_LOG_NONE; S.log_arg = d.log_arg;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
     if (S.out_power) stft512_kernel<true><<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, StftSmem::kTotal, ctx->stream>>>(S);
     else stft512_kernel<false><<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, StftSmem::kTotal, ctx->stream>>>(S);
     MAFE_LAUNCH_CHECK(ctx);
-    return MAFE_OK;
+    return d.utt_scalar_norm ? kFastNeedsPost : MAFE_OK;
   }
   FastParams P;
   P.wave = wave; P.wave_dtype = wave_dtype; P.wave_scale = wave_scale;

@@ -341,6 +341,10 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
               if (P.power == 1.0f) { pa = sqrtf(pa); pb = sqrtf(pb); }
               else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
             }
+            if (P.log_kind == MAFE_LOG_LN_PLUS) {
+              pa = P.log_arg == 1.0f ? log1pf(pa) : logf(pa + P.log_arg);
+              pb = P.log_arg == 1.0f ? log1pf(pb) : logf(pb + P.log_arg);
+            }
             oa[k] = pa;
             if (has_b) ob[k] = pb;
           }

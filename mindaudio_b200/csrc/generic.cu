@@ -223,6 +223,10 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
         else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
       }
       if (P.out_kind == MAFE_OUT_POWER) {
+        if (P.log_kind == MAFE_LOG_LN_PLUS) {   // log-compressed spectrogram (deepspeech2: log1p of the magnitude)
+          pa = P.log_arg == 1.0f ? log1pf(pa) : logf(pa + P.log_arg);
+          pb = P.log_arg == 1.0f ? log1pf(pb) : logf(pb + P.log_arg);
+        }
         if (fa < T) P.out[(fo + fa) * P.out_dim + k] = pa;
         if (fa + 1 < T) P.out[(fo + fa + 1) * P.out_dim + k] = pb;
       } else {

@@ -28,6 +28,8 @@ struct StftParams {
   float* out;           // [total_frames][257] complex64, or float |X|^power (out_power != 0: spectrum.spectrogram)
   int out_power;
   float power;
+  int log_kind;         // MAFE_LOG_LN_PLUS on the power kind: ln(|X|^power + log_arg)
+  float log_arg;
   int* queue_head;
 };
 
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) stft512_kernel(const __grid_c
       auto pw_of = [&](float re, float im) -> float {   // |X|^power of the power-spectrogram output kind
         float p = fmaf(re, re, im * im);
         if (P.power != 2.0f) p = P.power == 1.0f ? sqrtf(p) : powf(sqrtf(p), P.power);
+        if (P.log_kind == MAFE_LOG_LN_PLUS) p = P.log_arg == 1.0f ? log1pf(p) : logf(p + P.log_arg);
         return p;
       };
       if (half == 0) {

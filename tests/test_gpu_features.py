@@ -369,3 +369,22 @@ def test_padded_pipeline_reference_order(ma):
     assert np.array_equal(order, np.argsort(frames)[::-1]) and np.array_equal(ln, frames[order])
     xs2, ln2, mk2 = pipe.features_padded([waves[i] for i in order], spec_aug_conf=conf, rng=random.Random(5))
     assert np.array_equal(ln, ln2) and np.array_equal(mk, mk2) and np.allclose(xs, xs2, atol=2e-5)
+
+
+def test_ds2_features_fused(ma, golden):
+    """deepspeech2 front-end (examples/deepspeech2/dataset.py:36-47) through the fused output kind: the transform kernel
+    writes log1p(|X|) itself (MAFE_OUT_POWER + MAFE_LOG_LN_PLUS), the scalar normalisation follows on the device.  Golden =
+    the reference's own chain (stft -> magphase -> log1p -> (m - mean) / std) on the sample WAV."""
+    x = golden.wav()
+    out = ma.ds2_features(x)
+    assert out.shape == (161, 600) and out.dtype == np.float32
+    assert mixed_err(golden.take("spectrum/ds2_norm", out), golden["spectrum/ds2_norm"]) <= 1e-4
+    raw = ma.ds2_features(x, normalize=False)
+    ref = np.log1p(np.abs(R.stft(x, n_fft=320, hop_length=160, win_length=320)))
+    assert np.max(np.abs(raw - ref)) <= 1e-5 * max(1.0, np.max(ref))
+    for kw in (dict(n_fft=512, hop_length=128, win_length=400), dict(n_fft=2048, hop_length=300, win_length=1200), dict(n_fft=1024, hop_length=256, win_length=1024)):
+        raw = ma.ds2_features(x, normalize=False, **kw)
+        ref = np.log1p(np.abs(R.stft(x, **kw)))
+        assert raw.shape == ref.shape and np.max(np.abs(raw - ref)) <= 1e-5 * max(1.0, np.max(ref)), kw
+        nrm = ma.ds2_features(x, normalize=True, **kw)            # other transform kernels: normalisation as a post step
+        assert np.max(np.abs(nrm - (ref - ref.mean()) / ref.std())) <= 1e-4, kw
