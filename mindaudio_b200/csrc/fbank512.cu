@@ -809,11 +809,11 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     const int N1 = th->stftn, N = 16 * N1, B = N1 == 25 ? 5 : 4;   // N1 = 5 x B: twiddles W_N1^(j1 k1), j1 = 1..4, k1 = 1..B-1
     std::vector<float> wn(N);
     for (int i = 0; i < N; ++i) wn[i] = 0.5f * d->spec_scale * d->window[i];   // 1/2: the pair separation leaves 2X
-    std::vector<float2> twn(N);
+    std::vector<float2> twn(2 * N);   // t = 16..31: the rotated upper half-warp of stftn16_kernel
     for (int kj = 0; kj < N1; ++kj)
-      for (int t = 0; t < 16; ++t) {
-        double a = -2.0 * M_PI * (double)(t * kj) / (double)N;
-        twn[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
+      for (int t = 0; t < 32; ++t) {
+        double a = -2.0 * M_PI * (double)((t * kj) % N) / (double)N;
+        twn[kj * 32 + t] = make_float2((float)cos(a), (float)sin(a));
       }
     memset(th->tws, 0, sizeof(th->tws));
     for (int j1 = 1; j1 < 5; ++j1)
@@ -1008,7 +1008,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     if (scalar_norm) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * b->n_utts, ctx->stream));
     {
       ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-      const int grid = std::min(b->n_tiles, 2 * ctx->sm_count);
+      const int grid = std::min(b->n_tiles, (th->stftn == 20 ? StftN<20>::kCtasPerSm : StftN<25>::kCtasPerSm) * ctx->sm_count);
       if (th->stftn == 20) stftn16_kernel<20><<<grid, kFastThreads, StftN<20>::kTotal, ctx->stream>>>(S);
       else stftn16_kernel<25><<<grid, kFastThreads, StftN<25>::kTotal, ctx->stream>>>(S);
       MAFE_LAUNCH_CHECK(ctx);

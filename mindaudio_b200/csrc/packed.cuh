@@ -84,6 +84,54 @@ __device__ __forceinline__ void fft16p(c2* v) {
   for (int k2 = 0; k2 < 4; ++k2) dft4p(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
 }
 
+__device__ __forceinline__ c2 pli(c2 a) { return pk(-im(a), re(a)); }             // a * (+i)
+
+// forward 5-point DFT in place (same operation order as fft400.cuh::dft5)
+__device__ __forceinline__ void dft5p(c2& x0, c2& x1, c2& x2, c2& x3, c2& x4) {
+  const float c1 = 0.30901699437494742410f, c2_ = -0.80901699437494742410f;
+  const float s1 = -0.95105651629515357212f, s2 = -0.58778525229247312917f;  // -sin(2pi/5), -sin(4pi/5)
+  const c2 a1 = add2(x1, x4), b1 = sub2(x1, x4), a2 = add2(x2, x3), b2 = sub2(x2, x3);
+  const c2 m1 = fma2(bc(c2_), a2, fma2(bc(c1), a1, x0));
+  const c2 m2 = fma2(bc(c1), a2, fma2(bc(c2_), a1, x0));
+  const c2 t1 = fma2(bc(s2), b2, mul2(bc(s1), b1));     // n1 = i * (s1 b1 + s2 b2)
+  const c2 t2 = fma2(bc(-s1), b2, mul2(bc(s2), b1));    // n2 = i * (s2 b1 - s1 b2)
+  x0 = add2(add2(x0, a1), a2);
+  x1 = add2(m1, pli(t1));
+  x4 = sub2(m1, pli(t1));
+  x2 = add2(m2, pli(t2));
+  x3 = sub2(m2, pli(t2));
+}
+
+// forward 25-point DFT (5 x 5); index maps and twiddle table of fft400.cuh::fft25 (output bin k at v[fft25_pos(k)])
+__device__ __forceinline__ void fft25p(c2* v, const float2* tw25) {
+#pragma unroll
+  for (int j1 = 0; j1 < 5; ++j1) dft5p(v[j1], v[j1 + 5], v[j1 + 10], v[j1 + 15], v[j1 + 20]);
+#pragma unroll
+  for (int j1 = 1; j1 < 5; ++j1)
+#pragma unroll
+    for (int k1 = 1; k1 < 5; ++k1) {
+      const float2 w = tw25[(j1 - 1) * 4 + (k1 - 1)];
+      v[j1 + 5 * k1] = cmul(v[j1 + 5 * k1], w.x, w.y);
+    }
+#pragma unroll
+  for (int k1 = 0; k1 < 5; ++k1) dft5p(v[5 * k1], v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);
+}
+
+// forward 20-point DFT (4 x 5); fft400.cuh::fft20 (output bin k at v[fft20_pos(k)])
+__device__ __forceinline__ void fft20p(c2* v, const float2* tw20) {
+#pragma unroll
+  for (int j1 = 0; j1 < 5; ++j1) dft4p(v[j1], v[j1 + 5], v[j1 + 10], v[j1 + 15]);
+#pragma unroll
+  for (int j1 = 1; j1 < 5; ++j1)
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1) {
+      const float2 w = tw20[(j1 - 1) * 3 + (k1 - 1)];
+      v[j1 + 5 * k1] = cmul(v[j1 + 5 * k1], w.x, w.y);
+    }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft5p(v[5 * k1], v[5 * k1 + 1], v[5 * k1 + 2], v[5 * k1 + 3], v[5 * k1 + 4]);
+}
+
 __device__ __forceinline__ c2 lds_c2(const float2* p) { return *reinterpret_cast<const c2*>(p); }
 __device__ __forceinline__ void sts_c2(float2* p, c2 v) { *reinterpret_cast<c2*>(p) = v; }
 

@@ -11,6 +11,7 @@
 // complex64 (stft) or |X|^power (spectrogram: msaudio.Spectrogram, window pre-scaled by the normalisation).
 #pragma once
 #include "fft400.cuh"
+#include "packed.cuh"
 
 namespace mafe {
 
@@ -24,16 +25,12 @@ struct StftN {
   static constexpr int kZBytes = ((kPairs * kSlot * 8) + 127) & ~127;
   static constexpr size_t kRaw = kZBytes;                       // the waveform tile (own region: the next tile is
                                                                 // fetched while this one is transformed and stored)
-  static constexpr int kSkew = kRawBytes / 4 + 16;              // floats from copy 0 to the skewed copy 1 of the tile (16 banks
-                                                                // apart: with hop = 160 the two pairs of a warp start on the same bank)
-  static constexpr size_t kWin = kRaw + 2 * kRawBytes + 64;     // float[kN]
-  static constexpr size_t kTw = kWin + sizeof(float) * kN;      // float2[N1][16]  W_N^(t kj)
-  static constexpr size_t kBar = kTw + sizeof(float2) * kN;
+  static constexpr size_t kBar = kRaw + kRawBytes + 64;         // (window and W_N twiddles: tensor memory, see the kernel)
+  static constexpr int kCtasPerSm = (3 * (kBar + 32 + 2 * 96 + 1024) <= 227 * 1024) ? 3 : 2;
   static constexpr size_t kInfo = kBar + 32;
   static constexpr size_t kTotal = kInfo + 2 * 96;
-  static_assert(kRaw % 128 == 0 && 2 * (kTotal + 1024) <= 228 * 1024, "raw landing zone / 2 CTAs per SM");
+  static_assert(kRaw % 128 == 0 && kCtasPerSm * (kTotal + 1024) <= 228 * 1024, "raw landing zone / CTAs per SM");
   static_assert(kSlot >= kN + 1, "slot holds the spectrum and the copy of bin 0");
-  static_assert(kSkew % 32 == 16 && (kSkew * 4) % 16 == 0, "skewed copy: 16 banks away, 16 B aligned");
 };
 
 struct StftNParams {
@@ -45,7 +42,7 @@ struct StftNParams {
   int n_tiles;
   int hop, center, pad_mode;
   const float* window;     // [kN], pre-scaled by 1/2 (the pair separation leaves 2X)
-  const float2* twn;       // [N1][16]  W_N^(t kj)
+  const float2* twn;       // [N1][32]  W_N^(t kj), t = 0..31 (t >= 16: the rotated upper half-warp, see the load)
   float* out;              // [total_frames][kBins] complex64, or float |X|^power (out_power != 0)
   int out_power;           // 0: complex STFT; 1: power / magnitude spectrogram (spectrum.spectrogram, spectrum.py:547-606)
   float power;
@@ -57,31 +54,67 @@ struct StftNParams {
 };
 
 template <int N1>
-__global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_constant__ StftNParams P) {
+__global__ void __launch_bounds__(kFastThreads, StftN<N1>::kCtasPerSm) stftn16_kernel(const __grid_constant__ StftNParams P) {
   typedef StftN<N1> G;
   constexpr int kN = G::kN, kBins = G::kBins, kSlot = G::kSlot;
   extern __shared__ __align__(128) unsigned char smem[];
   float2* Zs = reinterpret_cast<float2*>(smem);
   float* rawz = reinterpret_cast<float*>(smem + G::kRaw);
-  float* s_win = reinterpret_cast<float*>(smem + G::kWin);
-  float2* s_tw = reinterpret_cast<float2*>(smem + G::kTw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::kBar);
   int* s_work = reinterpret_cast<int*>(bars) + 4;
   F400TileInfo* info = reinterpret_cast<F400TileInfo*>(smem + G::kInfo);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
-  // the upper half-warp's pair starts 2 * hop floats after the lower one: it reads a second, skewed copy of the tile
-  // when that offset would put both on (nearly) the same banks
+  // The upper half-warp's pair starts 2 * hop floats after the lower one.  When that offset puts both on (nearly) the same
+  // banks (hop 160: exactly), the upper half reads its frame ROTATED by one block of 16 samples: register j holds sample
+  // t + 16 ((j + 1) mod N1).  The N1-point DFT of the rotated sequence is the wanted one times W_N1^(-kj); the lane's window
+  // entries and twiddles -- per-lane constants in tensor memory -- are those of t + 16, which absorbs it: W_N^((t + 16) kj).
+  // (Round 1 had the TMA engine deliver a second, skewed copy of the tile: 21 KB of shared memory and twice the L2 reads.)
   const int pair_banks = (2 * hop) & 31;
-  const bool use_skew = pair_banks < 8 || pair_banks > 24;
-  for (int i = tid; i < kN; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.twn[i]; }
+  const int rot = ((pair_banks < 8 || pair_banks > 24) && (lane >> 4)) ? 1 : 0;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // Per-lane constants in tensor memory (round 2; helpers and rationale in fbank512_v6.cuh): the window entries w[t + 16 j]
+  // (columns 0..N1-1) and the twiddles W_N^(t kj), kj = 1..N1-1 (columns 32 + 2 (kj - 1)) depend on t = lane & 15 only.
+  // From shared memory they were 58 of the ~310 shared-memory wavefronts a warp spends per tile on the kernel's busiest unit.
+  uint32_t* s_tm = reinterpret_cast<uint32_t*>(bars) + 6;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(s_tm)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = *s_tm + ((uint32_t)(32 * (warp & 3)) << 16);
+  constexpr int kTwBlocks = (2 * (N1 - 1) + 7) / 8;   // eight-word blocks of twiddles (4 per block)
+  if (warp < 4) {
+    const int tt = lane & 15;
+    float c8[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c8[i] = 8 * c + i < N1 ? P.window[tt + 16 * ((8 * c + i + rot) % N1)] : 0.f;
+      tm_st8(tb + 8 * c, c8);
+    }
+#pragma unroll
+    for (int c = 0; c < kTwBlocks; ++c) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kj = 4 * c + 1 + i;
+        const float2 w = kj < N1 ? P.twn[kj * 32 + tt + 16 * rot] : make_float2(0.f, 0.f);
+        c8[2 * i] = w.x; c8[2 * i + 1] = w.y;
+      }
+      tm_st8(tb + 32 + 8 * c, c8);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh / fbank400.cuh) ----
   int nx_w = P.n_tiles;
@@ -110,9 +143,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
-      mbar_expect_tx(&bars[slot], use_skew ? 2 * bytes : bytes);
+      mbar_expect_tx(&bars[slot], bytes);
       tma_bulk_g2s(rawz + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
-      if (use_skew) tma_bulk_g2s(rawz + G::kSkew + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
     } else {
       mbar_arrive(&bars[slot]);
     }
@@ -149,9 +181,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     float* xr = rawz + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
     if (cur.cov_end < cur.end_elem) {   // bytes the 16 B-granular bulk copy could not cover (end of the flat array)
       for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
-        const float x = P.wave[e];
-        rawz[cur.lpad + (e - cur.base_elem)] = x;
-        if (use_skew) rawz[G::kSkew + cur.lpad + (e - cur.base_elem)] = x;
+        rawz[cur.lpad + (e - cur.base_elem)] = P.wave[e];
       }
       __syncthreads();
     }
@@ -169,23 +199,33 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
           x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
         }
         xr[i] = x;
-        if (use_skew) xr[G::kSkew + i] = x;
       }
       __syncthreads();
     }
 
-    // ---- load: frame pair -> N1 windowed complex points per lane ----
-    cpx v[N1];
+    // ---- load: frame pair -> N1 windowed complex points per lane (packed: (a, b) * w) ----
+    c2 v[N1];
     {
-      const float* xa = xr + ((lane >> 4) && use_skew ? G::kSkew : 0) + (2 * pair) * hop + t;
+      const float* xa = xr + (2 * pair) * hop + t + 16 * rot;
       const float* xb = xa + hop;
+      const int last = 16 * (N1 - 1) - 16 * N1 * rot;   // the last register block wraps to block 0 in the rotated half
       const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 #pragma unroll
-      for (int j = 0; j < N1; ++j) {
-        const float a = fa_ok ? xa[16 * j] : 0.f;
-        const float b = fb_ok ? xb[16 * j] : 0.f;
-        const float w = s_win[t + 16 * j];
-        v[j] = cx(a * w, b * w);
+      for (int c = 0; c < (N1 + 7) / 8; ++c) {
+        float w8[8];
+        tm_ld8(tb + 8 * c, w8);
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (8 * c + i < N1) {
+            const int o = 8 * c + i == N1 - 1 ? last : 16 * (8 * c + i);
+            a[i] = fa_ok ? xa[o] : 0.f;
+            b[i] = fb_ok ? xb[o] : 0.f;
+          }
+        tm_wait8(w8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (8 * c + i < N1) v[8 * c + i] = mul2(pk(a[i], b[i]), bc(w8[i]));
       }
     }
     __syncthreads();   // the waveform has been consumed: the buffer may be refilled
@@ -195,17 +235,20 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     }
 
     // ---- stage 1: N1-point DFT in registers, twiddle W_N^(t kj), rows [kj][t] of the pair's slot ----
-    if (N1 == 25) fft25(v, P.tws); else fft20(v, P.tws);
+    if (N1 == 25) fft25p(v, P.tws); else fft20p(v, P.tws);
     {
       float2* slot = Zs + pair * kSlot;
+      sts_c2(&slot[t], v[0]);
 #pragma unroll
-      for (int kj = 0; kj < N1; ++kj) {
-        cpx x = v[N1 == 25 ? fft25_pos(kj) : fft20_pos(kj)];
-        if (kj > 0) {
-          const float2 tw = s_tw[kj * 16 + t];
-          x = cmulf(x, cx(tw.x, tw.y));
+      for (int c = 0; c < kTwBlocks; ++c) {
+        float w8[8];
+        tm_ld8(tb + 32 + 8 * c, w8);
+        tm_wait8(w8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kj = 4 * c + 1 + i;
+          if (kj < N1) sts_c2(&slot[kj * kRowStride + t], cmul(v[N1 == 25 ? fft25_pos(kj) : fft20_pos(kj)], w8[2 * i], w8[2 * i + 1]));
         }
-        slot[kj * kRowStride + t] = make_float2(x.x, x.y);
       }
     }
     __syncwarp();
@@ -213,34 +256,28 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
 
     // ---- stage 2: the warp's 2 x N1 sixteen-point DFTs over t, two rounds of 32 lanes ----
     {
-      cpx u0[16], u1[16];
       constexpr int kSecond = 2 * N1 - 32;                             // tasks of the second round (18 / 8)
       const int q0 = lane / N1, kj0 = lane - N1 * q0;                  // task = lane        (0..31)
       const int task1 = 32 + lane, q1 = task1 / N1, kj1 = task1 - N1 * q1;   // task = 32 + lane (valid for lane < kSecond)
-      const float2* s0 = Zs + (warp * 2 + q0) * kSlot;
-      const float2* s1 = Zs + (warp * 2 + (lane < kSecond ? q1 : 0)) * kSlot;
+      const bool second = lane < kSecond;
+      const float2* s0 = Zs + (warp * 2 + q0) * kSlot + kj0 * kRowStride;
+      const float2* s1 = Zs + (warp * 2 + (second ? q1 : 0)) * kSlot + (second ? kj1 : 0) * kRowStride;
+      c2 u0[16], u1[16];
 #pragma unroll
-      for (int tt = 0; tt < 16; ++tt) {
-        const float2 x = s0[kj0 * kRowStride + tt];
-        u0[tt] = cx(x.x, x.y);
-        const float2 y = s1[(lane < kSecond ? kj1 : 0) * kRowStride + tt];
-        u1[tt] = cx(y.x, y.y);
-      }
+      for (int tt = 0; tt < 16; ++tt) u0[tt] = lds_c2(s0 + tt);
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) u1[tt] = second ? lds_c2(s1 + tt) : 0ull;   // idle lanes issue no shared-memory wavefronts
       __syncwarp();
-      fft16(u0);
-      fft16(u1);
-      float2* d0 = Zs + (warp * 2 + q0) * kSlot;
-      float2* d1 = Zs + (warp * 2 + q1) * kSlot;
+      fft16p(u0);
+      float2* d0 = Zs + (warp * 2 + q0) * kSlot + kj0;
 #pragma unroll
-      for (int kt = 0; kt < 16; ++kt) {
-        const cpx x = u0[fft16_pos(kt)];
-        d0[kj0 + N1 * kt] = make_float2(x.x, x.y);
-        if (lane < kSecond) {
-          const cpx y = u1[fft16_pos(kt)];
-          d1[kj1 + N1 * kt] = make_float2(y.x, y.y);
-        }
-      }
-      if (kj0 == 0) d0[kN] = make_float2(u0[fft16_pos(0)].x, u0[fft16_pos(0)].y);   // bin 0 again: its own partner
+      for (int kt = 0; kt < 16; ++kt) sts_c2(d0 + N1 * kt, u0[fft16_pos(kt)]);
+      if (kj0 == 0) sts_c2(d0 + kN, u0[fft16_pos(0)]);   // bin 0 again: its own partner
+      fft16p(u1);
+      float2* d1 = Zs + (warp * 2 + (second ? q1 : 0)) * kSlot + (second ? kj1 : 0);
+#pragma unroll
+      for (int kt = 0; kt < 16; ++kt)
+        if (second) sts_c2(d1 + N1 * kt, u1[fft16_pos(kt)]);
     }
     __syncwarp();
     if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);   // stage 4: the next tile lands while this one is stored
@@ -258,21 +295,20 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
         float2* ob = oa + kBins;
 #pragma unroll 2
         for (int k = lane; k < kBins; k += 32) {
-          const float2 zk = zp[k];
-          const float2 zn = zp[kN - k];
-          // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i
-          if (wa) oa[k] = make_float2(zk.x + zn.x, zk.y - zn.y);
-          if (wb) ob[k] = make_float2(zk.y + zn.y, zn.x - zk.x);
+          const c2 zk = lds_c2(zp + k), zn = lds_c2(zp + kN - k);
+          // window carries the 1/2:  A = Z[k] + conj Z[N-k],  B = (Z[k] - conj Z[N-k]) / i = swap(Z[N-k]) + (-i) Z[k]
+          if (wa) sts_c2(oa + k, add2(zk, cnj(zn)));
+          if (wb) sts_c2(ob + k, add2(swp(zn), mni(zk)));
         }
       } else {                  // rows of kBins floats: |X|^power
         float* oa = P.out + (cur.out_row + fa) * (int64_t)kBins;
         float* ob = oa + kBins;
 #pragma unroll 2
         for (int k = lane; k < kBins; k += 32) {
-          const float2 zk = zp[k];
-          const float2 zn = zp[kN - k];
-          const float ra = zk.x + zn.x, ia = zk.y - zn.y, rb = zk.y + zn.y, ib = zn.x - zk.x;
-          float pa = fmaf(ra, ra, ia * ia), pb = fmaf(rb, rb, ib * ib);
+          const c2 zk = lds_c2(zp + k), zn = lds_c2(zp + kN - k);
+          const c2 A = add2(zk, cnj(zn)), B = sub2(zk, cnj(zn));   // |B| is all the power kinds need of frame b
+          const c2 A2 = mul2(A, A), B2 = mul2(B, B);
+          float pa = re(A2) + im(A2), pb = re(B2) + im(B2);
           if (P.log_kind == MAFE_LOG_LN_PLUS && P.power == 1.0f) {
             // deepspeech2: ln(|X| + c).  MUFU square root and logarithm (2^-22 relative): the IEEE sqrtf / log1pf pair made
             // this emit compute bound (0.82 ms against 0.51 ms for the complex output that writes twice the bytes)
@@ -305,6 +341,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) stftn16_kernel(const __grid_c
     }
     __syncthreads();   // the Z slots may be overwritten; s_work / info of the next tile are visible
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*s_tm) : "memory");
 }
 
 // (x - mean) / std over ALL elements of an utterance from the moments accumulated by the transform (deepspeech2/dataset.py:44-47)
