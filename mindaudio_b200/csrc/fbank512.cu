@@ -334,6 +334,7 @@ struct FastTablesHost {
   float2 tws[16];         // W_N1^(j1 k1) of the in-register N1-point DFT
   bool f400 = false;      // n_fft = 400 mel front-end plan (fbank400_kernel)
   float2* tw400_dev = nullptr;
+  float* cover4_dev = nullptr;   // v6 FS: c' table
   F400Sweep sweep400;     // sweep program of fbank400_kernel (kernel-parameter bank)
   float2 tw25[16];
   bool tile_geom = false; // conformer geometry (400 / 160 / 512 / 80 filters): the v3 kernel and its pre-pass apply
@@ -883,6 +884,20 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       cover[r] = (float)c;
     }
     if ((rc = up(&th->dev.cover, cover))) return rc;
+    if (d->hop == kV2Hop) {
+      // c'(r) = c(r) - a c(r + 1) (fbank512_v6.cuh, FS), four copies, copy k shifted by k entries: a thread's 4 (8)
+      // coefficients are aligned 16-byte loads from copy r mod 4
+      std::vector<double> cd(d->hop, 0.0);
+      for (int r = 0; r < d->hop; ++r)
+        for (int n = r; n < d->frame_len; n += d->hop) cd[r] += (double)d->window[n];
+      std::vector<float> c4(4 * kCwRow, 0.f);
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < kCwRow; ++j) {
+          const int r = (j + k) % d->hop;
+          c4[k * kCwRow + j] = (float)(cd[r] - d->preemph * cd[(r + 1) % d->hop]);
+        }
+      if ((rc = up(&th->cover4_dev, c4))) return rc;
+    }
   }
   MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FastSmem::kTotal));
   th->tile_geom = d->frame_len == kV2Flen && d->hop == kV2Hop && d->n_mels == kV2Mels;
@@ -898,6 +913,8 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
       MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
       MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(fbank512_v6_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6Smem::kTotal));
     }
     std::vector<int> comb5;
     th->v5 = th->v3 && build_v5_program(bins, th->sweep5, comb5);
@@ -920,6 +937,7 @@ void fast_plan_free(mafe_plan* p) {
   cudaFree(th->comb3_dev);
   cudaFree(th->comb5_dev);
   cudaFree(th->tw400_dev);
+  cudaFree(th->cover4_dev);
   cudaFree(th->tw2048_dev); cudaFree(th->mstart_dev); cudaFree(th->mcount_dev); cudaFree(th->moff_dev); cudaFree(th->mweights_dev);
   delete th;
   p->fast_tables = nullptr;
@@ -1062,11 +1080,23 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     Q.window = th->dev.window; Q.w512 = th->dev.w512; Q.w256t = th->dev.w256t; Q.combine = th->comb3_dev;
     Q.out = out;
     Q.queue_head = b->queue_dev;
-    Q.tile_recs = nullptr;
+    Q.tile_recs = nullptr; Q.sum_recs = nullptr;
     Q.utt_done = nullptr; Q.lag = 0; Q.mean_norm = 0; Q.std_norm = 0;
+    Q.lag_s = 0; Q.cover4 = th->cover4_dev; Q.utt_fsum = b->utt_sum_dev; Q.fsum_done = nullptr;
+    static const bool halfwarp = getenv("MAFE_HALFWARP_SWEEP") != nullptr;   // experimental: 16 ranges, two frames per lane
+    static const bool force_v3 = getenv("MAFE_FBANK_V3") != nullptr;         // A/B switch: the round-1 kernel
+    static const bool no_tmem = getenv("MAFE_NO_TMEM") != nullptr;           // A/B switch: constants from shared memory
+    static const bool no_fuse = getenv("MAFE_NO_FUSED_CMVN") != nullptr;     // A/B switch: separate CMVN apply kernel
+    static const bool no_fs = getenv("MAFE_NO_FUSED_FRAMESUM") != nullptr;   // A/B switch: frame-mean pre-pass kernel
+    const bool use_v6 = th->v6 && !force_v3 && !halfwarp;
+    const bool fuse = use_v6 && cmvn && !no_tmem && !no_fuse;
+    // frame-mean sums inside the persistent kernel (needs the fused CMVN variant; dither changes the samples per frame;
+    // and a batch that amortises the lag_s sum-only items at the head of the queue; small batches keep the pre-pass)
+    const bool fs = fuse && !no_fs && d.remove_frame_mean && d.dither == 0.f && th->cover4_dev != nullptr &&
+                    b->n_tiles >= 12 * ctx->sm_count;
     MAFE_CUDA_CHECK(cudaMemsetAsync(b->queue_dev, 0, sizeof(int32_t), ctx->stream));
-    if (d.remove_frame_mean) {
-      MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
+    if (d.remove_frame_mean) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_sum_dev, 0, sizeof(double) * b->n_utts, ctx->stream));
+    if (d.remove_frame_mean && !fs) {
       ProfScope ps(ctx, MAFE_PROF_FRAME_MEAN);
       if (b->n_utts >= 4 * ctx->sm_count) {
         // enough utterances to fill the machine: one CTA streams one utterance (no per-tile latency chain)
@@ -1084,38 +1114,37 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
-    static const bool halfwarp = getenv("MAFE_HALFWARP_SWEEP") != nullptr;   // experimental: 16 ranges, two frames per lane
-    static const bool force_v3 = getenv("MAFE_FBANK_V3") != nullptr;         // A/B switch: the round-1 kernel
-    if (th->v6 && !force_v3 && !halfwarp) {
+    if (use_v6) {
       const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);   // persistent: 3 CTAs per SM, dynamic tile queue
       if (b->cap_tile_recs < (size_t)b->n_tiles) {   // grow-only
         if (b->tile_recs_dev) MAFE_CUDA_CHECK(cudaFree(b->tile_recs_dev));
         b->tile_recs_dev = nullptr; b->cap_tile_recs = 0;
         const size_t cap = (size_t)b->n_tiles + (size_t)b->n_tiles / 4 + 16;
-        MAFE_CUDA_CHECK(cudaMalloc(&b->tile_recs_dev, cap * sizeof(TileInfo)));
+        MAFE_CUDA_CHECK(cudaMalloc(&b->tile_recs_dev, cap * (sizeof(TileInfo) + sizeof(SumRec))));
         b->cap_tile_recs = cap;
       }
       Q.tile_recs = b->tile_recs_dev;
+      Q.sum_recs = (const unsigned char*)b->tile_recs_dev + b->cap_tile_recs * sizeof(TileInfo);
+      // FS: the sums run lag_s items ahead of the transforms (same rule as the CMVN lag below)
+      if (fs) Q.lag_s = (int)((b->max_utt_frames + kTileFrames - 1) / kTileFrames) + 3 * grid3 + 64;
       {
         ProfScope ps(ctx, MAFE_PROF_OTHER);
         const int pg = (b->n_tiles + 255) / 256;
-        if (wave_dtype == MAFE_WAVE_I16) tile_prepare_kernel<true><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev);
-        else tile_prepare_kernel<false><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev);
+        if (wave_dtype == MAFE_WAVE_I16) tile_prepare_kernel<true><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev, (SumRec*)Q.sum_recs);
+        else tile_prepare_kernel<false><<<pg, 256, 0, ctx->stream>>>(Q, (TileInfo*)b->tile_recs_dev, (SumRec*)Q.sum_recs);
         MAFE_LAUNCH_CHECK(ctx);
       }
-      static const bool no_tmem = getenv("MAFE_NO_TMEM") != nullptr;           // A/B switch: constants from shared memory
-      static const bool no_fuse = getenv("MAFE_NO_FUSED_CMVN") != nullptr;     // A/B switch: separate CMVN apply kernel
-      const bool fuse = cmvn && !no_tmem && !no_fuse;
       if (fuse) {
-        if (b->cap_utt_done < (size_t)b->n_utts) {   // grow-only
+        if (b->cap_utt_done < (size_t)b->n_utts) {   // grow-only; two counters per utterance (tiles finished, tiles summed)
           if (b->utt_done_dev) MAFE_CUDA_CHECK(cudaFree(b->utt_done_dev));
           b->utt_done_dev = nullptr; b->cap_utt_done = 0;
           const size_t cap = (size_t)b->n_utts + (size_t)b->n_utts / 4 + 16;
-          MAFE_CUDA_CHECK(cudaMalloc((void**)&b->utt_done_dev, cap * sizeof(int32_t)));
+          MAFE_CUDA_CHECK(cudaMalloc((void**)&b->utt_done_dev, 2 * cap * sizeof(int32_t)));
           b->cap_utt_done = cap;
         }
-        MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_done_dev, 0, sizeof(int32_t) * b->n_utts, ctx->stream));
+        MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_done_dev, 0, sizeof(int32_t) * 2 * b->n_utts, ctx->stream));
         Q.utt_done = b->utt_done_dev;
+        Q.fsum_done = b->utt_done_dev + b->n_utts;
         // the normalisation of a tile trails its computation by `lag` queue items: at least the longest utterance in tiles
         // (deadlock freedom), plus three rounds of the resident CTAs (a finished tile is published one iteration later; the
         // wait is then almost never entered).  ~1.4 k tiles = 14 MB of features + 28 MB of waveform in between: L2 resident
@@ -1123,6 +1152,14 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
         Q.mean_norm = d.utt_cmvn_mean; Q.std_norm = d.utt_cmvn_std;
       }
       ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
+      if (fs) {
+        if (wave_dtype == MAFE_WAVE_I16)
+          fbank512_v6_kernel<true, true, true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+        else
+          fbank512_v6_kernel<false, true, true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);
+        MAFE_LAUNCH_CHECK(ctx);
+        return MAFE_OK;
+      }
       if (fuse) {
         if (wave_dtype == MAFE_WAVE_I16)
           fbank512_v6_kernel<true, true, true><<<grid3, kFastThreads, V6Smem::kTotal, ctx->stream>>>(Q, th->sweep6);

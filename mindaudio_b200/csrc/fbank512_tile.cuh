@@ -36,10 +36,16 @@ struct V2Params {
   float* out;
   int* queue_head;               // dynamic work queue: next unclaimed tile index
   const void* tile_recs;         // v6: TileInfo[n_tiles], prepared per step by tile_prepare_kernel
+  const void* sum_recs;          // v6 FS: SumRec[n_tiles]
   // v6 with the utterance CMVN applied inside the persistent kernel (fbank512_v6.cuh, FUSE):
   int* utt_done;                 // [n_utts] tiles of the utterance whose features and statistics are complete (zeroed per step)
   int lag;                       // the CTA that claims tile w also normalises tile w - lag; >= the longest utterance in tiles
   int mean_norm, std_norm;
+  // v6 with the frame-mean sums accumulated inside the persistent kernel (FS): the pre-pass kernel is gone
+  int lag_s;                     // the CTA that claims item w sums tile w and transforms tile w - lag_s (0: pre-pass sums)
+  const float* cover4;           // [4][kCwRow] c'(r) = c(r) - preemph c(r + 1), copy k shifted by k entries
+  double* utt_fsum;              // [n_utts] sum_s x[s] c'(s) (zeroed per step)
+  int* fsum_done;                // [n_utts] tiles of the utterance whose samples have been summed (zeroed per step)
 };
 
 struct TileInfo {  // geometry of one work item, prepared by thread 0 one iteration ahead
@@ -52,6 +58,17 @@ struct TileInfo {  // geometry of one work item, prepared by thread 0 one iterat
   int T;              // frames of the tile's utterance
 };
 static_assert(sizeof(TileInfo) <= 64, "TileInfo slot");
+
+struct SumRec {  // FS (fbank512_v6.cuh): what the frame-sum duty of one tile needs, prepared per step by tile_prepare_kernel
+  int64_t ga;       // element index of the first 16 B-aligned sample group of the tile's periodic region
+  int nvec;         // 16-byte groups from there on
+  int r0;           // (sample index of ga inside the utterance) mod 160
+  int n_head;       // samples of the periodic region before ga (< group size), n_tail: behind the last group
+  int n_tail;
+  int utt;
+  int edge;         // first / last tile of an utterance: samples outside the periodic region exist (general rule)
+};
+static_assert(sizeof(SumRec) == 32, "SumRec slot");
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy (SASS: SYNCS.*, UBLKCP)
@@ -118,7 +135,7 @@ __device__ __forceinline__ TileSrc<I16> tile_src(const V2Params& P, const Tile t
 // pre-pass: the persistent kernel's producer thread then only copies a 64-byte record and issues the bulk copy -- the
 // 64-bit address arithmetic and the double division of the frame mean left its critical path.
 template <bool I16>
-__global__ void __launch_bounds__(256) tile_prepare_kernel(const V2Params P, TileInfo* __restrict__ recs) {
+__global__ void __launch_bounds__(256) tile_prepare_kernel(const V2Params P, TileInfo* __restrict__ recs, SumRec* __restrict__ srecs) {
   constexpr int ES = I16 ? 2 : 4;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_tiles) return;
@@ -136,10 +153,35 @@ __global__ void __launch_bounds__(256) tile_prepare_kernel(const V2Params P, Til
   r.utt = tile.utt;
   r.nf = min(kTileFrames, T - tile.frame0);
   r.shift = src.shift;
-  r.neg_mu = P.remove_mean ? -(float)(P.utt_sum[tile.utt] / ((double)T * (double)kV2Flen)) : 0.f;
+  // FS: the sums do not exist yet -- the record carries scale / (400 T); the persistent kernel turns it into -mu
+  if (P.lag_s > 0) r.neg_mu = (float)((double)P.wave_scale / ((double)T * (double)kV2Flen));
+  else r.neg_mu = P.remove_mean ? -(float)(P.utt_sum[tile.utt] / ((double)T * (double)kV2Flen)) : 0.f;
   r.bytes = src.bytes;
   r.T = T;
   recs[i] = r;
+  if (P.lag_s > 0) {
+    constexpr int V = I16 ? 8 : 4;
+    const int64_t s_lo = r.s0;
+    const int64_t framed_end = (int64_t)(T - 1) * kV2Hop + kV2Flen;
+    const bool last = s_lo + (int64_t)kTileFrames * kV2Hop >= (int64_t)T * kV2Hop;
+    const int64_t s_hi = last ? framed_end : s_lo + (int64_t)kTileFrames * kV2Hop;
+    // periodic region of c'(s): frames q, q - 1, q - 2 of s and of s + 1 all exist
+    int64_t f_lo = s_lo > 2 * kV2Hop ? s_lo : 2 * kV2Hop, f_hi = (int64_t)T * kV2Hop - 1;
+    if (f_hi > s_hi) f_hi = s_hi;
+    if (f_hi < f_lo) { f_lo = s_hi; f_hi = s_hi; }
+    const int64_t ga0 = (off + f_lo + V - 1) / V * V;   // the flat array itself is 16 B aligned
+    int64_t sa = ga0 - off;
+    if (sa > f_hi) sa = f_hi;
+    SumRec q;
+    q.ga = off + sa;
+    q.nvec = (int)((f_hi - sa) / V);
+    q.r0 = (int)(sa % kV2Hop);
+    q.n_head = (int)(sa - f_lo);
+    q.n_tail = (int)(f_hi - (sa + (int64_t)q.nvec * V));
+    q.utt = tile.utt;
+    q.edge = (s_lo < f_lo || f_hi < s_hi) ? 1 : 0;
+    srecs[i] = q;
+  }
 }
 
 // 256-point transform of v by the 16-lane group; result (bin 2*(t+16kt)+HALF at slot[t+16kt])

@@ -266,9 +266,156 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   return v;
 }
 __device__ __forceinline__ void red_relaxed_inc(int* p) { asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 
+// FS: the frame-mean sums inside the persistent kernel.  The reference subtracts ONE scalar per utterance -- the mean of the
+// whole windowed frame matrix (dataset.py:165) -- so every sample must be seen before any frame of the utterance can be
+// transformed; round 1 / early round 2 ran a streaming pre-pass kernel over the whole batch (0.96 ms, 5.5 GB: the waveform
+// came from HBM twice).  Now the queue runs lag_s items ahead of the transforms: the CTA that claims item w first adds
+//     sum_s x[s] c'(s),   c'(s) = c(s) - a c(s + 1)   (c = window summed over the frames covering s, a = pre-emphasis:
+//                                                        sum_s y[s] c(s) with y[s] = x[s] - a x[s - 1] telescopes)
+// over the samples tile w owns to utt_fsum[utt] (release + counter, like the CMVN duty), then transforms tile w - lag_s,
+// whose utterance is complete by then; the transform's bulk copy finds the samples in L2 (read ~lag_s tiles = 30 MB ago).
+// Inside an utterance c' has period 160: 240 threads take 16-byte groups 160 samples apart, so a thread's coefficients are
+// the same for all its groups of a tile (ONE 16-byte shared-memory load per thread and tile, from the copy of the table
+// shifted by r mod 4); the first 320 samples and the tail of an utterance use the general rule.
+#ifndef MAFE_FS_POLICY
+#define MAFE_FS_POLICY 1
+#endif
+#ifndef MAFE_FS_WARP7
+#define MAFE_FS_WARP7 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 
-template <bool I16, bool TM, bool FUSE>
+// This thread's part of sum_s x[s] c'(s) over the samples tile `sr` owns (FS above): issue() = every global load,
+// finish() = coefficients + FMAs.
+template <bool I16>
+struct V6Sum {
+  static constexpr int V = I16 ? 8 : 4;                       // samples per 16-byte group
+  static constexpr int GP = kV2Hop / V;                       // groups per period (40 / 20)
+  static constexpr int NT = (kFastThreads / GP) * GP;         // threads taking part (240)
+  static constexpr int PSTEP = NT / GP;                       // periods per sweep of the CTA (6 / 12)
+  static constexpr int KMAX = (kTileFrames + PSTEP - 1) / PSTEP;
+  int4 raw[KMAX];
+  int h0, h1;        // scalar head / tail samples around the 16 B-aligned groups (raw bits), coefficient indices
+  int i0, i1, r;
+  float acc;
+
+  static __device__ __forceinline__ int ld_raw(const void* wave, int64_t g) {
+    if (I16) return (int)__ldg((const int16_t*)wave + g);
+    return __float_as_int(__ldg((const float*)wave + g));
+  }
+  static __device__ __forceinline__ float to_f(int v) { return I16 ? (float)v : __int_as_float(v); }
+
+  __device__ __forceinline__ void issue(const V2Params& P, const SumRec& sr, const TileInfo* __restrict__ grec, int tid) {
+    acc = 0.f;
+    h0 = 0; h1 = 0; i0 = 0; i1 = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) raw[k] = make_int4(0, 0, 0, 0);
+    const int64_t ga = sr.ga;
+    const int nvec = sr.nvec, r0 = sr.r0;
+    if (sr.edge) {   // first / last tile of an utterance: the general rule outside the periodic region (2 of ~33 tiles)
+      const TileInfo si = *grec;
+      const int T = si.T;
+      const int need = (si.nf - 1) * kV2Hop + kV2Flen;
+      const int64_t off = si.end_elem - si.s0 - need;      // the utterance's first sample in the flat array
+      const int64_t s_lo = si.s0;
+      const int64_t framed_end = (int64_t)(T - 1) * kV2Hop + kV2Flen;
+      const bool last = s_lo + (int64_t)kTileFrames * kV2Hop >= (int64_t)T * kV2Hop;
+      const int64_t s_hi = last ? framed_end : s_lo + (int64_t)kTileFrames * kV2Hop;
+      const int64_t f_lo = ga - off - sr.n_head, f_hi = ga - off + (int64_t)nvec * V + sr.n_tail;
+      auto cgen = [&](int64_t q) -> float {
+        if (q >= framed_end) return 0.f;
+        const int64_t th = q / kV2Hop;
+        const int t_hi = (int)(th < T - 1 ? th : T - 1);
+        float c = 0.f;
+        for (int tt = t_hi; tt >= 0; --tt) {
+          const int64_t n = q - (int64_t)tt * kV2Hop;
+          if (n >= kV2Flen) break;
+          c += __ldg(&P.window[n]);
+        }
+        return c;
+      };
+      auto edge = [&](int64_t q) {
+        const float x = to_f(ld_raw(P.wave, off + q));
+        const float c1 = cgen(q + 1);
+        acc = fmaf(x, fmaf(-P.pre_lo, c1, fmaf(-P.pre_hi, c1, cgen(q))), acc);
+      };
+      for (int64_t q = s_lo + tid; q < f_lo; q += kFastThreads) edge(q);
+      for (int64_t q = f_hi + tid; q < s_hi; q += kFastThreads) edge(q);
+    }
+    if (tid < sr.n_head) {
+      h0 = ld_raw(P.wave, ga - sr.n_head + tid);
+      i0 = r0 - sr.n_head + tid;
+      if (i0 < 0) i0 += kV2Hop;
+    }
+    if (tid < sr.n_tail) {
+      h1 = ld_raw(P.wave, ga + (int64_t)nvec * V + tid);
+      i1 = (r0 + nvec * V + tid) % kV2Hop;
+    }
+    const int rho = tid % GP, p0 = tid / GP;
+    r = r0 + V * rho;
+    if (r >= kV2Hop) r -= kV2Hop;
+    if (tid < NT) {
+      const int4* src = reinterpret_cast<const int4*>((const unsigned char*)P.wave + ga * (I16 ? 2 : 4));
+#if MAFE_FS_POLICY
+      const uint64_t pol = l2_policy_evict_last();   // the transform's bulk copy wants these lines again ~lag_s tiles from now
+#endif
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int q = rho + GP * (p0 + PSTEP * k);
+#if MAFE_FS_POLICY
+        if (q < nvec) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                                   : "=r"(raw[k].x), "=r"(raw[k].y), "=r"(raw[k].z), "=r"(raw[k].w) : "l"(src + q), "l"(pol));
+#else
+        if (q < nvec) asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(raw[k].x), "=r"(raw[k].y), "=r"(raw[k].z), "=r"(raw[k].w) : "l"(src + q));
+#endif
+      }
+    }
+  }
+
+  __device__ __forceinline__ float finish(const float* __restrict__ s_cp4) {
+    const float* crow = s_cp4 + (r & 3) * kCwRow + (r - (r & 3));   // crow[i] = c'((r + i) mod 160), 16 B aligned
+    float c[V];
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(crow + i);
+      c[i] = c4.x; c[i + 1] = c4.y; c[i + 2] = c4.z; c[i + 3] = c4.w;
+    }
+    float a = fmaf(to_f(h0), s_cp4[i0], fmaf(to_f(h1), s_cp4[i1], acc));   // absent samples are zero bits
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {   // absent groups are zero
+      const int w4[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+      if (I16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a = fmaf((float)(int16_t)(w4[i] & 0xffff), c[(2 * i) % V], a);
+          a = fmaf((float)(int16_t)(w4[i] >> 16), c[(2 * i + 1) % V], a);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a = fmaf(__int_as_float(w4[i]), c[i % V], a);
+      }
+    }
+    return a;
+  }
+};
+
+template <bool I16, bool TM, bool FUSE, bool FS = false>
 __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __grid_constant__ V2Params P,
                                                                       const __grid_constant__ V6Sweep S) {
   using SM = V6Smem;
@@ -289,9 +436,17 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   float* s_norm = reinterpret_cast<float*>(smem + SM::kNorm);
   uint64_t* abar = reinterpret_cast<uint64_t*>(smem + SM::kABar);
   constexpr int ES = I16 ? 2 : 4;
+  static_assert(!FS || (TM && FUSE), "the frame-sum duty uses the shared memory the TMEM variant leaves idle");
+  static_assert(2 * sizeof(SumRec) + kFastThreads * sizeof(float) <= sizeof(float) * 400 && sizeof(float) * 4 * kCwRow <= 2 * sizeof(float2) * 256, "FS tables");
+  SumRec* sinfo = reinterpret_cast<SumRec*>(smem + SM::kWin);              // FS: [2] records of the tiles being summed
+  float* s_ws = reinterpret_cast<float*>(smem + SM::kWin + 2 * sizeof(SumRec));     // FS: [256] per-thread partial sums
+  float* s_cp4 = reinterpret_cast<float*>(smem + SM::kW512);               // FS: c' table, 4 shifted copies
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* s_tm = reinterpret_cast<uint32_t*>(smem + SM::kBar) + 6;   // TMEM base address of this CTA
+  if (FS) {
+    for (int i = tid; i < 4 * kCwRow; i += kFastThreads) s_cp4[i] = P.cover4[i];
+  }
   if (!TM) {
     for (int i = tid; i < kV2Flen; i += kFastThreads) s_win[i] = P.window[i];
     for (int i = tid; i < 256; i += kFastThreads) { s_w512[i] = P.w512[i]; s_w256[i] = P.w256t[i]; }
@@ -355,14 +510,25 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   // counter: uneven tiles balance by themselves.
   const TileInfo* recs = reinterpret_cast<const TileInfo*>(P.tile_recs);
   int nx_w = P.n_tiles;
-  auto fetch_rec = [&](int slot_i) {   // asynchronous 64-byte copy global -> shared
-    const uint32_t dst = smem_u32(&info[slot_i]);
-    const unsigned char* srcp = reinterpret_cast<const unsigned char*>(recs + nx_w);
+  const int lag_s = FS ? P.lag_s : 0;
+  auto fetch_to = [&](TileInfo* dstp, int tile_i) {   // asynchronous 64-byte copy global -> shared
+    const uint32_t dst = smem_u32(dstp);
+    const unsigned char* srcp = reinterpret_cast<const unsigned char*>(recs + tile_i);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * q), "l"(srcp + 16 * q) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  auto fetch_rec = [&](int slot_i) { fetch_to(&info[slot_i], nx_w - lag_s); };
+  const SumRec* srecs = reinterpret_cast<const SumRec*>(P.sum_recs);
+  auto fetch_srec = [&](int slot_i) {   // 32-byte sum record of tile nx_w; the tile's samples start their way into L2
+    const uint32_t dst = smem_u32(&sinfo[slot_i]);
+    const unsigned char* srcp = reinterpret_cast<const unsigned char*>(srecs + nx_w);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(srcp + 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto next_main = [&]() { return nx_w - lag_s >= 0 && nx_w - lag_s < P.n_tiles; };   // the next item transforms a tile
   auto issue_tile = [&](int slot_i) {  // the record has landed: bulk copy of the tile's bytes
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     const uint32_t bytes = info[slot_i].bytes;
@@ -370,17 +536,24 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
       mbar_expect_tx(&bars[slot_i], bytes);
-      tma_bulk_g2s(rb, (const unsigned char*)P.wave + ga_byte, bytes, &bars[slot_i]);
+      if (FS && MAFE_FS_POLICY)   // the last use of these lines
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         smem_u32(rb)), "l"((const unsigned char*)P.wave + ga_byte), "r"(bytes), "r"(smem_u32(&bars[slot_i])), "l"(l2_policy_evict_first()) : "memory");
+      else
+        tma_bulk_g2s(rb, (const unsigned char*)P.wave + ga_byte, bytes, &bars[slot_i]);
     } else {
       mbar_arrive(&bars[slot_i]);
     }
   };
 
-  const int n_items = FUSE ? P.n_tiles + P.lag : P.n_tiles;   // queue length: lag normalisation-only items at the end
-  if (tid == 0) {   // prologue: the first tile, all stages back to back
+  // queue: item w sums tile w (FS), transforms tile w - lag_s, normalises tile w - lag_s - lag (FUSE)
+  const int n_items = P.n_tiles + lag_s + (FUSE ? P.lag : 0);
+  if (tid == 0) {   // prologue: the first item, all stages back to back (with FS it is a sum-only item: lag_s > grid)
     nx_w = atomicAdd(P.queue_head, 1);
     s_work[0] = nx_w;
-    if (nx_w < P.n_tiles) { fetch_rec(0); issue_tile(0); }
+    if (FS && nx_w < P.n_tiles) fetch_srec(0);
+    if (next_main()) { fetch_rec(0); issue_tile(0); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   // service thread (the last thread of the CTA: its warp has only half a share of phase C): utterance of the tile this CTA
@@ -393,6 +566,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     prev_utt = -1;
   };
   uint32_t a_cnt = 0;                          // normalisation duties done by this CTA (parity of abar)
+  int m_utt = 0, m_need = 0, m_flag = 0;       // FS (thread 0): utterance of the next tile to transform, its tile count, tiles summed
 
   const int t = lane & 15;
   const int pair = warp * 2 + (lane >> 4);
@@ -408,18 +582,32 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
   const int cg = tid / kV2Mels, cm = tid - cg * kV2Mels;
   const int f_begin = S.f0[warp], f_end = S.f0[warp + 1], nw = S.nw[warp], wbase = S.wbase[warp];
 
-  // iteration it uses info / barrier slot it & 1; the slot's mbarrier completes its (it >> 1)-th phase
+  // iteration it uses info / barrier slot it & 1; the slot's mbarrier completes its ((it - it0) >> 1)-th phase
+  uint32_t it0 = FS ? 0xffffffffu : 0u;
   for (uint32_t it = 0;; ++it) {
     const int buf = it & 1;
     const int w = s_work[buf];
     if (w >= n_items) break;
-    const bool main_tile = !FUSE || w < P.n_tiles;
-    const bool duty = FUSE && w >= P.lag;              // normalise tile w - lag
+    const int u = w - lag_s;                           // the tile this item transforms
+    const bool main_tile = u >= 0 && u < P.n_tiles;
+    const bool duty = FUSE && u >= P.lag;              // normalise tile u - lag
+    const bool sum_duty = FS && w < P.n_tiles;         // sum the samples of tile w
     if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1 (issue): claim the next item
+#if MAFE_FS_WARP7
+    if (FS && sum_duty) { V6Sum<I16> fsum; fsum.issue(P, sinfo[buf], recs + w, tid); s_ws[tid] = fsum.finish(s_cp4); }   // reduced by warp 7 after the third barrier
+#else
+    if (FS && sum_duty) {
+      V6Sum<I16> fsum;
+      fsum.issue(P, sinfo[buf], recs + w, tid);
+      float fs = fsum.finish(s_cp4);
+      for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
+      if (lane == 0) s_ws[warp] = fs;                  // read by the service thread after the third barrier
+    }
+#endif
     if (FUSE && svc) {
       if (duty) {                          // the duty tile's record -> ainfo (asynchronous)
         const uint32_t dst = smem_u32(ainfo);
-        const unsigned char* srcp = reinterpret_cast<const unsigned char*>(recs + (w - P.lag));
+        const unsigned char* srcp = reinterpret_cast<const unsigned char*>(recs + (u - P.lag));
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * q), "l"(srcp + 16 * q) : "memory");
@@ -432,7 +620,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     float neg_mu = 0.f;
     if (main_tile) {
     // wait for this tile's bytes
-    mbar_wait(&bars[buf], (it >> 1) & 1);
+    if (FS && it0 == 0xffffffffu) it0 = it;   // FS: the first items of a CTA only sum -- the slots' phases count from its first transform
+    mbar_wait(&bars[buf], ((it - it0) >> 1) & 1);
     // scalar patch-up of what the 16 B-granular bulk copy could not cover (end of the flat array)
     if (cur.cov_end < cur.end_elem) {
       for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
@@ -500,7 +689,13 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     neg_mu = cur.neg_mu;
     }   // main_tile (pass P)
     __syncthreads();
-    if (tid == 0) s_work[buf ^ 1] = nx_w;   // stage 2: the claim has arrived during pass P -> publish it
+    if (tid == 0) {
+      s_work[buf ^ 1] = nx_w;   // stage 2: the claim has arrived during pass P -> publish it
+      if (FS) {                 // FS: both records of the next item travel during the FFT phase (its -mu needs two more round trips)
+        if (nx_w < P.n_tiles) fetch_srec(buf ^ 1);
+        if (next_main()) fetch_rec(buf ^ 1);
+      }
+    }
     if (FUSE && svc && duty) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       a_need = (ainfo->T + kTileFrames - 1) / kTileFrames;
@@ -582,7 +777,24 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     }
     __syncthreads();
     // stage 3: the next tile's record travels to the other info slot during the mel projection
-    if (tid == 0 && nx_w < P.n_tiles) fetch_rec(buf ^ 1);
+    if (!FS && tid == 0 && nx_w < P.n_tiles) fetch_rec(buf ^ 1);
+    if (FS && tid == 0) {   // the records have landed: how many tiles of the next tile's utterance have been summed? (used after the mel stage)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (nx_w < P.n_tiles) {   // the next item's samples: on their way into L2 now, read by the whole CTA one iteration later
+        const SumRec& nr = sinfo[buf ^ 1];
+        const uint32_t pbytes = (uint32_t)nr.nvec * 16u;
+#if MAFE_FS_POLICY
+        if (pbytes) asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"((const unsigned char*)P.wave + nr.ga * ES), "r"(pbytes), "l"(l2_policy_evict_last()) : "memory");
+#else
+        if (pbytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const unsigned char*)P.wave + nr.ga * ES), "r"(pbytes) : "memory");
+#endif
+      }
+      if (next_main()) {
+        m_utt = info[buf ^ 1].utt;
+        m_need = (info[buf ^ 1].T + kTileFrames - 1) / kTileFrames;
+        m_flag = ld_relaxed(P.fsum_done + m_utt);
+      }
+    }
     double st_s1 = 0.0, st_s2 = 0.0;
     if (FUSE && duty) {
       if (svc) {   // the duty tile's raw log-mel rows come back from L2 into the (now idle) waveform buffer
@@ -628,10 +840,36 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
     }
     __syncthreads();
     // the Z region has been read for the last time -> the next tile's waveform may land in its upper part
-    if (tid == 0 && nx_w < P.n_tiles) issue_tile(buf ^ 1);
+    if (tid == 0 && next_main()) issue_tile(buf ^ 1);
+    double m_sum = 0.0;
+    if (FS && tid == 0 && next_main()) {
+      // its utterance's sum: complete unless this CTA is early (rare: lag_s covers the longest utterance + three rounds of the
+      // resident CTAs).  The load is issued after the branch on the counter and served by L2, where the writers' fences put
+      // the sum before the counter; it is consumed after phase C.
+      while (m_flag != m_need) m_flag = ld_acquire(P.fsum_done + m_utt);
+      m_sum = ld_cg_f64(P.utt_fsum + m_utt);
+    }
     // the tile this CTA finished in the previous iteration: its feature stores and statistics atomics were issued before
-    // barriers passed since -> publish it (here, where the service thread's warp has slack)
-    if (FUSE && svc && prev_utt >= 0) publish();
+    // barriers passed since -> publish it (here, where the service thread's warp has slack); FS: and this item's sample sum
+    if (FS) {
+      float t8 = 0.f;
+#if MAFE_FS_WARP7
+      if (sum_duty && warp == kFastWarps - 1) {   // the service thread's warp adds the CTA's 256 partial sums
+        const float4 a4 = *reinterpret_cast<const float4*>(s_ws + 8 * lane), b4 = *reinterpret_cast<const float4*>(s_ws + 8 * lane + 4);
+        t8 = ((a4.x + a4.y) + (a4.z + a4.w)) + ((b4.x + b4.y) + (b4.z + b4.w));
+        for (int o = 16; o > 0; o >>= 1) t8 += __shfl_xor_sync(0xffffffffu, t8, o);
+      }
+#else
+      if (svc && sum_duty) t8 = ((s_ws[0] + s_ws[1]) + (s_ws[2] + s_ws[3])) + ((s_ws[4] + s_ws[5]) + (s_ws[6] + s_ws[7]));
+#endif
+      if (svc && (sum_duty || prev_utt >= 0)) {
+        const int s_utt = sinfo[buf].utt;
+        if (sum_duty) atomicAdd(P.utt_fsum + s_utt, (double)t8);
+        __threadfence();
+        if (sum_duty) red_relaxed_inc(P.fsum_done + s_utt);
+        if (prev_utt >= 0) { red_relaxed_inc(P.utt_done + prev_utt); prev_utt = -1; }
+      }
+    } else if (FUSE && svc && prev_utt >= 0) publish();
     float* part = stage;  // [3][2][80] per-group CMVN partial sums (lower part of the Z region, free after the sweep)
     if (main_tile) {
 
@@ -697,6 +935,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __gr
         o4[q] = make_float4((v.x - mu.x) * iv.x, (v.y - mu.y) * iv.y, (v.z - mu.z) * iv.z, (v.w - mu.w) * iv.w);
       }
     }
+    if (FS && tid == 0 && next_main()) info[buf ^ 1].neg_mu = -((float)m_sum * info[buf ^ 1].neg_mu);   // the record carried scale / (400 T)
     __syncthreads();   // the next tile's geometry (thread 0, above) and the partial sums are visible
     if (FUSE && svc && main_tile) prev_utt = cur.utt;
     // per-utterance CMVN statistics: one double atomic per (filter, moment)

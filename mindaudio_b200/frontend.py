@@ -50,28 +50,36 @@ def ds2_features(audio, n_fft=320, hop_length=160, win_length=320, window="hann"
     YAML's hamming is never passed --, centred, constant padding) -> ``magphase(power=1)`` -> ``log1p`` -> scalar
     ``(m - m.mean()) / m.std()`` over the whole matrix.  One transform kernel writes ``log1p(|X|)`` directly (no complex
     spectrum, no separate magnitude pass) and accumulates the utterance's moments (plan flag ``utt_scalar_norm``); one
-    streaming pass normalises.  float32 ``[n_fft // 2 + 1, T]`` like the reference.  ``audio``: 1-D waveform."""
-    x = np.ascontiguousarray(np.asarray(audio), dtype=np.float32).reshape(-1)
-    if n_fft > x.shape[0]:
-        raise ValueError("n_fft={} is too small for input signal of length={}".format(n_fft, x.shape[0]))
+    streaming pass normalises.  float32 ``[n_fft // 2 + 1, T]`` like the reference.  ``audio``: a 1-D waveform, or a list
+    of waveforms (one ragged batch, one launch; every utterance normalised by its own moments) -> a list of matrices."""
+    many = isinstance(audio, (list, tuple))
+    xs = [np.ascontiguousarray(np.asarray(a), dtype=np.float32).reshape(-1) for a in (audio if many else [audio])]
+    for x in xs:
+        if n_fft > x.shape[0]:
+            raise ValueError("n_fft={} is too small for input signal of length={}".format(n_fft, x.shape[0]))
     eng = get_engine()
     plan = eng.plan(n_fft=n_fft, hop=hop_length, center=True, pad_mode="constant", out_kind=L.OUT_POWER,
                     window=T.analysis_window(window, win_length, n_fft), power=1.0, log_kind=L.LOG_LN_PLUS, log_arg=1.0,
                     utt_scalar_norm=bool(normalize))
+    offs = np.zeros(len(xs) + 1, dtype=np.int64)
+    np.cumsum([x.shape[0] for x in xs], out=offs[1:])
+    flat = xs[0] if len(xs) == 1 else np.concatenate(xs)
     with eng.lock:
-        b = eng.batch(plan, np.array([0, x.shape[0]], dtype=np.int64))
+        b = eng.batch(plan, offs)
         try:
             out = np.empty((b.total_frames, plan.out_dim), dtype=np.float32)
-            dw = eng.buf("wave", x.nbytes)
+            fo = np.array(b.frame_offsets, dtype=np.int64)
+            dw = eng.buf("wave", flat.nbytes)
             do = eng.buf("out", out.nbytes)
-            keep = eng.h2d(dw, x)
+            keep = eng.h2d(dw, flat)
             L.check(eng.lib.mafe_frontend_run(eng.ctx, plan.h, b.h, dw, L.WAVE_F32, 1.0, do, L.DBGROUP_NONE))
             eng.d2h(out, do)
             eng.sync()
             del keep
         finally:
             b.close()
-    return np.ascontiguousarray(out.T)
+    mats = [np.ascontiguousarray(out[fo[i]:fo[i + 1]].T) for i in range(len(xs))]
+    return mats if many else mats[0]
 
 
 class FbankPipeline:

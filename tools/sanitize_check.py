@@ -41,4 +41,11 @@ ma.mfcc(x22, n_fft=2048, n_mels=128, n_mfcc=64, hop_length=256, deltas=False, co
 many = [np.round(synth(200 + i, (int(n),)) * 32768).astype(np.float32) for i, n in enumerate(rng.integers(400, 9000, size=96))]
 pipe = ma.FbankPipeline(cmvn="utt")
 pipe.features(many, chunk_utts=40)
+# the deepspeech2 output kind (log1p|X| + scalar normalisation, moments accumulated by the transform)
+ma.ds2_features([x22[0], x22[1, :4000]])
+# frame-mean sums inside the persistent kernel (needs >= 12 tiles per SM): ragged, with one- and two-frame utterances
+big_l = [int(v) for v in rng.integers(20000, 40000, size=420)] + [400, 560, 399, 0, 5520, 5521]
+big = [np.round(synth(900 + i, (n,)) * 32768).astype(np.float32) for i, n in enumerate(big_l)]
+pipe.features(big, chunk_utts=len(big))
+pipe.features([w.astype(np.int16) for w in big], chunk_utts=len(big))
 print("sanitize script ok")
