@@ -13,6 +13,7 @@
 // the DCT of MFCC run in the existing follow-up kernels (db_clamp_kernel, dct_kernel).
 #pragma once
 #include "fft400.cuh"
+#include "packed.cuh"
 
 namespace mafe {
 
@@ -49,7 +50,7 @@ struct F400Params {
   int log_kind;
   float log_arg, log_mult, log_offset;
   const float* window;     // [400], pre-scaled by spec_scale * wave_scale * 1/2
-  const float2* tw400;     // [25][16]  W400^(t kj)
+  const float2* tw400;     // [25][32]  W400^(t kj), t = 0..31 (t >= 16: the rotated upper half-warp, see stftn16.cuh)
   const int* combine;      // [n_mels]: plane rows A | B << 8 holding the filter's partial sums
   float* out;              // [total_frames][n_mels]
   int* queue_head;
@@ -66,16 +67,16 @@ struct F400TileInfo {
 };
 static_assert(sizeof(F400TileInfo) <= 96, "F400TileInfo slot");
 
-// dynamic shared memory: [Z 54400][planes rows*33*4][window 1600][tw400 3200][bars 32][info 192][skewed tile copy]
+// dynamic shared memory: [Z 54400][planes rows*33*4][bars 32][info 192]   (window and W400 twiddles: tensor memory)
 __host__ __device__ inline size_t f400_planes_bytes(int rows) { return ((size_t)rows * kPlaneStride * 4 + 15) & ~(size_t)15; }
-// second copy of the waveform tile, 16 banks away from the first (which lands at float kRaw400InZ / 4 = 0 mod 32 of Z)
-__host__ __device__ inline size_t f400_skew_offset(int rows) {
-  return ((kZ400Bytes + f400_planes_bytes(rows) + 1600 + 3200 + 32 + 192 + 127) & ~(size_t)127) + 64;
-}
-__host__ __device__ inline size_t f400_smem_bytes(int rows) { return f400_skew_offset(rows) + kRaw400Bytes; }
-static_assert((kRaw400InZ / 4) % 32 == 0, "tile copy 0 starts on bank 0");
+__host__ __device__ inline size_t f400_smem_bytes(int rows) { return kZ400Bytes + f400_planes_bytes(rows) + 32 + 192; }
+static_assert((kRaw400InZ / 4) % 32 == 0, "the tile starts on bank 0");
+#ifndef MAFE_F400_CTAS
+#define MAFE_F400_CTAS 2
+#endif
+static_assert(MAFE_F400_CTAS * (kZ400Bytes + ((kMaxRows400 * kPlaneStride * 4 + 15) & ~15) + 32 + 192 + 1024) <= 227 * 1024, "CTAs per SM");
 
-__global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_constant__ F400Params P,
+__global__ void __launch_bounds__(kFastThreads, MAFE_F400_CTAS) fbank400_kernel(const __grid_constant__ F400Params P,
                                                                    const __grid_constant__ F400Sweep S) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int nm = P.n_mels;
@@ -83,27 +84,57 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
   float* rawz = reinterpret_cast<float*>(smem + kRaw400InZ);
   float* planes = reinterpret_cast<float*>(smem + kZ400Bytes);
   unsigned char* tail_base = smem + kZ400Bytes + f400_planes_bytes(P.plane_rows);
-  float* s_win = reinterpret_cast<float*>(tail_base);
-  float2* s_tw = reinterpret_cast<float2*>(tail_base + 1600);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail_base + 1600 + 3200);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail_base);
   int* s_work = reinterpret_cast<int*>(bars) + 4;
-  F400TileInfo* info = reinterpret_cast<F400TileInfo*>(tail_base + 1600 + 3200 + 32);
+  F400TileInfo* info = reinterpret_cast<F400TileInfo*>(tail_base + 32);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hop = P.hop;
-  // the upper half-warp's pair starts 2 * hop floats after the lower one (hop 160: same bank): it reads a second copy
-  // of the tile that sits 16 banks away whenever the natural offset would collide
+  // The upper half-warp's pair starts 2 * hop floats after the lower one (hop 160: same bank).  When the two would collide it
+  // reads its frame rotated by one block of 16 samples; the per-lane constants in tensor memory (window entries, W400
+  // twiddles) are those of t + 16, which absorbs the rotation -- see stftn16.cuh (round 1: a second, skewed copy of the tile).
   const int pair_banks = (2 * hop) & 31;
-  const bool use_skew = pair_banks < 8 || pair_banks > 24;
-  const int skew = (int)((f400_skew_offset(P.plane_rows) - kRaw400InZ) / 4);   // floats from copy 0 to copy 1
-  for (int i = tid; i < kN400; i += kFastThreads) { s_win[i] = P.window[i]; s_tw[i] = P.tw400[i]; }
+  const int rot = ((pair_banks < 8 || pair_banks > 24) && (lane >> 4)) ? 1 : 0;
   if (tid < kPlaneStride) planes[S.zero_row * kPlaneStride + tid] = 0.f;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // per-lane constants in tensor memory (helpers in fbank512_v6.cuh): columns 0..24 w[t + 16 j], 32 + 2 (kj - 1) W400^(t kj)
+  uint32_t* s_tm = reinterpret_cast<uint32_t*>(bars) + 6;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(s_tm)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = *s_tm + ((uint32_t)(32 * (warp & 3)) << 16);
+  if (warp < 4) {
+    const int tt = lane & 15;
+    float c8[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c8[i] = 8 * c + i < 25 ? P.window[tt + 16 * ((8 * c + i + rot) % 25)] : 0.f;
+      tm_st8(tb + 8 * c, c8);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kj = 4 * c + 1 + i;
+        const float2 w = kj < 25 ? P.tw400[kj * 32 + tt + 16 * rot] : make_float2(0.f, 0.f);
+        c8[2 * i] = w.x; c8[2 * i + 1] = w.y;
+      }
+      tm_st8(tb + 32 + 8 * c, c8);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- staged preparation of the next tile by thread 0 (see fbank512_v3.cuh) ----
   // Centre padding: the first tile of an utterance lands `pad` floats into the buffer and the last one leaves room
@@ -135,9 +166,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     const uint32_t bytes = gb > ga ? (uint32_t)(gb - ga) : 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (bytes) {
-      mbar_expect_tx(&bars[slot], use_skew ? 2 * bytes : bytes);
+      mbar_expect_tx(&bars[slot], bytes);
       tma_bulk_g2s(rawz + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
-      if (use_skew) tma_bulk_g2s(rawz + skew + lpad, (const unsigned char*)P.wave + ga, bytes, &bars[slot]);
     } else {
       mbar_arrive(&bars[slot]);
     }
@@ -178,9 +208,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     float* xr = rawz + cur.shift;   // xr[i] = padded sample p_lo + i of the utterance; data at xr[lpad .. lpad + n_loaded)
     if (cur.cov_end < cur.end_elem) {   // bytes the 16 B-granular bulk copy could not cover (end of the flat array)
       for (int64_t e = cur.cov_end + tid; e < cur.end_elem; e += kFastThreads) {
-        const float x = P.wave[e];
-        rawz[cur.lpad + (e - cur.base_elem)] = x;
-        if (use_skew) rawz[skew + cur.lpad + (e - cur.base_elem)] = x;
+        rawz[cur.lpad + (e - cur.base_elem)] = P.wave[e];
       }
       __syncthreads();
     }
@@ -198,23 +226,33 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
           x = (r >= 0 && r < cur.n_loaded) ? xr[cur.lpad + r] : __ldg(P.wave + cur.off + u);
         }
         xr[i] = x;
-        if (use_skew) xr[skew + i] = x;
       }
       __syncthreads();
     }
 
-    // ---- load: frame pair -> 25 windowed complex points per lane ----
-    cpx v[25];
+    // ---- load: frame pair -> 25 windowed complex points per lane (packed: (a, b) * w) ----
+    c2 v[25];
     {
-      const float* xa = xr + ((lane >> 4) && use_skew ? skew : 0) + (2 * pair) * hop + t;
+      const float* xa = xr + (2 * pair) * hop + t + 16 * rot;
       const float* xb = xa + hop;
+      const int last = 16 * 24 - 16 * 25 * rot;   // the last register block wraps to block 0 in the rotated half
       const bool fa_ok = 2 * pair < cur.nf, fb_ok = 2 * pair + 1 < cur.nf;
 #pragma unroll
-      for (int j = 0; j < 25; ++j) {
-        const float a = fa_ok ? xa[16 * j] : 0.f;
-        const float b = fb_ok ? xb[16 * j] : 0.f;
-        const float w = s_win[t + 16 * j];
-        v[j] = cx(a * w, b * w);
+      for (int c = 0; c < 4; ++c) {
+        float w8[8];
+        tm_ld8(tb + 8 * c, w8);
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (8 * c + i < 25) {
+            const int o = 8 * c + i == 24 ? last : 16 * (8 * c + i);
+            a[i] = fa_ok ? xa[o] : 0.f;
+            b[i] = fb_ok ? xb[o] : 0.f;
+          }
+        tm_wait8(w8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (8 * c + i < 25) v[8 * c + i] = mul2(pk(a[i], b[i]), bc(w8[i]));
       }
     }
     __syncthreads();   // the waveform has been consumed: the Z region may be written
@@ -224,17 +262,20 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     }
 
     // ---- stage 1: 25-point DFT in registers, twiddle W400^(t kj), rows [kj][t] of the pair's slot ----
-    fft25(v, P.tw25);
+    fft25p(v, P.tw25);
     {
       float2* slot = Zs + pair * kSlot400;
+      sts_c2(&slot[t], v[0]);
 #pragma unroll
-      for (int kj = 0; kj < 25; ++kj) {
-        cpx x = v[fft25_pos(kj)];
-        if (kj > 0) {
-          const float2 tw = s_tw[kj * 16 + t];
-          x = cmulf(x, cx(tw.x, tw.y));
+      for (int c = 0; c < 6; ++c) {
+        float w8[8];
+        tm_ld8(tb + 32 + 8 * c, w8);
+        tm_wait8(w8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kj = 4 * c + 1 + i;
+          sts_c2(&slot[kj * kRowStride + t], cmul(v[fft25_pos(kj)], w8[2 * i], w8[2 * i + 1]));
         }
-        slot[kj * kRowStride + t] = make_float2(x.x, x.y);
       }
     }
     __syncwarp();
@@ -242,33 +283,27 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
 
     // ---- stage 2: the warp's 2 x 25 sixteen-point DFTs over t, two rounds of 32 lanes ----
     {
-      cpx u0[16], u1[16];
       const int q0 = lane / 25, kj0 = lane - 25 * q0;                 // task = lane        (0..31)
       const int task1 = 32 + lane, q1 = task1 / 25, kj1 = task1 - 25 * q1;   // task = 32 + lane (valid for lane < 18)
-      const float2* s0 = Zs + (warp * 2 + q0) * kSlot400;
-      const float2* s1 = Zs + (warp * 2 + (lane < 18 ? q1 : 0)) * kSlot400;
+      const bool second = lane < 18;
+      const float2* s0 = Zs + (warp * 2 + q0) * kSlot400 + kj0 * kRowStride;
+      const float2* s1 = Zs + (warp * 2 + (second ? q1 : 0)) * kSlot400 + (second ? kj1 : 0) * kRowStride;
+      c2 u0[16], u1[16];
 #pragma unroll
-      for (int tt = 0; tt < 16; ++tt) {
-        const float2 x = s0[kj0 * kRowStride + tt];
-        u0[tt] = cx(x.x, x.y);
-        const float2 y = s1[(lane < 18 ? kj1 : 0) * kRowStride + tt];
-        u1[tt] = cx(y.x, y.y);
-      }
+      for (int tt = 0; tt < 16; ++tt) u0[tt] = lds_c2(s0 + tt);
+#pragma unroll
+      for (int tt = 0; tt < 16; ++tt) u1[tt] = second ? lds_c2(s1 + tt) : 0ull;   // idle lanes issue no shared-memory wavefronts
       __syncwarp();
-      fft16(u0);
-      fft16(u1);
-      float2* d0 = Zs + (warp * 2 + q0) * kSlot400;
-      float2* d1 = Zs + (warp * 2 + q1) * kSlot400;
+      fft16p(u0);
+      float2* d0 = Zs + (warp * 2 + q0) * kSlot400 + kj0;
 #pragma unroll
-      for (int kt = 0; kt < 16; ++kt) {
-        const cpx x = u0[fft16_pos(kt)];
-        d0[kj0 + 25 * kt] = make_float2(x.x, x.y);
-        if (lane < 18) {
-          const cpx y = u1[fft16_pos(kt)];
-          d1[kj1 + 25 * kt] = make_float2(y.x, y.y);
-        }
-      }
-      if (kj0 == 0) d0[kN400] = make_float2(u0[fft16_pos(0)].x, u0[fft16_pos(0)].y);   // bin 0 again: its own partner
+      for (int kt = 0; kt < 16; ++kt) sts_c2(d0 + 25 * kt, u0[fft16_pos(kt)]);
+      if (kj0 == 0) sts_c2(d0 + kN400, u0[fft16_pos(0)]);   // bin 0 again: its own partner
+      fft16p(u1);
+      float2* d1 = Zs + (warp * 2 + (second ? q1 : 0)) * kSlot400 + (second ? kj1 : 0);
+#pragma unroll
+      for (int kt = 0; kt < 16; ++kt)
+        if (second) sts_c2(d1 + 25 * kt, u1[fft16_pos(kt)]);
     }
     __syncthreads();   // every pair's spectrum is in its slot
 
@@ -355,6 +390,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) fbank400_kernel(const __grid_
     }
     __syncthreads();   // planes are free again; s_work / info of the next tile are visible
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*s_tm) : "memory");
 }
 
 }  // namespace mafe

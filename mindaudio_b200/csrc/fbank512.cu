@@ -832,11 +832,11 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
   if (th->f400) {
     std::vector<float> w400(kN400);
     for (int i = 0; i < kN400; ++i) w400[i] = 0.5f * d->spec_scale * d->window[i];   // 1/2: the pair separation leaves 2X
-    std::vector<float2> tw400(kN400);
+    std::vector<float2> tw400(2 * kN400);   // t = 16..31: the rotated upper half-warp
     for (int kj = 0; kj < 25; ++kj)
-      for (int t = 0; t < 16; ++t) {
-        double a = -2.0 * M_PI * (double)(t * kj) / 400.0;
-        tw400[kj * 16 + t] = make_float2((float)cos(a), (float)sin(a));
+      for (int t = 0; t < 32; ++t) {
+        double a = -2.0 * M_PI * (double)((t * kj) % 400) / 400.0;
+        tw400[kj * 32 + t] = make_float2((float)cos(a), (float)sin(a));
       }
     for (int j1 = 1; j1 < 5; ++j1)
       for (int k1 = 1; k1 < 5; ++k1) {
@@ -1006,7 +1006,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-    fbank400_kernel<<<std::min(b->n_tiles, 2 * ctx->sm_count), kFastThreads, f400_smem_bytes(F.plane_rows), ctx->stream>>>(F, th->sweep400);
+    fbank400_kernel<<<std::min(b->n_tiles, MAFE_F400_CTAS * ctx->sm_count), kFastThreads, f400_smem_bytes(F.plane_rows), ctx->stream>>>(F, th->sweep400);
     MAFE_LAUNCH_CHECK(ctx);
     return kFastNeedsPost;
   }
