@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--cpu-utts", type=int, default=2048, help="utterances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--chunk-utts", type=int, default=512, help="utterances per chunk of the pipelined host path")
+    ap.add_argument("--chunk-utts", type=int, default=128, help="utterances per chunk of the pipelined host path")
     ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of the sustained-clock window (0: skip)")
     ap.add_argument("--oracle-utts", type=int, default=4, help="utterances of the timed output checked against the oracle (0: skip)")
     args = ap.parse_args()

@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--utts", type=int, default=1000000, help="utterances over ALL ranks")
     ap.add_argument("--chunk", type=int, default=8192, help="utterances per host call")
     ap.add_argument("--pool", type=int, default=2, help="distinct pinned chunks in the ring")
-    ap.add_argument("--sub-chunk", type=int, default=512, help="utterances per pipelined device chunk inside a call")
+    ap.add_argument("--sub-chunk", type=int, default=128, help="utterances per pipelined device chunk inside a call")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
