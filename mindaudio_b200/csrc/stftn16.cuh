@@ -350,19 +350,31 @@ __global__ void __launch_bounds__(kFastThreads, StftN<N1>::kCtasPerSm) stftn16_k
 __global__ void __launch_bounds__(256, 8) scalar_norm_apply_kernel(float* __restrict__ feats, const Tile* __restrict__ tiles, int n_tiles,
                                                                  const int64_t* __restrict__ frame_offsets, const double* __restrict__ utt_stats,
                                                                  int dim, int tile_frames) {
-  for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+  // a CTA takes a CONTIGUOUS range of tiles: consecutive tiles mostly belong to one utterance, so the dependent chain
+  // tile -> offsets -> moments (three round trips to L2 with a grid-stride order) is paid once per utterance, not per tile
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(n_tiles, t0 + per);
+  int utt = -1, T = 0;
+  int64_t fo = 0;
+  float m = 0.f, inv = 0.f;
+  for (int ti = t0; ti < t1; ++ti) {
     const Tile tile = tiles[ti];
-    const int64_t fo = frame_offsets[tile.utt];
-    const int T = (int)(frame_offsets[tile.utt + 1] - fo);
+    if (tile.utt != utt) {
+      utt = tile.utt;
+      fo = frame_offsets[utt];
+      T = (int)(frame_offsets[utt + 1] - fo);
+      const double n = (double)T * (double)dim;
+      const double mean = utt_stats[2 * (size_t)utt] / n;
+      double var = utt_stats[2 * (size_t)utt + 1] / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      m = (float)mean;
+      inv = (float)(1.0 / sqrt(var));
+    }
     const int nf = min(tile_frames, T - tile.frame0);
-    const double n = (double)T * (double)dim;
-    const double mean = utt_stats[2 * (size_t)tile.utt] / n;
-    double var = utt_stats[2 * (size_t)tile.utt + 1] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float m = (float)mean, inv = (float)(1.0 / sqrt(var));
     float* p = feats + (fo + tile.frame0) * (int64_t)dim;
-    const int64_t cnt = (int64_t)nf * dim;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) p[i] = (p[i] - m) * inv;
+    const int cnt = nf * dim;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt; i += 256) p[i] = (p[i] - m) * inv;
   }
 }
 
