@@ -281,16 +281,31 @@ __global__ void __launch_bounds__(kGenericThreads) generic_frontend_kernel(Gener
 }
 
 // top_db clamp in place: x = max(x, groupmax - top_db)   (spectrum.py:78-89)
-__global__ void db_clamp_kernel(float* data, int dim, const Tile* tiles, const int64_t* frame_offsets, int tile_frames,
-                                const int* group_max, const int* utt_group, int db_group, float top_db) {
-  const Tile tile = tiles[blockIdx.x];
-  const int64_t fo = frame_offsets[tile.utt];
-  const int64_t T = frame_offsets[tile.utt + 1] - fo;
-  int nf = (int)min((int64_t)tile_frames, T - tile.frame0);
-  int g = db_group == MAFE_DBGROUP_UTT ? tile.utt : (db_group == MAFE_DBGROUP_BATCH ? 0 : utt_group[tile.utt]);
-  const float floor_v = key_to_float(group_max[g]) - top_db;
-  float* base = data + (fo + tile.frame0) * dim;
-  for (int i = threadIdx.x; i < nf * dim; i += blockDim.x) base[i] = fmaxf(base[i], floor_v);
+__global__ void __launch_bounds__(256, 8) db_clamp_kernel(float* __restrict__ data, int dim, const Tile* __restrict__ tiles, int n_tiles,
+                                                        const int64_t* __restrict__ frame_offsets, int tile_frames,
+                                                        const int* __restrict__ group_max, const int* __restrict__ utt_group, int db_group,
+                                                        float top_db) {
+  // a CTA takes a contiguous range of tiles: the chain tile -> offsets -> group maximum is paid once per utterance
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(n_tiles, t0 + per);
+  int utt = -1;
+  int64_t fo = 0, T = 0;
+  float floor_v = 0.f;
+  for (int ti = t0; ti < t1; ++ti) {
+    const Tile tile = tiles[ti];
+    if (tile.utt != utt) {
+      utt = tile.utt;
+      fo = frame_offsets[utt];
+      T = frame_offsets[utt + 1] - fo;
+      const int g = db_group == MAFE_DBGROUP_UTT ? utt : (db_group == MAFE_DBGROUP_BATCH ? 0 : utt_group[utt]);
+      floor_v = key_to_float(group_max[g]) - top_db;
+    }
+    const int nf = (int)min((int64_t)tile_frames, T - tile.frame0);
+    float* base = data + (fo + tile.frame0) * dim;
+    const int cnt = nf * dim;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt; i += 256) base[i] = fmaxf(base[i], floor_v);
+  }
 }
 
 // MFCC: out[f][c] = sum_m clamp(logmel[f][m]) * dct[m][c]   (features.py:356-361)
@@ -556,7 +571,7 @@ int generic_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wa
 
 int db_clamp_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, float* data, int dim, int db_group) {
   if (b->n_tiles == 0 || db_group == MAFE_DBGROUP_NONE || p->d.top_db < 0.f) return MAFE_OK;
-  db_clamp_kernel<<<b->n_tiles, 256, 0, ctx->stream>>>(data, dim, b->tiles_dev, b->frame_offsets_dev, p->tile_frames,
+  db_clamp_kernel<<<std::min(b->n_tiles, 8 * ctx->sm_count), 256, 0, ctx->stream>>>(data, dim, b->tiles_dev, b->n_tiles, b->frame_offsets_dev, p->tile_frames,
                                                        b->group_max_dev, b->utt_group_dev, db_group, p->d.top_db);
   MAFE_LAUNCH_CHECK(ctx);
   return MAFE_OK;
