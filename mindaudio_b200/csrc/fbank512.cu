@@ -783,18 +783,37 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
     if ((rc = up(&th->dev.window, w2))) return rc;
     if ((rc = up(&th->tw2048_dev, tw))) return rc;
     if (d->out_kind >= MAFE_OUT_MEL) {
+      // Per warp of 32 filters (thread = filter in the kernel): every filter's support starts on a multiple of 4 bins
+      // (16-byte loads of the power rows) and is padded with zero weights to the warp's widest filter, so the warp walks
+      // nch 4-bin chunks in lock step; the weights of chunk i sit at float4 index base + 32 i + lane: consecutive lanes
+      // read consecutive 16-byte words.  (First version: compact per-filter arrays at unaligned starts -- the weight loads
+      // ran at 2.6 x and the eight scalar power loads per chunk at 2.7 x their ideal wavefronts, ncu source page.)
       std::vector<int> ms(d->n_mels, 0), mc(d->n_mels, 0), mo(d->n_mels, 0);
       std::vector<float> mw;
-      for (int m = 0; m < d->n_mels; ++m) {
-        int k0 = -1, k1 = -1;
-        for (int k = 0; k < kBins2048; ++k)
-          if (d->mel_fb[(size_t)m * kBins2048 + k] != 0.f) { if (k0 < 0) k0 = k; k1 = k + 1; }
-        if (k0 < 0) { k0 = 0; k1 = 0; }
-        // the support in whole groups of 4 bins (16-byte weight loads), zero weights pad it; rows have kPRow2048 >= 1028 floats
-        int cnt = (k1 - k0 + 3) & ~3;
-        if (k0 + cnt > kPRow2048) k0 = kPRow2048 - cnt;
-        ms[m] = k0; mc[m] = cnt; mo[m] = (int)mw.size();
-        for (int k = k0; k < k0 + cnt; ++k) mw.push_back(k < kBins2048 ? d->mel_fb[(size_t)m * kBins2048 + k] : 0.f);
+      for (int m0 = 0; m0 < d->n_mels; m0 += 32) {
+        const int m1 = std::min(d->n_mels, m0 + 32);
+        std::vector<int> k0s(32, 0), k1s(32, 0);
+        int nch = 1;
+        for (int m = m0; m < m1; ++m) {
+          int k0 = -1, k1 = -1;
+          for (int k = 0; k < kBins2048; ++k)
+            if (d->mel_fb[(size_t)m * kBins2048 + k] != 0.f) { if (k0 < 0) k0 = k; k1 = k + 1; }
+          if (k0 < 0) { k0 = 0; k1 = 0; }
+          k0s[m - m0] = k0 & ~3; k1s[m - m0] = k1;
+          nch = std::max(nch, (k1 - (k0 & ~3) + 3) / 4);
+        }
+        const int base4 = (int)(mw.size() / 4);
+        mw.resize(mw.size() + (size_t)nch * 32 * 4, 0.f);
+        for (int m = m0; m < m1; ++m) {
+          int k0 = k0s[m - m0];
+          if (k0 + 4 * nch > kPRow2048) k0 = kPRow2048 - 4 * nch;   // rows hold kPRow2048 (multiple of 4) floats, the pad is zero
+          ms[m] = k0; mc[m] = nch; mo[m] = base4;
+          for (int i = 0; i < nch; ++i)
+            for (int j = 0; j < 4; ++j) {
+              const int k = k0 + 4 * i + j;
+              mw[((size_t)base4 + 32 * i + (m - m0)) * 4 + j] = (k >= 0 && k < kBins2048) ? d->mel_fb[(size_t)m * kBins2048 + k] : 0.f;
+            }
+        }
       }
       th->mw_floats_2048 = (int)mw.size();
       if ((rc = up(&th->mstart_dev, ms))) return rc;

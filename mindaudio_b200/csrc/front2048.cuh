@@ -43,9 +43,9 @@ struct F2048Params {
   int out_kind;
   float power;
   int n_mels;
-  const int* mstart;          // [n_mels] first bin of the filter's support
-  const int* mcount;          // [n_mels] bins in the support
-  const int* moff;            // [n_mels] offset of its weights
+  const int* mstart;          // [n_mels] first bin the filter reads (multiple of 4)
+  const int* mcount;          // [n_mels] 4-bin chunks its warp of 32 filters walks
+  const int* moff;            // [n_mels] float4 index of that warp's weight block: chunk i of lane l at moff + 32 i + l
   const float* mweights;
   int log_kind;
   float log_arg, log_mult, log_offset;
@@ -371,17 +371,19 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
         for (int m0 = 0; m0 < P.n_mels; m0 += 128) {
           const int m = m0 + t;
           if (m >= P.n_mels) continue;
-          const int s = P.mstart[m], c = P.mcount[m];      // c: a multiple of 4 (zero weights pad the support)
-          const float* w = s_mw + P.moff[m];
-          const float* ra = prow + s;
+          const int s = P.mstart[m], nch = P.mcount[m];     // nch: the same for the 32 filters of a warp
+          const float4* w4 = reinterpret_cast<const float4*>(s_mw) + P.moff[m] + (t & 31);
+          const float4* ra4 = reinterpret_cast<const float4*>(prow + s);
+          const float4* rb4 = reinterpret_cast<const float4*>(prow + kPRow2048 + s);
           c2 acc = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
-#pragma unroll 1
-          for (int i = 0; i < c; i += 4) {
-            const float4 ww = *reinterpret_cast<const float4*>(w + i);
-            acc = fma2(pk(ra[i], ra[kPRow2048 + i]), bc(ww.x), acc);
-            acc1 = fma2(pk(ra[i + 1], ra[kPRow2048 + i + 1]), bc(ww.y), acc1);
-            acc = fma2(pk(ra[i + 2], ra[kPRow2048 + i + 2]), bc(ww.z), acc);
-            acc1 = fma2(pk(ra[i + 3], ra[kPRow2048 + i + 3]), bc(ww.w), acc1);
+#pragma unroll 2
+          for (int i = 0; i < nch; ++i) {
+            const float4 ww = w4[32 * i];
+            const float4 pa4 = ra4[i], pb4 = rb4[i];
+            acc = fma2(pk(pa4.x, pb4.x), bc(ww.x), acc);
+            acc1 = fma2(pk(pa4.y, pb4.y), bc(ww.y), acc1);
+            acc = fma2(pk(pa4.z, pb4.z), bc(ww.z), acc);
+            acc1 = fma2(pk(pa4.w, pb4.w), bc(ww.w), acc1);
           }
           acc = add2(acc, acc1);
           float o[2] = {re(acc), im(acc)};
