@@ -1134,7 +1134,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     }
     if (cmvn) MAFE_CUDA_CHECK(cudaMemsetAsync(b->utt_stats_dev, 0, sizeof(double) * 2 * kV2Mels * b->n_utts, ctx->stream));
     if (use_v6) {
-      const int grid3 = std::min(b->n_tiles, 3 * ctx->sm_count);   // persistent: 3 CTAs per SM, dynamic tile queue
+      const int grid3 = std::min(b->n_tiles, MAFE_V6_CTAS * ctx->sm_count);   // persistent: 3 CTAs per SM, dynamic tile queue
       if (b->cap_tile_recs < (size_t)b->n_tiles) {   // grow-only
         if (b->tile_recs_dev) MAFE_CUDA_CHECK(cudaFree(b->tile_recs_dev));
         b->tile_recs_dev = nullptr; b->cap_tile_recs = 0;

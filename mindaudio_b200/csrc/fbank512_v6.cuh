@@ -416,7 +416,10 @@ struct V6Sum {
 };
 
 template <bool I16, bool TM, bool FUSE, bool FS = false>
-__global__ void __launch_bounds__(kFastThreads, 3) fbank512_v6_kernel(const __grid_constant__ V2Params P,
+#ifndef MAFE_V6_CTAS
+#define MAFE_V6_CTAS 3
+#endif
+__global__ void __launch_bounds__(kFastThreads, MAFE_V6_CTAS) fbank512_v6_kernel(const __grid_constant__ V2Params P,
                                                                       const __grid_constant__ V6Sweep S) {
   using SM = V6Smem;
   extern __shared__ __align__(128) unsigned char smem[];
