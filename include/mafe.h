@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MAFE_VERSION 100 /* 0.1.0 */
+#define MAFE_VERSION 101 /* 0.1.1: mafe_frontend_desc gained utt_scalar_norm */
 
 /* ---- status codes ---- */
 #define MAFE_OK 0

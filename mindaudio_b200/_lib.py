@@ -143,7 +143,7 @@ def load():
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.mafe_version() != 100:
+    if lib.mafe_version() != 101:
         raise MafeError("libmafe.so version mismatch: %d" % lib.mafe_version())
     _lib = lib
     return lib
