@@ -118,6 +118,8 @@ struct mafe_plan {
   float* window_dev = nullptr;    // [frame_len]
   mafe::MelCSR mel;
   float* dct_dev = nullptr;  // [n_mels][n_mfcc]
+  float* dct_img_dev = nullptr;  // tensor-core path (dct_mma.cuh): B_hi | B_lo images, N x K floats each, or null
+  int dct_n_pad = 0;             // N: n_mfcc padded to a multiple of 16
   // fast path tables (fbank512.cu)
   void* fast_tables = nullptr;
 };

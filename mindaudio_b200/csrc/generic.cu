@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "fft_generic.cuh"
+#include "dct_mma.cuh"
 
 namespace mafe {
 
@@ -484,6 +485,27 @@ int generic_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) 
   }
   if (d->out_kind == MAFE_OUT_MFCC) {
     if ((rc = upload(&p->dct_dev, d->dct, (size_t)d->n_mels * d->n_mfcc))) return rc;
+    {
+      // tensor-core path: DCT^T split into TF32 hi / lo parts, laid out as the UMMA canonical K-major images
+      const int K = d->n_mels, N = (d->n_mfcc + 15) / 16 * 16;
+      if (K % 16 == 0 && K <= 96 && N <= 64 && dct_mma_smem_bytes(K, N) <= 227 * 1024) {
+        std::vector<float> img((size_t)2 * N * K, 0.f);
+        for (int n = 0; n < d->n_mfcc; ++n)
+          for (int k = 0; k < K; ++k) {
+            const float x = d->dct[(size_t)k * d->n_mfcc + n];
+            uint32_t bits;
+            memcpy(&bits, &x, 4);
+            bits &= 0xffffe000u;
+            float hi;
+            memcpy(&hi, &bits, 4);
+            const size_t o = dm_canon_off(n, k, K) / 4;
+            img[o] = hi;
+            img[(size_t)N * K + o] = x - hi;
+          }
+        if ((rc = upload(&p->dct_img_dev, img.data(), img.size()))) return rc;
+        p->dct_n_pad = N;
+      }
+    }
   }
   {
     size_t tab = sizeof(float) * (size_t)d->frame_len;
@@ -506,6 +528,7 @@ void generic_plan_free(mafe_plan* p) {
   cudaFree(p->mel.col);
   cudaFree(p->mel.val);
   cudaFree(p->dct_dev);
+  cudaFree(p->dct_img_dev);
 }
 
 static void fill_params(GenericParams& P, const mafe_plan* p, const mafe_batch* b, const void* wave, int wave_dtype,
@@ -581,6 +604,35 @@ int dct_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const float* logme
   if (b->n_tiles == 0) return MAFE_OK;
   const int nm = p->d.n_mels, nc = p->d.n_mfcc;
   MAFE_REQUIRE(nc <= 128 && p->tile_frames >= 2 && p->tile_frames <= kDctFrames, "MFCC: n_mfcc %d / tile of %d frames not supported", nc, p->tile_frames);
+  if (p->dct_img_dev != nullptr && p->tile_frames == 32 && getenv("MAFE_DCT_TILED") == nullptr) {
+    // tensor cores (3 x TF32): dct_mma.cuh
+    DctMmaParams Q;
+    Q.logmel = logmel; Q.out = out; Q.K = nm; Q.n_mfcc = nc; Q.N = p->dct_n_pad; Q.bimg = p->dct_img_dev;
+    Q.tiles = b->tiles_dev; Q.n_tiles = b->n_tiles; Q.frame_offsets = b->frame_offsets_dev; Q.tile_frames = p->tile_frames;
+    Q.group_max = b->group_max_dev; Q.utt_group = b->utt_group_dev;
+    Q.db_group = (p->d.log_kind == MAFE_LOG_DB && p->d.top_db >= 0.f && db_group != MAFE_DBGROUP_NONE) ? db_group : MAFE_DBGROUP_NONE;
+    Q.top_db = p->d.top_db;
+    const size_t smem = dct_mma_smem_bytes(nm, p->dct_n_pad);
+    const int n_items = (b->n_tiles + 3) / 4;
+    const int grid = std::max(1, std::min((n_items + 1) / 2, ctx->sm_count));
+    auto launch = [&](auto kern) -> int {
+      MAFE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 256, smem, ctx->stream>>>(Q);
+      return MAFE_OK;
+    };
+    int rc;
+    switch ((nm + 15) / 16) {
+      case 1: rc = launch(dct_mma_kernel<1>); break;
+      case 2: rc = launch(dct_mma_kernel<2>); break;
+      case 3: rc = launch(dct_mma_kernel<3>); break;
+      case 4: rc = launch(dct_mma_kernel<4>); break;
+      case 5: rc = launch(dct_mma_kernel<5>); break;
+      default: rc = launch(dct_mma_kernel<6>); break;
+    }
+    if (rc) return rc;
+    MAFE_LAUNCH_CHECK(ctx);
+    return MAFE_OK;
+  }
   const int cpt_need = (nc + 7) / 8;
   const int cpt = cpt_need <= 2 ? 2 : cpt_need <= 4 ? 4 : cpt_need <= 5 ? 5 : cpt_need <= 8 ? 8 : 16;
   const size_t smem = sizeof(float) * ((size_t)nm * 8 * cpt + (size_t)nm * kDctXStride);
