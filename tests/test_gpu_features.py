@@ -55,6 +55,18 @@ def test_fbank_mfcc_deltas_context(ma, golden):
     assert mfcc_err(ma.mfcc(x3), R.mfcc(x3)) <= TOL_LOGMEL                                # 4-D context route
 
 
+@pytest.mark.parametrize("n_mels,n_mfcc", [(80, 40), (32, 13), (48, 20), (64, 64), (96, 39), (16, 16)])
+def test_mfcc_tensor_core_sizes(ma, n_mels, n_mfcc):
+    """MFCC on the 32-frame tile kernels (n_fft 400 / 2048) with n_mels % 16 == 0: the DCT runs on the tensor cores
+    (dct_mma_kernel: tcgen05 kind::tf32, three passes over the hi / lo split) -- every K / 16 instantiation, coefficient
+    counts that are not multiples of 8, ragged last tiles, the top_db clamp on and off."""
+    x = synth(22, (5, 20000)) * np.array([1.0, 0.02, 1.0, 0.3, 1e-3], dtype=np.float32)[:, None]
+    for n_fft in (400, 2048):
+        kw = dict(deltas=False, context=False, n_fft=n_fft, n_mels=n_mels, n_mfcc=n_mfcc)
+        assert mfcc_err(ma.mfcc(x, **kw), R.mfcc(x, **kw)) <= TOL_LOGMEL, n_fft
+        assert mfcc_err(ma.mfcc(x[1, :4321], log_mels=True, **kw), R.mfcc(x[1, :4321], log_mels=True, **kw)) <= TOL_LOGMEL, n_fft
+
+
 @pytest.mark.parametrize("n_fft,n_mels,n_mfcc", [(1024, 40, 13), (600, 64, 20), (2048, 128, 64), (400, 128, 128), (512, 23, 23)])
 def test_mfcc_other_sizes(ma, n_fft, n_mels, n_mfcc):
     """MFCC through every DCT tiling (coefficients per thread 2/4/5/8/16) and generic-kernel tile sizes (2..16 frames)."""

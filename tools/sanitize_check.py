@@ -41,6 +41,9 @@ ma.mfcc(x22, n_fft=2048, n_mels=128, n_mfcc=64, hop_length=256, deltas=False, co
 many = [np.round(synth(200 + i, (int(n),)) * 32768).astype(np.float32) for i, n in enumerate(rng.integers(400, 9000, size=96))]
 pipe = ma.FbankPipeline(cmvn="utt")
 pipe.features(many, chunk_utts=40)
+# the MFCC projection on the tensor cores (dct_mma_kernel): 80 -> 40 and a K / 16 = 3 instantiation with 13 coefficients
+ma.mfcc(x, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160)
+ma.mfcc(x[0, :5000], deltas=False, context=False, n_mels=48, n_mfcc=13, hop_length=160)
 # the deepspeech2 output kind (log1p|X| + scalar normalisation, moments accumulated by the transform)
 ma.ds2_features([x22[0], x22[1, :4000]])
 # frame-mean sums inside the persistent kernel (needs >= 12 tiles per SM): ragged, with one- and two-frame utterances
