@@ -14,7 +14,7 @@ run stftn16_20 "stftn16_kernel" 3 python tools/bench_ds2.py
 run scalar_norm "scalar_norm_apply" 2 python tools/bench_ds2.py
 run fbank400 "fbank400_kernel" 3 python tools/bench_features.py
 run db_clamp "db_clamp_kernel" 3 python tools/bench_features.py
-run dct "dct_kernel" 3 python tools/bench_features.py --mfcc
+run dct "dct_" 3 python tools/bench_features.py --mfcc
 run front2048 "front2048_kernel" 3 python tools/bench_features.py --fastspeech2
 run cmvn_stats "cmvn_stats" 2 python tools/bench_cfg4.py --steps 3
 run cmvn_apply "cmvn_apply" 2 python tools/bench_cfg4.py --steps 3
