@@ -3,6 +3,7 @@ filterbanks, DCT-II matrices.  Computed once per configuration in float64 and ro
 float32 for the device.  (Constants, not the hot path: the per-sample arithmetic is all CUDA.)"""
 from __future__ import annotations
 
+import functools
 import math
 
 import numpy as np
@@ -27,6 +28,27 @@ def analysis_window(window, win_length, n_fft, coerce=False):
     return np.pad(w, (lpad, n_fft - win_length - lpad))
 
 
+def _cached(fn):
+    """Memoise a table builder on its (hashable) arguments; the cached arrays are read-only.  Per-call API functions
+    (`compute_fbank_feats`, `fbank`, `mfcc`, ...) rebuilt these tables on every call: 0.12 of 0.44 ms for one 10 s utterance."""
+    @functools.lru_cache(maxsize=64)
+    def build(*args):
+        out = np.asarray(fn(*args))
+        out.setflags(write=False)
+        return out
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        if kw:
+            return fn(*args, **kw)
+        try:
+            return build(*args)
+        except TypeError:       # unhashable argument (an array-valued window, ...)
+            return fn(*args)
+    return wrapper
+
+
+@_cached
 def povey_window(n):
     """Symmetric hann ** 0.85 (``examples/conformer/dataset.py:126``)."""
     k = np.arange(n, dtype=np.float64)
@@ -50,6 +72,7 @@ def _from_mel(m, kind):
     return np.where(m >= 15.0, 1000.0 * np.exp((m - 15.0) * (math.log(6.4) / 27.0)), m * 200.0 / 3.0)
 
 
+@_cached
 def hz_triangle_bank(n_stft, n_mels, sample_rate, f_min, f_max, norm=NormType.NONE, mel_type=MelType.HTK):
     """MelScale filterbank: triangles linear in Hz between mel-spaced corner
     frequencies; returned as ``[n_mels, n_stft]`` (rows = filters) for the C ABI."""
@@ -65,6 +88,7 @@ def hz_triangle_bank(n_stft, n_mels, sample_rate, f_min, f_max, norm=NormType.NO
     return bank
 
 
+@_cached
 def kaldi_triangle_bank(num_bins, n_fft, sample_rate, low_freq, high_freq):
     """Conformer-example filterbank (``examples/conformer/dataset.py:68-113``): triangles linear
     on the mel axis (1127 ln(1 + f/700)); Nyquist column zero; ``[num_bins, n_fft//2 + 1]``."""
@@ -78,6 +102,7 @@ def kaldi_triangle_bank(num_bins, n_fft, sample_rate, low_freq, high_freq):
     return np.concatenate([bank, np.zeros((num_bins, 1))], axis=1)
 
 
+@_cached
 def dct_matrix(n_mfcc, n_mels, norm=NormMode.ORTHO):
     """``create_dct``: ``[n_mels, n_mfcc]`` float32."""
     norm = NormMode(norm).value
