@@ -286,9 +286,6 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
 #ifndef MAFE_FS_POLICY
 #define MAFE_FS_POLICY 1
 #endif
-#ifndef MAFE_FS_WARP7
-#define MAFE_FS_WARP7 0
-#endif
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -440,9 +437,9 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_V6_CTAS) fbank512_v6_kernel
   uint64_t* abar = reinterpret_cast<uint64_t*>(smem + SM::kABar);
   constexpr int ES = I16 ? 2 : 4;
   static_assert(!FS || (TM && FUSE), "the frame-sum duty uses the shared memory the TMEM variant leaves idle");
-  static_assert(2 * sizeof(SumRec) + kFastThreads * sizeof(float) <= sizeof(float) * 400 && sizeof(float) * 4 * kCwRow <= 2 * sizeof(float2) * 256, "FS tables");
+  static_assert(2 * sizeof(SumRec) + 8 * sizeof(float) <= sizeof(float) * 400 && sizeof(float) * 4 * kCwRow <= 2 * sizeof(float2) * 256, "FS tables");
   SumRec* sinfo = reinterpret_cast<SumRec*>(smem + SM::kWin);              // FS: [2] records of the tiles being summed
-  float* s_ws = reinterpret_cast<float*>(smem + SM::kWin + 2 * sizeof(SumRec));     // FS: [256] per-thread partial sums
+  float* s_ws = reinterpret_cast<float*>(smem + SM::kWin + 2 * sizeof(SumRec));     // FS: [8] warp partial sums
   float* s_cp4 = reinterpret_cast<float*>(smem + SM::kW512);               // FS: c' table, 4 shifted copies
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -596,9 +593,6 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_V6_CTAS) fbank512_v6_kernel
     const bool duty = FUSE && u >= P.lag;              // normalise tile u - lag
     const bool sum_duty = FS && w < P.n_tiles;         // sum the samples of tile w
     if (tid == 0) nx_w = atomicAdd(P.queue_head, 1);   // stage 1 (issue): claim the next item
-#if MAFE_FS_WARP7
-    if (FS && sum_duty) { V6Sum<I16> fsum; fsum.issue(P, sinfo[buf], recs + w, tid); s_ws[tid] = fsum.finish(s_cp4); }   // reduced by warp 7 after the third barrier
-#else
     if (FS && sum_duty) {
       V6Sum<I16> fsum;
       fsum.issue(P, sinfo[buf], recs + w, tid);
@@ -606,7 +600,6 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_V6_CTAS) fbank512_v6_kernel
       for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
       if (lane == 0) s_ws[warp] = fs;                  // read by the service thread after the third barrier
     }
-#endif
     if (FUSE && svc) {
       if (duty) {                          // the duty tile's record -> ainfo (asynchronous)
         const uint32_t dst = smem_u32(ainfo);
@@ -856,15 +849,7 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_V6_CTAS) fbank512_v6_kernel
     // barriers passed since -> publish it (here, where the service thread's warp has slack); FS: and this item's sample sum
     if (FS) {
       float t8 = 0.f;
-#if MAFE_FS_WARP7
-      if (sum_duty && warp == kFastWarps - 1) {   // the service thread's warp adds the CTA's 256 partial sums
-        const float4 a4 = *reinterpret_cast<const float4*>(s_ws + 8 * lane), b4 = *reinterpret_cast<const float4*>(s_ws + 8 * lane + 4);
-        t8 = ((a4.x + a4.y) + (a4.z + a4.w)) + ((b4.x + b4.y) + (b4.z + b4.w));
-        for (int o = 16; o > 0; o >>= 1) t8 += __shfl_xor_sync(0xffffffffu, t8, o);
-      }
-#else
       if (svc && sum_duty) t8 = ((s_ws[0] + s_ws[1]) + (s_ws[2] + s_ws[3])) + ((s_ws[4] + s_ws[5]) + (s_ws[6] + s_ws[7]));
-#endif
       if (svc && (sum_duty || prev_utt >= 0)) {
         const int s_utt = sinfo[buf].utt;
         if (sum_duty) atomicAdd(P.utt_fsum + s_utt, (double)t8);
