@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 8) cmvn_utt_apply_kernel(float* __restric
       const double s2 = utt_stats[((size_t)tile.utt * 2 + 1) * kV2Mels + threadIdx.x];
       const double mean = s1 / T;
       double var = s2 / T - mean * mean;
-      if (var < 0.0) var = 0.0;
+      if (var < 0.0 || T == 1) var = 0.0;   // one frame: np.std is exactly 0 (the reference divides by it: nan / inf), whatever the rounding of s2
       s_mean[threadIdx.x] = mean_norm ? (float)mean : 0.f;
       s_inv[threadIdx.x] = std_norm ? (float)(1.0 / sqrt(var)) : 1.f;
     }

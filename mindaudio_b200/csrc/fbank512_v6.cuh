@@ -828,7 +828,8 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_V6_CTAS) fbank512_v6_kernel
       double r = (double)(1.0f / (float)T);
       r = r * (2.0 - dT * r);
       const double mean = st_s1 * r;
-      const float var = (float)fmax(fma(st_s2, r, -mean * mean), 0.0);
+      // one frame: np.std is exactly 0 (the reference divides by it: nan / inf), whatever the rounding of the float partial sums
+      const float var = T == 1 ? 0.f : (float)fmax(fma(st_s2, r, -mean * mean), 0.0);
       float y = rsqrtf(var);
       if (var > 0.f) y = y * (1.5f - 0.5f * var * y * y);
       s_norm[tid] = P.mean_norm ? (float)mean : 0.f;

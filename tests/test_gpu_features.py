@@ -1,4 +1,6 @@
 """GPU parity: fbank / mfcc / deltas / context / conformer front-end / CMVN vs oracle and goldens."""
+import os
+
 import numpy as np
 import pytest
 
@@ -269,6 +271,34 @@ def test_frame_mean_sums_inside_the_persistent_kernel(ma):
             assert got.shape == ref.shape, u
             if ref.shape[0] > 1:
                 assert logmel_err(got * ref.std(axis=0) + ref.mean(axis=0), ref) <= 2.0, (u, lens[u], dtype)
+
+
+def test_kernel_variants_agree(tmp_path):
+    """The fused default kernels against their unfused / FP32 counterparts (A/B environment switches, read once per
+    process -> subprocesses): frame-mean sums inside the persistent kernel vs the pre-pass kernel, utterance CMVN inside
+    the kernel vs the apply kernel, per-lane constants in TMEM vs shared memory, tensor-core DCT vs FP32 DCT."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("default", {}), ("prepass", {"MAFE_NO_FUSED_FRAMESUM": "1"}), ("apply", {"MAFE_NO_FUSED_CMVN": "1"}),
+                      ("smem", {"MAFE_NO_TMEM": "1"}), ("fp32dct", {"MAFE_DCT_TILED": "1"})):
+        path = str(tmp_path / (name + ".npz"))
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, os.path.join(root, "tests", "variant_probe.py"), path], check=True, cwd=root, env=e, timeout=300)
+        outs[name] = np.load(path)
+    ref = outs["default"]
+    ok = np.isfinite(ref["feats"])                                  # one-frame utterances normalise to nan / inf in every variant
+    for name in ("prepass", "apply", "smem"):
+        o = outs[name]
+        assert np.array_equal(o["fo"], ref["fo"]), name
+        assert np.array_equal(np.isfinite(o["feats"]), ok), name
+        # normalised features: the variants differ in summation order (atomics, float vs double partial sums) only
+        d = np.abs(o["feats"][ok] - ref["feats"][ok])
+        assert np.mean(d > 1e-4) <= 1e-4 and d.max() <= 5e-3, (name, float(d.max()), float(np.mean(d > 1e-4)))
+    d = np.abs(outs["fp32dct"]["mfcc"] - ref["mfcc"])
+    assert d.max() <= 1e-4 * max(1.0, float(np.abs(ref["mfcc"]).max())), float(d.max())   # 3 x TF32 vs FP32 FMA
 
 
 def test_pad_sequence_and_padded_pipeline(ma):
