@@ -20,7 +20,9 @@ roofline= dominant kernel (fbank512_v6_kernel) timed with CUDA events on its own
           run, algorithmic bytes (960 B/frame) and flops (14 253/frame) from SURVEY.md section 8d.
           `bound` names the BINDING roofline (FP32 FMA peak measured in this run vs the measured HBM
           copy bandwidth), `frac` = that roofline's time / kernel time; `step` covers all kernels
-          of the step (pre-pass, tile records, main, CMVN apply) with their DRAM traffic.
+          of the step with their DRAM traffic (tile records + the persistent kernel with the frame-mean
+          sums and the utterance CMVN fused; the pre-pass / CMVN-apply slots are 0 unless the
+          MAFE_NO_FUSED_* switches are set).
 oracle_check = after the timed region a seeded sample of utterances of the TIMED output is compared
           with the float64 oracle (the checker, outside every timed region).
 sustained = the same step repeated for >= --sustain-s seconds with the clocks sampled over that window.
