@@ -11,6 +11,7 @@ run() {  # name, kernel regex, skip, command...
 }
 run stft512 "stft512_kernel" 3 python tools/bench_stft.py
 run stftn16_20 "stftn16_kernel" 3 python tools/bench_ds2.py
+run stftn16_25 "stftn16_kernel" 3 python tools/bench_stft.py --n-fft 400 --hop 160
 run scalar_norm "scalar_norm_apply" 2 python tools/bench_ds2.py
 run fbank400 "fbank400_kernel" 3 python tools/bench_features.py
 run db_clamp "db_clamp_kernel" 3 python tools/bench_features.py
