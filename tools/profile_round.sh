@@ -8,7 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
 #    frame-mean sums fused; SKIP=6 COUNT=3 with MAFE_NO_FUSED_FRAMESUM=1: pre-pass, tile records, main kernel); the warm-up's are skipped
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fbank512_v6|frame_sum|tile_prepare|cmvn_utt_apply" -s ${SKIP:-4} -c ${COUNT:-2} -f -o gpurun_out/${R}_step python bench.py --steps 1 --warmup 2 --no-cpu-baseline --no-e2e --sustain-s 0 --oracle-utts 0 > gpurun_out/full_bench.log 2>&1
 # 3) the FP32 lane rate of scalar vs packed instructions
-[ -x scratch/fp2/fp2 ] && ./scratch/fp2/fp2 > gpurun_out/${R}_fp32x2_peak.txt 2>&1
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o gpurun_out/fp32x2_peak tools/fp32x2_peak.cu 2>/dev/null && ./gpurun_out/fp32x2_peak > gpurun_out/${R}_fp32x2_peak.txt 2>&1
 # 4) sanitizers
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_check.py > gpurun_out/san_mem.log 2>&1; tail -3 gpurun_out/san_mem.log
 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_check.py > gpurun_out/san_race.log 2>&1; tail -3 gpurun_out/san_race.log
