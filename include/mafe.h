@@ -176,6 +176,11 @@ int32_t mafe_plan_is_fast(const mafe_plan* plan);
 int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
                       const int32_t* utt_group_host, mafe_batch** out);
 int mafe_batch_destroy(mafe_batch* batch);
+/* Re-lay an existing batch object for new offsets (any plan of the same ctx).  Its device tables only grow, so a caller that
+ * keeps batch objects between calls pays no cudaMalloc / cudaFree per batch (a per-utterance API call otherwise spends more
+ * time in them than in the kernels).  Stream ordered on the ctx stream: work enqueued earlier with the old layout is safe. */
+int mafe_batch_refill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, const int64_t* sample_offsets_host, int32_t n_utts,
+                      const int32_t* utt_group_host);
 int64_t mafe_batch_total_frames(const mafe_batch* batch);
 int64_t mafe_batch_total_samples(const mafe_batch* batch);
 /* frame_offsets_host_out: int64[n_utts+1] */

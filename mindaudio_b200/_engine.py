@@ -44,6 +44,7 @@ class Engine:
         self.pid = os.getpid()
         self.lock = threading.RLock()
         self._plans = {}
+        self._batch_pool = []     # handles of closed batches, re-laid by mafe_batch_refill (Engine.batch)
         self._bufs = {}
         self._pinned = {}
 
@@ -168,12 +169,30 @@ class Engine:
 
     # ---- ragged batch ----
     def batch(self, plan, sample_offsets, utt_group=None):
+        """Batch layout for ``sample_offsets``.  Closed batches go back to a small pool and are re-laid with
+        ``mafe_batch_refill`` (their device tables only grow): no cudaMalloc / cudaFree per call."""
         so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
         ug = None if utt_group is None else np.ascontiguousarray(utt_group, dtype=np.int32)
+        ugp = None if ug is None else ug.ctypes.data_as(C.c_void_p)
+        with self.lock:
+            h = self._batch_pool.pop() if self._batch_pool else None
+        if h is not None:
+            try:
+                L.check(self.lib.mafe_batch_refill(self.ctx, plan.h, h, so.ctypes.data_as(C.c_void_p), len(so) - 1, ugp))
+            except Exception:
+                self.lib.mafe_batch_destroy(h)
+                raise
+            return Batch(self, h, len(so) - 1)
         h = C.c_void_p()
-        L.check(self.lib.mafe_batch_create(self.ctx, plan.h, so.ctypes.data_as(C.c_void_p), len(so) - 1,
-                                           None if ug is None else ug.ctypes.data_as(C.c_void_p), C.byref(h)))
+        L.check(self.lib.mafe_batch_create(self.ctx, plan.h, so.ctypes.data_as(C.c_void_p), len(so) - 1, ugp, C.byref(h)))
         return Batch(self, h, len(so) - 1)
+
+    def _recycle_batch(self, h):
+        with self.lock:
+            if len(self._batch_pool) < 4:
+                self._batch_pool.append(h)
+                return
+        self.lib.mafe_batch_destroy(h)
 
     # ---- numpy in / numpy out ----
     def run_frontend(self, plan, flat_wave, sample_offsets, wave_scale=1.0, db_group=L.DBGROUP_NONE, utt_group=None):
@@ -213,8 +232,8 @@ class Batch:
 
     def close(self):
         if self.h is not None:
-            self.engine.lib.mafe_batch_destroy(self.h)
-            self.h = None
+            h, self.h = self.h, None
+            self.engine._recycle_batch(h)
 
     def __del__(self):
         try:

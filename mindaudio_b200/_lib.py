@@ -72,6 +72,7 @@ _PROTOS = {
     "mafe_plan_is_fast": (_I32, [_P]),
     "mafe_batch_create": (C.c_int, [_P, _P, _P, _I32, _P, C.POINTER(_P)]),
     "mafe_batch_destroy": (C.c_int, [_P]),
+    "mafe_batch_refill": (C.c_int, [_P, _P, _P, _P, _I32, _P]),
     "mafe_batch_total_frames": (_I64, [_P]),
     "mafe_batch_total_samples": (_I64, [_P]),
     "mafe_batch_frame_offsets": (C.c_int, [_P, _P]),

@@ -340,6 +340,15 @@ int mafe_batch_create(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, i
   return MAFE_OK;
 }
 
+int mafe_batch_refill(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* b, const int64_t* so, int32_t n_utts,
+                      const int32_t* utt_group) {
+  MAFE_REQUIRE(ctx && plan && b && (so || n_utts == 0), "mafe_batch_refill: NULL argument");
+  MAFE_REQUIRE(n_utts >= 0, "n_utts=%d", n_utts);
+  MAFE_REQUIRE(b->device == ctx->device, "mafe_batch_refill: the batch belongs to device %d", b->device);
+  DeviceGuard g(ctx->device);
+  return batch_fill(ctx, plan, b, so, n_utts, utt_group, 0);
+}
+
 int mafe_batch_destroy(mafe_batch* b) {
   if (!b) return MAFE_OK;
   DeviceGuard g(b->device);
