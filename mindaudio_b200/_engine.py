@@ -122,6 +122,21 @@ class Engine:
         assert arr.flags["C_CONTIGUOUS"]
         L.check(self.lib.mafe_memcpy_d2h(self.ctx, arr.ctypes.data_as(C.c_void_p), dev, arr.nbytes))
 
+    def d2h_staged(self, arr, dev):
+        """Large results: device -> pinned staging at full PCIe rate, then a multi-threaded copy into ``arr`` (synchronous)."""
+        assert arr.flags["C_CONTIGUOUS"]
+        L.check(self.lib.mafe_memcpy_d2h_staged(self.ctx, arr.ctypes.data_as(C.c_void_p), dev, arr.nbytes))
+
+    def h2d_gather(self, dev, arrays):
+        """Upload a list of C-contiguous arrays back to back at ``dev`` (the library's host threads gather them into pinned
+        staging, one async copy uploads it); the arrays may be released when this returns."""
+        n = len(arrays)
+        if n == 0:
+            return
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        sizes = np.fromiter((a.nbytes for a in arrays), dtype=np.int64, count=n)
+        L.check(self.lib.mafe_memcpy_h2d_gather(self.ctx, dev, ptrs, sizes.ctypes.data_as(C.c_void_p), n))
+
     # ---- plans ----
     def plan(self, *, n_fft, frame_len=None, hop, center, pad_mode="constant", out_kind, window, preemph=0.0,
              remove_frame_mean=False, dither=0.0, dither_seed=0, power=2.0, spec_scale=1.0, mel_fb=None,
@@ -209,9 +224,17 @@ class Engine:
                 if b.total_frames:
                     dw = self.buf("wave", flat_wave.nbytes)
                     do = self.buf("out", out.nbytes)
-                    keep = self.h2d(dw, flat_wave)
+                    big = 4 << 20     # large arrays go through the pinned staging buffers (multi-threaded host copies)
+                    keep = None
+                    if flat_wave.nbytes >= big:
+                        self.h2d_gather(dw, [flat_wave])
+                    else:
+                        keep = self.h2d(dw, flat_wave)
                     L.check(self.lib.mafe_frontend_run(self.ctx, plan.h, b.h, dw, wdt, float(wave_scale), do, db_group))
-                    self.d2h(out, do)
+                    if out.nbytes >= big:
+                        self.d2h_staged(out, do)
+                    else:
+                        self.d2h(out, do)
                     self.sync()
                     del keep
                 return out, b.frame_offsets

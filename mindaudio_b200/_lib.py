@@ -65,6 +65,8 @@ _PROTOS = {
     "mafe_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "mafe_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "mafe_memset": (C.c_int, [_P, _P, C.c_int, C.c_size_t]),
+    "mafe_memcpy_h2d_gather": (C.c_int, [_P, _P, _P, _P, _I32]),
+    "mafe_memcpy_d2h_staged": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "mafe_plan_create": (C.c_int, [_P, C.POINTER(FrontendDesc), C.POINTER(_P)]),
     "mafe_plan_destroy": (C.c_int, [_P]),
     "mafe_plan_num_frames": (_I64, [_P, _I64]),

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -76,6 +78,9 @@ int mafe_ctx_destroy(mafe_ctx* ctx) {
     cudaFree(l.out_dev);
     mafe_batch_destroy(l.batch);
   }
+  if (ctx->stage_up) cudaFreeHost(ctx->stage_up);
+  if (ctx->stage_down) cudaFreeHost(ctx->stage_down);
+  if (ctx->stage_up_done) cudaEventDestroy(ctx->stage_up_done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return MAFE_OK;
@@ -173,6 +178,77 @@ int mafe_memcpy_d2h(mafe_ctx* ctx, void* dst_host, const void* src_dev, size_t b
   if (bytes) MAFE_CUDA_CHECK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return MAFE_OK;
 }
+// parallel host memcpy of a list of (dst, src, bytes) pieces: threads take contiguous byte ranges of the concatenation
+static void parallel_copy(unsigned char* dst, const void* const* srcs, const int64_t* bytes, int32_t n, bool scatter_to_dst) {
+  // scatter_to_dst == true: srcs[i] -> dst + prefix[i] (gather into one buffer)
+  std::vector<int64_t> pre((size_t)n + 1, 0);
+  for (int32_t i = 0; i < n; ++i) pre[i + 1] = pre[i] + (bytes[i] > 0 ? bytes[i] : 0);
+  const int64_t total = pre[n];
+  if (total == 0) return;
+  int hw = (int)std::thread::hardware_concurrency();
+  int nt = (int)std::min<int64_t>(std::max(1, std::min(8, hw / 2)), std::max<int64_t>(1, total / (4 << 20)));
+  auto work = [&](int t) {
+    const int64_t lo = total * t / nt, hi = total * (t + 1) / nt;
+    int32_t i = (int32_t)(std::upper_bound(pre.begin(), pre.end(), lo) - pre.begin()) - 1;
+    for (int64_t pos = lo; pos < hi; ++i) {
+      const int64_t a = std::max(pos, pre[i]), b = std::min(hi, pre[i + 1]);
+      if (b > a) memcpy(dst + a, (const unsigned char*)srcs[i] + (a - pre[i]), (size_t)(b - a));
+      pos = pre[i + 1];
+    }
+  };
+  (void)scatter_to_dst;
+  if (nt == 1) { work(0); return; }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+}
+
+int mafe_memcpy_h2d_gather(mafe_ctx* ctx, void* dst_dev, const void* const* src_host, const int64_t* bytes, int32_t n) {
+  MAFE_REQUIRE(ctx != nullptr && n >= 0 && (n == 0 || (src_host && bytes)), "mafe_memcpy_h2d_gather: bad argument");
+  DeviceGuard g(ctx->device);
+  int64_t total = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    MAFE_REQUIRE(bytes[i] >= 0 && (bytes[i] == 0 || src_host[i]), "mafe_memcpy_h2d_gather: piece %d", i);
+    total += bytes[i];
+  }
+  if (total == 0) return MAFE_OK;
+  MAFE_REQUIRE(dst_dev != nullptr, "mafe_memcpy_h2d_gather: dst_dev is NULL");
+  if (ctx->stage_up_done) MAFE_CUDA_CHECK(cudaEventSynchronize(ctx->stage_up_done));   // the previous upload has read the buffer
+  if ((size_t)total > ctx->cap_stage_up) {
+    if (ctx->stage_up) cudaFreeHost(ctx->stage_up);
+    ctx->stage_up = nullptr; ctx->cap_stage_up = 0;
+    const size_t cap = (size_t)total + (size_t)total / 4;
+    MAFE_CUDA_CHECK(cudaHostAlloc(&ctx->stage_up, cap, cudaHostAllocDefault));
+    ctx->cap_stage_up = cap;
+  }
+  if (!ctx->stage_up_done) MAFE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->stage_up_done, cudaEventDisableTiming));
+  parallel_copy((unsigned char*)ctx->stage_up, src_host, bytes, n, true);
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(dst_dev, ctx->stage_up, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+  MAFE_CUDA_CHECK(cudaEventRecord(ctx->stage_up_done, ctx->stream));
+  return MAFE_OK;
+}
+
+int mafe_memcpy_d2h_staged(mafe_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (bytes == 0) return MAFE_OK;
+  MAFE_REQUIRE(dst_host && src_dev, "mafe_memcpy_d2h_staged: NULL argument");
+  DeviceGuard g(ctx->device);
+  if (bytes > ctx->cap_stage_down) {
+    if (ctx->stage_down) cudaFreeHost(ctx->stage_down);
+    ctx->stage_down = nullptr; ctx->cap_stage_down = 0;
+    const size_t cap = bytes + bytes / 4;
+    MAFE_CUDA_CHECK(cudaHostAlloc(&ctx->stage_down, cap, cudaHostAllocDefault));
+    ctx->cap_stage_down = cap;
+  }
+  MAFE_CUDA_CHECK(cudaMemcpyAsync(ctx->stage_down, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MAFE_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const void* src = ctx->stage_down;
+  const int64_t b = (int64_t)bytes;
+  parallel_copy((unsigned char*)dst_host, &src, &b, 1, false);
+  return MAFE_OK;
+}
+
 int mafe_memset(mafe_ctx* ctx, void* dst_dev, int value, size_t bytes) {
   MAFE_REQUIRE(ctx != nullptr, "ctx is NULL");
   DeviceGuard g(ctx->device);

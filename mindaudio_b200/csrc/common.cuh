@@ -77,6 +77,12 @@ struct mafe_ctx {
   int64_t prof_n[MAFE_PROF_COUNT] = {0, 0, 0, 0};
   std::vector<mafe_prof_pending> prof_pending;
   std::vector<mafe_lane> lanes;
+  // pinned staging of mafe_memcpy_h2d_gather / mafe_memcpy_d2h_staged (grow-only; one buffer per direction)
+  void* stage_up = nullptr;
+  size_t cap_stage_up = 0;
+  cudaEvent_t stage_up_done = nullptr;   // the upload that last read stage_up
+  void* stage_down = nullptr;
+  size_t cap_stage_down = 0;
 };
 
 namespace mafe {

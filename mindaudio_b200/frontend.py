@@ -193,18 +193,16 @@ class FbankPipeline:
         ``pad_sequence`` -- so the random draws land on the utterances in that order and the batch rows come out in it.
         A fourth value, ``order`` (row i = input utterance ``order[i]``), is then returned.  With the default ``False`` rows
         and draws follow the input order (callers that pre-sort get the reference's result either way)."""
-        lens = [len(w) for w in waves]
         dt = np.int16 if waves and all(np.asarray(w).dtype == np.int16 for w in waves) else np.float32
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=dt) for w in waves])) if waves else np.zeros(0, dt)
-        so = np.zeros(len(lens) + 1, dtype=np.int64)
-        np.cumsum(lens, out=so[1:])
+        arrs = [np.ascontiguousarray(np.asarray(w), dtype=dt).reshape(-1) for w in waves]   # no copy when already dt
+        so = np.zeros(len(arrs) + 1, dtype=np.int64)
+        np.cumsum([a.shape[0] for a in arrs], out=so[1:])
         eng = self.eng
         with eng.lock:
-            d_w = eng.buf("wave", max(flat.nbytes, 16))
-            keep = eng.h2d(d_w, flat)
+            d_w = eng.buf("wave", max(int(so[-1]) * np.dtype(dt).itemsize, 16))
+            eng.h2d_gather(d_w, arrs)       # gathered into pinned staging by the library's host threads, one upload
             res = self._padded_from_device(d_w, L.WAVE_I16 if dt == np.int16 else L.WAVE_F32, so, max_len, padding_value,
                                            wave_scale, spec_aug_conf, rng, sort_by_length)
-            del keep
         return res
 
     def features_from_wav(self, files, max_len=None, padding_value=0.0, spec_aug_conf=None, rng=None, speeds=None,
@@ -262,8 +260,8 @@ class FbankPipeline:
                                                             d_r, len(rects), 0.0))
                     L.check(eng.lib.mafe_pad_sequence(eng.ctx, d_f, C.c_void_p(b.frame_offsets_dev), n, self.mel_bin,
                                                       max_len, float(padding_value), 1, d_p, d_m))
-                    eng.d2h(xs_pad, d_p)
                     eng.d2h(xs_masks, d_m)
+                    eng.d2h_staged(xs_pad, d_p)      # the big one: pinned staging + multi-threaded copy-out (synchronises)
                     eng.sync()
                     del keep_r
                 if order is not None:
