@@ -301,6 +301,30 @@ def test_kernel_variants_agree(tmp_path):
     assert d.max() <= 1e-4 * max(1.0, float(np.abs(ref["mfcc"]).max())), float(d.max())   # 3 x TF32 vs FP32 FMA
 
 
+def test_gather_upload_and_staged_download(ma):
+    """mafe_memcpy_h2d_gather / mafe_memcpy_d2h_staged (numpy-in / numpy-out plumbing): many pieces of ragged sizes incl.
+    empty ones, single-threaded (small) and multi-threaded (>= 8 MiB) totals, back-to-back calls reusing the staging."""
+    from mindaudio_b200._engine import get_engine
+    eng = get_engine()
+    rng = np.random.default_rng(12)
+    for sizes in ([0, 5, 0, 1], [1000, 0, 3, 777777, 1], list(rng.integers(1, 300000, size=97)) + [0, 4 << 20]):
+        arrs = [rng.integers(-32768, 32767, size=int(n)).astype(np.int16) for n in sizes]
+        ref = np.concatenate(arrs) if arrs else np.zeros(0, np.int16)
+        with eng.lock:
+            dev = eng.buf("wave", max(ref.nbytes, 16))
+            for _ in range(2):                      # the second call waits for the first upload before refilling the staging
+                eng.h2d_gather(dev, arrs)
+            back = np.empty_like(ref)
+            if ref.nbytes:
+                eng.d2h_staged(back, dev)
+            eng.sync()
+        assert np.array_equal(back, ref)
+    # the public API through the large-array route (>= 4 MiB in and out)
+    x = synth(31, (24, 48000))
+    out = ma.stft(x, n_fft=512, hop_length=128)
+    assert np.abs(out - R.stft(x, n_fft=512, hop_length=128)).max() <= 1e-5 * np.abs(out).max()
+
+
 def test_pad_sequence_and_padded_pipeline(ma):
     """Scope row f3: pad_sequence on the device (bit exact vs the restated reference), and front-end + collate in one
     device round trip (xs_pad / xs_lengths / xs_masks of examples/conformer/dataset.py:563-569, 616-621)."""
