@@ -32,7 +32,7 @@ def _digest():
     for name in SOURCES + HEADERS + included:
         with open(os.path.join(CSRC, name), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("MAFE_NVCC_EXTRA", "").split()).encode())   # A/B builds: extra -D switches
     return h.hexdigest()
 
 
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("MAFE_NVCC_EXTRA", "").split()
     if verbose:
         flags += ["-Xptxas", "-v"]
     procs = []

@@ -14,7 +14,8 @@
 // over the two power rows (thread = filter).  A CTA = two such 128-thread groups (named barriers, nothing CTA-wide inside
 // a pair); persistent CTAs claim half-tiles (16 frames) from a queue and stage their samples -- centre padding resolved
 // while staging -- in shared memory once, so every sample is read from L2 / HBM once per half-tile instead of once per
-// frame that covers it (n_fft / hop = 6.8 times).  The per-thread window entries live in registers.
+// frame that covers it (n_fft / hop = 6.8 times).  Only the part of a frame that meets the window's support (whole rows of 128
+// samples: 1280 of 2048 for win 1200) is staged.  The per-thread window entries live in registers.
 #pragma once
 #include "packed.cuh"
 
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int hop = P.hop;
+  const int lo = 128 * P.j0, span = 128 * (P.j1 - P.j0);   // staged part of a frame (window support, whole rows)
   const int n_items = 2 * P.n_tiles;   // half-tiles of 16 frames (the batch tiles hold 32)
   float vmax = -INFINITY;
   int vmax_utt = -1;
@@ -180,8 +182,9 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
     if (it.frame0 >= it.T) return it;
     it.ok = true;
     it.nf = min(kHalfFrames2048, it.T - it.frame0);
-    it.s_lo = (int64_t)it.frame0 * hop - (P.center ? kN2048 / 2 : 0);
-    it.n_need = (it.nf - 1) * hop + kN2048;
+    // only the rows that meet the window's support are staged: samples [lo, lo + span) of every frame
+    it.s_lo = (int64_t)it.frame0 * hop - (P.center ? kN2048 / 2 : 0) + lo;
+    it.n_need = (it.nf - 1) * hop + span;
     it.direct = it.s_lo >= 0 && it.s_lo + it.n_need <= it.L && P.wave_dtype == MAFE_WAVE_F32;   // plain float copy
     return it;
   };
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
       const bool has_b = fa + 1 < nf;
       c2 v[16];
       {  // load + window; frame b = frame a + hop
-        const float* ya = stage + fa * hop + t;
+        const float* ya = stage + fa * hop + t - lo;   // stage[i] = sample lo + i of the half-tile's first frame
         const float* yb = ya + (has_b ? hop : 0);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -403,7 +406,12 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
           }
         }
       }
-      group_bar(g);   // the scratch / power rows are free for the group's next pair
+      // The next pair's stage-A stores go to the scratch, whose last readers (pair separation) all passed a barrier since:
+      // the mel kinds (power rows -> barrier -> projection) need no barrier here, the spectrum kinds read Z until now.
+#ifndef MAFE_F2048_KEEP_BAR7
+      if (P.out_kind == MAFE_OUT_COMPLEX || P.out_kind == MAFE_OUT_POWER)
+#endif
+        group_bar(g);
     }
     }   // cur.ok
     cur = nxt; cur_item = nxt_item; cur_async = nxt_async;
