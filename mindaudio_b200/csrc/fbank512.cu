@@ -821,7 +821,9 @@ int fast_plan_init(mafe_ctx* ctx, mafe_plan* p, const mafe_frontend_desc* d) {
       if ((rc = up(&th->moff_dev, mo))) return rc;
       if ((rc = up(&th->mweights_dev, mw))) return rc;
     }
-    MAFE_CUDA_CHECK(cudaFuncSetAttribute(front2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2048SmemBudget));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(front2048_kernel<3, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2048SmemBudget));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(front2048_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2048SmemBudget));
+    MAFE_CUDA_CHECK(cudaFuncSetAttribute(front2048_kernel<-1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2048SmemBudget));
     return MAFE_OK;
   }
   th->stftn = stftn_plan_supported(d);
@@ -1002,7 +1004,11 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
       MAFE_LAUNCH_CHECK(ctx);
     }
     ProfScope ps(ctx, MAFE_PROF_FBANK_MAIN);
-    front2048_kernel<<<std::min(2 * b->n_tiles, 2 * ctx->sm_count), 256, smem_bytes, ctx->stream>>>(F);
+    // window rows as compile-time constants for the two usual supports: win 1200 (fastspeech2 / wavegrad) and the full window
+    const int grid = std::min(2 * b->n_tiles, 2 * ctx->sm_count);
+    if (F.j0 == 3 && F.j1 == 13) front2048_kernel<3, 13><<<grid, 256, smem_bytes, ctx->stream>>>(F);
+    else if (F.j0 == 0 && F.j1 == 16) front2048_kernel<0, 16><<<grid, 256, smem_bytes, ctx->stream>>>(F);
+    else front2048_kernel<-1, 0><<<grid, 256, smem_bytes, ctx->stream>>>(F);
     MAFE_LAUNCH_CHECK(ctx);
     return (d.out_kind >= MAFE_OUT_MEL || d.utt_scalar_norm) ? kFastNeedsPost : MAFE_OK;
   }

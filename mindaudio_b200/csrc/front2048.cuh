@@ -91,6 +91,14 @@ __device__ __forceinline__ void group_bar(int g) {
   asm volatile("barrier.sync %0, 128;" ::"r"(1 + g) : "memory");
 }
 
+// J0 >= 0: the rows [J0, J1) that meet the window's support are compile-time constants (win 1200: rows 3..12, full window:
+// 0..15) -- the load loop has no predicates and the zero rows fold out of the first butterfly layer; J0 < 0: run-time range.
+#ifndef MAFE_F2048_MEL_UNROLL
+#define MAFE_F2048_MEL_UNROLL 2
+#endif
+#define MAFE_PRAGMA_(x) _Pragma(#x)
+#define MAFE_UNROLL(n) MAFE_PRAGMA_(unroll n)
+template <int J0, int J1>
 __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* stage_base = reinterpret_cast<float*>(smem);
@@ -98,17 +106,16 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   int* s_work = reinterpret_cast<int*>(smem + f2048_off_work(P.stage_floats, P.n_stage, P.mw_floats));
   const int tid = threadIdx.x, g = tid >> 7, t = tid & 127;
   float2* scr = reinterpret_cast<float2*>(smem + f2048_off_scr(P.stage_floats, P.n_stage)) + g * kScr2048;
-  float* prow = reinterpret_cast<float*>(smem + f2048_off_p(P.stage_floats, P.n_stage)) + g * 2 * kPRow2048;
+  // power rows of the group's pair, interleaved: prow[k] = (|X_a[k]|^p, |X_b[k]|^p) -- one 16-byte load = two ready operand pairs
+  float2* prow = reinterpret_cast<float2*>(smem + f2048_off_p(P.stage_floats, P.n_stage)) + g * kPRow2048;
   for (int i = tid; i < P.mw_floats; i += 256) s_mw[i] = P.mweights[i];
-  if (t < 2 * (kPRow2048 - kBins2048)) {   // the pad of the power rows is read (times a zero weight) by the last filters
-    const int f = t / (kPRow2048 - kBins2048), i = t % (kPRow2048 - kBins2048);
-    prow[f * kPRow2048 + kBins2048 + i] = 0.f;
-  }
+  if (t < kPRow2048 - kBins2048) prow[kBins2048 + t] = make_float2(0.f, 0.f);   // the pad is read (times a zero weight) by the last filters
+  const int j0 = J0 >= 0 ? J0 : P.j0, j1 = J0 >= 0 ? J1 : P.j1;
 
   // this thread's window entries w[t + 128 j]
   float win[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) win[j] = P.window[t + 128 * j] * P.wave_scale;   // the staged samples are raw
+  for (int j = 0; j < 16; ++j) win[j] = (j >= j0 && j < j1) ? P.window[t + 128 * j] * P.wave_scale : 0.f;   // the staged samples are raw
   // this thread's twiddles live in its TMEM lane (tcgen05.ld, 12-cycle latency, off the shared-memory pipe): columns 0..29
   // W2048^(t k1), k1 = 1..15 (stage A), columns 32..61 W128^(n3 k2), k2 = 1..15 (stage B).  Threads t and t + 128 (warps w
   // and w + 4) share a TMEM lane and need the same values.
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int hop = P.hop;
-  const int lo = 128 * P.j0, span = 128 * (P.j1 - P.j0);   // staged part of a frame (window support, whole rows)
+  const int lo = 128 * j0, span = 128 * (j1 - j0);   // staged part of a frame (window support, whole rows)
   const int n_items = 2 * P.n_tiles;   // half-tiles of 16 frames (the batch tiles hold 32)
   float vmax = -INFINITY;
   int vmax_utt = -1;
@@ -188,11 +195,21 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
     it.direct = it.s_lo >= 0 && it.s_lo + it.n_need <= it.L && P.wave_dtype == MAFE_WAVE_F32;   // plain float copy
     return it;
   };
-  auto stage_async = [&](const Item& it, float* dst) {   // 4-byte cp.async: the source has no alignment guarantee
-    const float* w = (const float*)P.wave + it.off + it.s_lo;
+  auto stage_async = [&](const Item& it, float* dst) {   // float32 input; 4-byte cp.async: the source has no alignment guarantee
     const uint32_t d = smem_u32(dst);
-    for (int i = tid; i < it.n_need; i += 256)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * i), "l"(w + i) : "memory");
+    if (it.direct) {
+      const float* w = (const float*)P.wave + it.off + it.s_lo;
+      for (int i = tid; i < it.n_need; i += 256)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * i), "l"(w + i) : "memory");
+    } else {   // first / last half-tiles of an utterance: centre padding resolved per element, zeros stored directly
+      const float* w = (const float*)P.wave + it.off;
+      for (int i = tid; i < it.n_need; i += 256) {
+        int64_t sidx = it.s_lo + i;
+        if (sidx < 0 || sidx >= it.L) sidx = P.center ? pad_index_fast(sidx, it.L, P.pad_mode) : -1;
+        if (sidx >= 0 && sidx < it.L) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * i), "l"(w + sidx) : "memory");
+        else dst[i] = 0.f;
+      }
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto stage_sync = [&](const Item& it, float* dst) {     // centre padding / PCM16 resolved while staging
@@ -218,13 +235,13 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
       dst[i] = v;
     }
   };
-  const bool two = P.n_stage == 2;
+  const bool two = P.n_stage == 2 && P.wave_dtype == MAFE_WAVE_F32;   // double buffer: the next item is staged asynchronously
   if (tid == 0) s_work[0] = atomicAdd(P.queue_head, 1);
   __syncthreads();
   Item cur = geometry(s_work[0]);
   int cur_item = s_work[0];
   bool cur_async = false;
-  if (two && cur.ok && cur.direct) { stage_async(cur, stage_base); cur_async = true; }
+  if (two && cur.ok) { stage_async(cur, stage_base); cur_async = true; }
   for (uint32_t iter = 0; cur_item < n_items; ++iter) {
     const int buf = two ? (int)(iter & 1) : 0;
     float* stage = stage_base + (size_t)buf * P.stage_floats;
@@ -233,7 +250,7 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
     const int nxt_item = s_work[1 + (iter & 1)];
     const Item nxt = geometry(nxt_item);
     bool nxt_async = false;
-    if (two && nxt.ok && nxt.direct) { stage_async(nxt, stage_base + (size_t)(buf ^ 1) * P.stage_floats); nxt_async = true; }
+    if (two && nxt.ok) { stage_async(nxt, stage_base + (size_t)(buf ^ 1) * P.stage_floats); nxt_async = true; }
     if (cur.ok) {
       if (cur_async) {
         if (nxt_async) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
         const float* yb = ya + (has_b ? hop : 0);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (j >= P.j0 && j < P.j1) v[j] = mul2(pk(ya[128 * j], yb[128 * j]), bc(win[j]));
+          if (j >= j0 && j < j1) v[j] = mul2(pk(ya[128 * j], yb[128 * j]), bc(win[j]));
           else v[j] = pk(0.f, 0.f);
         }
       }
@@ -323,70 +340,101 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
       }
       group_bar(g);
       // ---- pair separation, emit ----
+      // X_a[k] = Z[k] + conj Z[N-k], X_b[k] = -i (Z[k] - conj Z[N-k]); thread t owns bins t + 128 i, i < 8, thread 0 also bin 1024
+      auto sep = [&](int k, c2& xa, c2& xb) {
+        const int kn = (kN2048 - k) & (kN2048 - 1);
+        const c2 zk = lds_c2(scr + k + (k >> 4)), zn = cnj(lds_c2(scr + kn + (kn >> 4)));
+        xa = add2(zk, zn);
+        xb = mni(sub2(zk, zn));
+      };
+      auto powers = [&](c2 xa, c2 xb, float& pa, float& pb) {   // |X|^power (+ log1p of the deepspeech2 kind)
+        const c2 qa = mul2(xa, xa), qb = mul2(xb, xb);
+        pa = re(qa) + im(qa); pb = re(qb) + im(qb);
+        if (P.power != 2.0f) {
+          if (P.power == 1.0f) { pa = sqrtf(pa); pb = sqrtf(pb); }
+          else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
+        }
+      };
       const int64_t row_a = fo + frame0 + fa;
-      if (P.out_kind == MAFE_OUT_COMPLEX || P.out_kind == MAFE_OUT_POWER) {
+      if (P.out_kind == MAFE_OUT_COMPLEX) {
+        c2* oa = reinterpret_cast<c2*>(P.out + row_a * P.out_dim);
+        c2* ob = reinterpret_cast<c2*>(P.out + (row_a + 1) * P.out_dim);
+        c2 xa[8], xb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sep(t + 128 * i, xa[i], xb[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          oa[t + 128 * i] = xa[i];
+          if (has_b) ob[t + 128 * i] = xb[i];
+        }
+        if (t == 0) {
+          sep(kBins2048 - 1, xa[0], xb[0]);
+          oa[kBins2048 - 1] = xa[0];
+          if (has_b) ob[kBins2048 - 1] = xb[0];
+        }
+      } else if (P.out_kind == MAFE_OUT_POWER) {
         float* oa = P.out + row_a * P.out_dim;
         float* ob = oa + P.out_dim;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {            // warp-uniform trip count: bin 1024 belongs to thread 0 alone
+        const int n_own = t == 0 ? 9 : 8;
+#pragma unroll 1
+        for (int i = 0; i < n_own; ++i) {        // rolled: the general power / log forms are long (they were 90 KB of code unrolled)
           const int k = t + 128 * i;
-          if (k >= kBins2048) continue;
-          const int kn = (kN2048 - k) & (kN2048 - 1);
-          const c2 zk = lds_c2(scr + k + (k >> 4)), zn = cnj(lds_c2(scr + kn + (kn >> 4)));
-          const c2 xa = add2(zk, zn), xb = mni(sub2(zk, zn));
-          if (P.out_kind == MAFE_OUT_COMPLEX) {
-            reinterpret_cast<c2*>(oa)[k] = xa;
-            if (has_b) reinterpret_cast<c2*>(ob)[k] = xb;
-          } else {
-            const c2 qa = mul2(xa, xa), qb = mul2(xb, xb);
-            float pa = re(qa) + im(qa), pb = re(qb) + im(qb);
-            if (P.power != 2.0f) {
-              if (P.power == 1.0f) { pa = sqrtf(pa); pb = sqrtf(pb); }
-              else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
-            }
-            if (P.log_kind == MAFE_LOG_LN_PLUS) {
-              pa = P.log_arg == 1.0f ? log1pf(pa) : logf(pa + P.log_arg);
-              pb = P.log_arg == 1.0f ? log1pf(pb) : logf(pb + P.log_arg);
-            }
-            oa[k] = pa;
-            if (has_b) ob[k] = pb;
+          c2 xa, xb;
+          sep(k, xa, xb);
+          float pa, pb;
+          powers(xa, xb, pa, pb);
+          if (P.log_kind == MAFE_LOG_LN_PLUS) {
+            pa = P.log_arg == 1.0f ? log1pf(pa) : logf(pa + P.log_arg);
+            pb = P.log_arg == 1.0f ? log1pf(pb) : logf(pb + P.log_arg);
           }
+          oa[k] = pa;
+          if (has_b) ob[k] = pb;
         }
       } else {
+        if (P.power == 2.0f) {                   // the usual mel front-end: branch-free, all 16 loads of a thread in flight
+          c2 xa[8], xb[8];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int k = t + 128 * i;
-          if (k >= kBins2048) continue;
-          const int kn = (kN2048 - k) & (kN2048 - 1);
-          const c2 zk = lds_c2(scr + k + (k >> 4)), zn = cnj(lds_c2(scr + kn + (kn >> 4)));
-          const c2 xa = add2(zk, zn), xb = mni(sub2(zk, zn));
-          const c2 qa = mul2(xa, xa), qb = mul2(xb, xb);
-          float pa = re(qa) + im(qa), pb = re(qb) + im(qb);
-          if (P.power != 2.0f) {
-            if (P.power == 1.0f) { pa = sqrtf(pa); pb = sqrtf(pb); }
-            else { pa = powf(sqrtf(pa), P.power); pb = powf(sqrtf(pb), P.power); }
+          for (int i = 0; i < 8; ++i) sep(t + 128 * i, xa[i], xb[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const c2 qa = mul2(xa[i], xa[i]), qb = mul2(xb[i], xb[i]);
+            prow[t + 128 * i] = make_float2(re(qa) + im(qa), re(qb) + im(qb));
           }
-          prow[k] = pa;
-          prow[kPRow2048 + k] = pb;
+          if (t == 0) {
+            sep(kBins2048 - 1, xa[0], xb[0]);
+            const c2 qa = mul2(xa[0], xa[0]), qb = mul2(xb[0], xb[0]);
+            prow[kBins2048 - 1] = make_float2(re(qa) + im(qa), re(qb) + im(qb));
+          }
+        } else {
+          const int n_own = t == 0 ? 9 : 8;
+#pragma unroll 1
+          for (int i = 0; i < n_own; ++i) {
+            const int k = t + 128 * i;
+            c2 xa, xb;
+            sep(k, xa, xb);
+            float pa, pb;
+            powers(xa, xb, pa, pb);
+            prow[k] = make_float2(pa, pb);
+          }
         }
         group_bar(g);
-        // mel projection: thread = filter, dense dot product over the filter's support for both frames
+        // mel projection: thread = filter, dense dot product over the filter's support for both frames: chunk i = 4 bins =
+        // two 16-byte loads of (a, b) pairs against one 16-byte load of weights
         for (int m0 = 0; m0 < P.n_mels; m0 += 128) {
           const int m = m0 + t;
           if (m >= P.n_mels) continue;
           const int s = P.mstart[m], nch = P.mcount[m];     // nch: the same for the 32 filters of a warp
           const float4* w4 = reinterpret_cast<const float4*>(s_mw) + P.moff[m] + (t & 31);
-          const float4* ra4 = reinterpret_cast<const float4*>(prow + s);
-          const float4* rb4 = reinterpret_cast<const float4*>(prow + kPRow2048 + s);
+          const float4* r4 = reinterpret_cast<const float4*>(prow + s);
           c2 acc = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
-#pragma unroll 2
+MAFE_UNROLL(MAFE_F2048_MEL_UNROLL)
           for (int i = 0; i < nch; ++i) {
             const float4 ww = w4[32 * i];
-            const float4 pa4 = ra4[i], pb4 = rb4[i];
-            acc = fma2(pk(pa4.x, pb4.x), bc(ww.x), acc);
-            acc1 = fma2(pk(pa4.y, pb4.y), bc(ww.y), acc1);
-            acc = fma2(pk(pa4.z, pb4.z), bc(ww.z), acc);
-            acc1 = fma2(pk(pa4.w, pb4.w), bc(ww.w), acc1);
+            const float4 p01 = r4[2 * i], p23 = r4[2 * i + 1];
+            acc = fma2(pk(p01.x, p01.y), bc(ww.x), acc);
+            acc1 = fma2(pk(p01.z, p01.w), bc(ww.y), acc1);
+            acc = fma2(pk(p23.x, p23.y), bc(ww.z), acc);
+            acc1 = fma2(pk(p23.z, p23.w), bc(ww.w), acc1);
           }
           acc = add2(acc, acc1);
           float o[2] = {re(acc), im(acc)};

@@ -56,6 +56,8 @@ def test_stft_shapes_and_layout(ma, golden):
     (512, 256, None, "hann", "wrap"),                                                    # host-pad fallback
     (256, 64, None, "hann", "reflect"), (4096, 1024, None, "hann", "constant"), (8192, 2048, 6000, "hamming", "constant"),
     (1024, 256, None, "hann", "constant"), (128, 32, None, "hann", "constant"),          # radix-16 passes: 16*16, 16^3, 16^3*2, 16*16*4; 128 = 4^3*2
+    # front2048_kernel: window rows as run-time range (win 1000 -> rows 4..11), full window with zero / symmetric centre padding
+    (2048, 400, 1000, "hamming", "edge"), (2048, 512, None, "hann", "constant"), (2048, 300, 1200, "hann", "symmetric"),
 ])
 def test_stft_batch_vs_oracle(ma, n_fft, hop, win, window, mode):
     x = synth(2, (3, 16000))
@@ -198,6 +200,15 @@ def test_spectrogram_melspectrogram_melscale(ma, golden):
         for shape in ((3, 16000), (2, 32 * 200 + 399), (4, kw["n_fft"])):
             xs = synth(31 + shape[1] % 7, shape)
             assert rel(ma.spectrogram(xs, **kw), R.spectrogram(xs, **kw)) <= 1e-5, (kw, shape)
+    # front2048_kernel: power / mel output, every power form, ragged half-tile borders (16 frames), run-time window rows
+    for kw in (dict(n_fft=2048, win_length=1200, hop_length=300), dict(n_fft=2048, hop_length=512, power=1.0, pad_mode="constant"),
+               dict(n_fft=2048, win_length=900, hop_length=256, power=3.0, window="hamming", pad_mode="edge")):
+        for shape in ((2, 22050), (3, 15 * kw["hop_length"] + 2048), (2, 2048)):
+            xs = synth(41 + shape[1] % 5, shape)
+            assert rel(ma.spectrogram(xs, **kw), R.spectrogram(xs, **kw)) <= 1e-5, (kw, shape)
+            for p in (2.0, 1.0):
+                mk = dict(kw, power=p, n_mels=64, f_max=7000.0)
+                assert rel(ma.melspectrogram(xs, **mk), R.melspectrogram(xs, **mk)) <= 1e-5, (mk, shape)
 
 
 def test_phase_vocoder_and_time_stretch(ma):
