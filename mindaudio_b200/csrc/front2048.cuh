@@ -93,11 +93,6 @@ __device__ __forceinline__ void group_bar(int g) {
 
 // J0 >= 0: the rows [J0, J1) that meet the window's support are compile-time constants (win 1200: rows 3..12, full window:
 // 0..15) -- the load loop has no predicates and the zero rows fold out of the first butterfly layer; J0 < 0: run-time range.
-#ifndef MAFE_F2048_MEL_UNROLL
-#define MAFE_F2048_MEL_UNROLL 2
-#endif
-#define MAFE_PRAGMA_(x) _Pragma(#x)
-#define MAFE_UNROLL(n) MAFE_PRAGMA_(unroll n)
 template <int J0, int J1>
 __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -156,6 +151,8 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const bool mel_kind = P.out_kind >= MAFE_OUT_MEL && t < P.n_mels;
+  const int mel_s = mel_kind ? P.mstart[t] : 0, mel_n = mel_kind ? P.mcount[t] : 1, mel_o = mel_kind ? P.moff[t] : 0;
   const int hop = P.hop;
   const int lo = 128 * j0, span = 128 * (j1 - j0);   // staged part of a frame (window support, whole rows)
   const int n_items = 2 * P.n_tiles;   // half-tiles of 16 frames (the batch tiles hold 32)
@@ -423,19 +420,24 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
         for (int m0 = 0; m0 < P.n_mels; m0 += 128) {
           const int m = m0 + t;
           if (m >= P.n_mels) continue;
-          const int s = P.mstart[m], nch = P.mcount[m];     // nch: the same for the 32 filters of a warp
-          const float4* w4 = reinterpret_cast<const float4*>(s_mw) + P.moff[m] + (t & 31);
+          // the filter's table entries: registers for the first 128 filters (loaded once per kernel, not once per pair)
+          const int s = m0 == 0 ? mel_s : P.mstart[m], nch = m0 == 0 ? mel_n : P.mcount[m];     // nch: the same for the 32 filters of a warp
+          const float4* w4 = reinterpret_cast<const float4*>(s_mw) + (m0 == 0 ? mel_o : P.moff[m]) + (t & 31);
           const float4* r4 = reinterpret_cast<const float4*>(prow + s);
           c2 acc = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
-MAFE_UNROLL(MAFE_F2048_MEL_UNROLL)
-          for (int i = 0; i < nch; ++i) {
-            const float4 ww = w4[32 * i];
-            const float4 p01 = r4[2 * i], p23 = r4[2 * i + 1];
+          float4 ww = w4[0], p01 = r4[0], p23 = r4[1];      // nch >= 1; the next chunk's loads are issued before this chunk's FMAs
+          for (int i = 1; i < nch; ++i) {
+            const float4 nw = w4[32 * i], n01 = r4[2 * i], n23 = r4[2 * i + 1];
             acc = fma2(pk(p01.x, p01.y), bc(ww.x), acc);
             acc1 = fma2(pk(p01.z, p01.w), bc(ww.y), acc1);
             acc = fma2(pk(p23.x, p23.y), bc(ww.z), acc);
             acc1 = fma2(pk(p23.z, p23.w), bc(ww.w), acc1);
+            ww = nw; p01 = n01; p23 = n23;
           }
+          acc = fma2(pk(p01.x, p01.y), bc(ww.x), acc);
+          acc1 = fma2(pk(p01.z, p01.w), bc(ww.y), acc1);
+          acc = fma2(pk(p23.x, p23.y), bc(ww.z), acc);
+          acc1 = fma2(pk(p23.z, p23.w), bc(ww.w), acc1);
           acc = add2(acc, acc1);
           float o[2] = {re(acc), im(acc)};
 #pragma unroll
