@@ -992,7 +992,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     F.group_max = b->group_max_dev; F.utt_group = b->utt_group_dev;
     // staging buffers for this hop and window support: (16 - 1) hop + 128 (j1 - j0) samples, rounded to 16 bytes; two when
     // they fit 2 CTAs per SM (fastspeech2: win 1200 -> 10 of 16 rows, 23 KB per buffer instead of 26: both fit)
-    F.stage_floats = (((kHalfFrames2048 - 1) * d.hop + 128 * (th->j1_2048 - th->j0_2048)) + 3) & ~3;
+    F.stage_floats = (((kHalfFrames2048 - 1) * d.hop + 128 * (th->j1_2048 - th->j0_2048)) + 3 + 4) & ~3;   // + the alignment shift (<= 3)
     F.mw_floats = d.out_kind >= MAFE_OUT_MEL ? ((th->mw_floats_2048 + 3) & ~3) : 0;
     F.n_stage = f2048_smem_total(F.stage_floats, 2, F.mw_floats) <= kF2048SmemBudget ? 2 : 1;
     const size_t smem_bytes = f2048_smem_total(F.stage_floats, F.n_stage, F.mw_floats);

@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   const bool want_max = P.out_kind >= MAFE_OUT_MEL && P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE;
 
   // geometry of a work item (half-tile)
-  struct Item { int frame0, nf, T; int utt; int64_t off, L, fo, s_lo; int n_need; bool ok, direct; };
+  struct Item { int frame0, nf, T; int utt; int64_t off, L, fo, s_lo; int n_need, sh; bool ok, direct; };
   auto geometry = [&](int item) {
     Item it;
-    it.ok = false; it.direct = false; it.frame0 = 0; it.nf = 0; it.T = 0; it.utt = 0; it.off = 0; it.L = 0; it.fo = 0; it.s_lo = 0; it.n_need = 0;
+    it.ok = false; it.direct = false; it.frame0 = 0; it.nf = 0; it.T = 0; it.utt = 0; it.off = 0; it.L = 0; it.fo = 0; it.s_lo = 0; it.n_need = 0; it.sh = 0;
     if (item >= n_items) return it;
     const Tile tile = P.tiles[item >> 1];
     it.frame0 = tile.frame0 + kHalfFrames2048 * (item & 1);
@@ -190,14 +190,19 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
     it.s_lo = (int64_t)it.frame0 * hop - (P.center ? kN2048 / 2 : 0) + lo;
     it.n_need = (it.nf - 1) * hop + span;
     it.direct = it.s_lo >= 0 && it.s_lo + it.n_need <= it.L && P.wave_dtype == MAFE_WAVE_F32;   // plain float copy
+    // plain copies land `sh` floats into the staging buffer, so that source and destination share their 16-byte phase
+    if (it.direct) it.sh = (int)((reinterpret_cast<uintptr_t>((const float*)P.wave + it.off + it.s_lo) >> 2) & 3);
     return it;
   };
   auto stage_async = [&](const Item& it, float* dst) {   // float32 input; 4-byte cp.async: the source has no alignment guarantee
     const uint32_t d = smem_u32(dst);
-    if (it.direct) {
+    if (it.direct) {   // dst = buffer + it.sh: 16-byte copies between the (<= 3)-element head and tail
       const float* w = (const float*)P.wave + it.off + it.s_lo;
-      for (int i = tid; i < it.n_need; i += 256)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * i), "l"(w + i) : "memory");
+      const int head = min((4 - it.sh) & 3, it.n_need), n16 = (it.n_need - head) >> 2, tail0 = head + 4 * n16;
+      if (tid < head) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * tid), "l"(w + tid) : "memory");
+      for (int q = tid; q < n16; q += 256)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 4u * (head + 4 * q)), "l"(w + head + 4 * q) : "memory");
+      if (tid < it.n_need - tail0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * (tail0 + tid)), "l"(w + tail0 + tid) : "memory");
     } else {   // first / last half-tiles of an utterance: centre padding resolved per element, zeros stored directly
       const float* w = (const float*)P.wave + it.off;
       for (int i = tid; i < it.n_need; i += 256) {
@@ -238,16 +243,16 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   Item cur = geometry(s_work[0]);
   int cur_item = s_work[0];
   bool cur_async = false;
-  if (two && cur.ok) { stage_async(cur, stage_base); cur_async = true; }
+  if (two && cur.ok) { stage_async(cur, stage_base + cur.sh); cur_async = true; }
   for (uint32_t iter = 0; cur_item < n_items; ++iter) {
     const int buf = two ? (int)(iter & 1) : 0;
-    float* stage = stage_base + (size_t)buf * P.stage_floats;
+    float* stage = stage_base + (size_t)buf * P.stage_floats + cur.sh;
     if (tid == 0) s_work[1 + (iter & 1)] = atomicAdd(P.queue_head, 1);   // claim the next item
     __syncthreads();   // the other staging buffer (previous item) is no longer read; the claim is visible
     const int nxt_item = s_work[1 + (iter & 1)];
     const Item nxt = geometry(nxt_item);
     bool nxt_async = false;
-    if (two && nxt.ok) { stage_async(nxt, stage_base + (size_t)(buf ^ 1) * P.stage_floats); nxt_async = true; }
+    if (two && nxt.ok) { stage_async(nxt, stage_base + (size_t)(buf ^ 1) * P.stage_floats + nxt.sh); nxt_async = true; }
     if (cur.ok) {
       if (cur_async) {
         if (nxt_async) asm volatile("cp.async.wait_group 1;" ::: "memory");
