@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const bool mel_kind = P.out_kind >= MAFE_OUT_MEL && t < P.n_mels;
+  const int n_mels = P.n_mels, out_dim = P.out_dim, log_kind = P.log_kind;
+  const bool mel_kind = P.out_kind >= MAFE_OUT_MEL && t < n_mels;
   const int mel_s = mel_kind ? P.mstart[t] : 0, mel_n = mel_kind ? P.mcount[t] : 1, mel_o = mel_kind ? P.moff[t] : 0;
   const int hop = P.hop;
   const int lo = 128 * j0, span = 128 * (j1 - j0);   // staged part of a frame (window support, whole rows)
@@ -305,9 +306,11 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
         for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds_c2(scr + k1 * 136 + 8 * n2 + n3);
         group_bar(g);                          // everyone has read the stage-A layout: the scratch is re-used
         fft16p(v);
+        // column k2 ^ 8 (k1 & 1): two bases, compile-time offsets (k2 < 8 -> dlo + k2, else dhi + k2 - 8)
         const int sw = (k1 & 1) << 3;
-        float2* dst = scr + n3 * 257 + k1 * 16;
-        sts_c2(dst + (0 ^ sw), v[fft16_pos(0)]);
+        float2* dlo = scr + n3 * 257 + k1 * 16 + sw;
+        float2* dhi = scr + n3 * 257 + k1 * 16 + (sw ^ 8);
+        sts_c2(dlo, v[fft16_pos(0)]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float tw[8];
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int k2 = 4 * c + 1 + i;
-            if (k2 < 16) sts_c2(dst + (k2 ^ sw), cmul(v[fft16_pos(k2)], tw[2 * i], tw[2 * i + 1]));
+            if (k2 < 16) sts_c2(k2 < 8 ? dlo + k2 : dhi + (k2 - 8), cmul(v[fft16_pos(k2)], tw[2 * i], tw[2 * i + 1]));
           }
         }
       }
@@ -333,11 +336,12 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
         group_bar(g);
         dft8p(w0);
         dft8p(w1);
+        // skewed index k + k / 16 of k = k1 + 16 k2 + 256 k3 (k1 < 16): k1 + 17 k2 + 272 k3 -- one base, compile-time offsets
+        float2* zb = scr + k1a + 17 * k2;
 #pragma unroll
         for (int k3 = 0; k3 < 8; ++k3) {
-          const int ka = k1a + 16 * k2 + 256 * k3, kb = k1b + 16 * k2 + 256 * k3;
-          sts_c2(scr + ka + (ka >> 4), w0[k3]);
-          sts_c2(scr + kb + (kb >> 4), w1[k3]);
+          sts_c2(zb + 272 * k3, w0[k3]);
+          sts_c2(zb + 272 * k3 + 8, w1[k3]);
         }
       }
       group_bar(g);
@@ -422,12 +426,9 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
         group_bar(g);
         // mel projection: thread = filter, dense dot product over the filter's support for both frames: chunk i = 4 bins =
         // two 16-byte loads of (a, b) pairs against one 16-byte load of weights
-        for (int m0 = 0; m0 < P.n_mels; m0 += 128) {
-          const int m = m0 + t;
-          if (m >= P.n_mels) continue;
-          // the filter's table entries: registers for the first 128 filters (loaded once per kernel, not once per pair)
-          const int s = m0 == 0 ? mel_s : P.mstart[m], nch = m0 == 0 ? mel_n : P.mcount[m];     // nch: the same for the 32 filters of a warp
-          const float4* w4 = reinterpret_cast<const float4*>(s_mw) + (m0 == 0 ? mel_o : P.moff[m]) + (t & 31);
+        float* orow = P.out + row_a * out_dim;
+        auto mel_filter = [&](int m, int s, int nch, int off4) {
+          const float4* w4 = reinterpret_cast<const float4*>(s_mw) + off4 + (t & 31);
           const float4* r4 = reinterpret_cast<const float4*>(prow + s);
           c2 acc = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
           float4 ww = w4[0], p01 = r4[0], p23 = r4[1];      // nch >= 1; the next chunk's loads are issued before this chunk's FMAs
@@ -448,18 +449,21 @@ __global__ void __launch_bounds__(256, 2) front2048_kernel(const F2048Params P) 
 #pragma unroll
           for (int f = 0; f < 2; ++f) {
             float x = o[f];
-            switch (P.log_kind) {
+            switch (log_kind) {
               case MAFE_LOG_LN_EPS_IF_ZERO: x = logf(x == 0.f ? 2.220446049250313e-16f : x); break;
               case MAFE_LOG_LN_PLUS: x = logf(x + P.log_arg); break;
               case MAFE_LOG_DB: x = P.log_mult * log10f(fmaxf(x, P.log_arg)) - P.log_offset; break;
               default: break;
             }
             if (f == 0 || has_b) {
-              P.out[(row_a + f) * P.out_dim + m] = x;
+              orow[(int64_t)f * out_dim + m] = x;
               if (want_max) vmax = fmaxf(vmax, x);
             }
           }
-        }
+        };
+        // the first 128 filters: table entries in registers (loaded once per kernel, not once per pair); more: from the tables
+        if (mel_kind) mel_filter(t, mel_s, mel_n, mel_o);
+        for (int m = 128 + t; m < n_mels; m += 128) mel_filter(m, P.mstart[m], P.mcount[m], P.moff[m]);
       }
       // The next pair's stage-A stores go to the scratch, whose last readers (pair separation) all passed a barrier since:
       // the mel kinds (power rows -> barrier -> projection) need no barrier here, the spectrum kinds read Z until now.
