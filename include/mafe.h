@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MAFE_VERSION 101 /* 0.1.1: mafe_frontend_desc gained utt_scalar_norm */
+#define MAFE_VERSION 102 /* 0.1.2: mafe_frontend_run_aux (0.1.1: mafe_frontend_desc gained utt_scalar_norm) */
 
 /* ---- status codes ---- */
 #define MAFE_OK 0
@@ -208,6 +208,18 @@ const int64_t* mafe_batch_frame_offsets_dev(const mafe_batch* batch);
  */
 int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, const void* wave_dev, int32_t wave_dtype,
                       float wave_scale, float* out_dev, int32_t db_group);
+
+/*
+ * mafe_frontend_run of a MAFE_OUT_LOGMEL / MAFE_OUT_MFCC plan that ALSO writes the mel energies the features are the
+ * log / DCT of -- exactly what the same front-end with out_kind MAFE_OUT_MEL writes -- to aux_mel_dev
+ * [total_frames][n_mels].  For pipelines that call melspectrogram() and fbank() / mfcc() on the same waveforms with
+ * the same front-end parameters (spectrum.py:609-698 next to features.py:196-270 / :273-373; BASELINE configs[3]):
+ * one transform instead of two.  aux_mel_dev == NULL: plain mafe_frontend_run.  Returns MAFE_E_UNSUPPORTED, with
+ * nothing launched, when the plan's kernel cannot emit the second output (today: anything but the n_fft 400 tile
+ * kernel on 16-byte aligned float32 input with wave_scale 1); the caller then runs a MAFE_OUT_MEL plan beside it.
+ */
+int mafe_frontend_run_aux(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, const void* wave_dev, int32_t wave_dtype,
+                          float wave_scale, float* out_dev, int32_t db_group, float* aux_mel_dev);
 
 /*
  * The same path with HOST buffers (what a numpy / data-loader caller has): wave_host is the flat waveform

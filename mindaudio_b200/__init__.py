@@ -15,6 +15,7 @@ from .data.processing import *  # noqa: F401,F403
 from .data.cmvn import *  # noqa: F401,F403
 from .data.features import *  # noqa: F401,F403
 from .data.spectrum import *  # noqa: F401,F403
+from .data.features import mel_and_fbank, mel_and_mfcc  # noqa: F401  (extensions: two outputs of one transform)
 from .frontend import FbankPipeline, compute_fbank_feats, ds2_features  # noqa: F401
 
 __version__ = "0.1.0"

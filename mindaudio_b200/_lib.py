@@ -15,6 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "mafe.h")
 
 # ---- constants mirrored from include/mafe.h ----
 OK = 0
+E_UNSUPPORTED = -4
 PAD = {"constant": 0, "reflect": 1, "edge": 2, "symmetric": 3}
 OUT_COMPLEX, OUT_POWER, OUT_MEL, OUT_LOGMEL, OUT_MFCC = range(5)
 LOG_NONE, LOG_LN_EPS_IF_ZERO, LOG_LN_PLUS, LOG_DB = range(4)
@@ -80,6 +81,7 @@ _PROTOS = {
     "mafe_batch_frame_offsets": (C.c_int, [_P, _P]),
     "mafe_batch_frame_offsets_dev": (_P, [_P]),
     "mafe_frontend_run": (C.c_int, [_P, _P, _P, _P, _I32, _F, _P, _I32]),
+    "mafe_frontend_run_aux": (C.c_int, [_P, _P, _P, _P, _I32, _F, _P, _I32, _P]),
     "mafe_frontend_run_host": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _F, _P, _P, _I32, _I32]),
     "mafe_magphase": (C.c_int, [_P, _P, _I64, _F, _P, _P]),
     "mafe_amplitude_to_db": (C.c_int, [_P, _P, _P, _I64, _I64, _F, _F, _F, _F]),
@@ -146,7 +148,7 @@ def load():
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.mafe_version() != 101:
+    if lib.mafe_version() != 102:
         raise MafeError("libmafe.so version mismatch: %d" % lib.mafe_version())
     _lib = lib
     return lib

@@ -490,6 +490,22 @@ int mafe_frontend_run(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, c
   return MAFE_OK;
 }
 
+int mafe_frontend_run_aux(mafe_ctx* ctx, const mafe_plan* plan, mafe_batch* batch, const void* wave_dev, int32_t wave_dtype,
+                          float wave_scale, float* out_dev, int32_t db_group, float* aux_mel_dev) {
+  if (!aux_mel_dev) return mafe_frontend_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev, db_group);
+  MAFE_REQUIRE(ctx && plan && batch, "mafe_frontend_run_aux: NULL handle");
+  MAFE_REQUIRE(plan->d.out_kind == MAFE_OUT_LOGMEL || plan->d.out_kind == MAFE_OUT_MFCC,
+               "mafe_frontend_run_aux: the plan's out_kind must be MAFE_OUT_LOGMEL or MAFE_OUT_MFCC");
+  if (!plan->fast || !fast_has_aux_mel(plan) || wave_dtype != MAFE_WAVE_F32 || wave_scale != 1.0f || ((uintptr_t)wave_dev & 15) != 0) {
+    set_error("mafe_frontend_run_aux: this plan / input runs on a kernel without the second output");
+    return MAFE_E_UNSUPPORTED;
+  }
+  ctx->aux_mel = aux_mel_dev;
+  const int rc = mafe_frontend_run(ctx, plan, batch, wave_dev, wave_dtype, wave_scale, out_dev, db_group);
+  ctx->aux_mel = nullptr;
+  return rc;
+}
+
 // ---------------------------------------------------------------- host-to-host hot path
 int mafe_frontend_run_host(mafe_ctx* ctx, const mafe_plan* plan, const int64_t* so, int32_t n_utts, const void* wave_host,
                            int32_t wave_dtype, float wave_scale, float* out_host, int64_t* frame_offsets_out,

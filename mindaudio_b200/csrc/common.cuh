@@ -83,6 +83,7 @@ struct mafe_ctx {
   cudaEvent_t stage_up_done = nullptr;   // the upload that last read stage_up
   void* stage_down = nullptr;
   size_t cap_stage_down = 0;
+  float* aux_mel = nullptr;   // mafe_frontend_run_aux: second output of the running call (mel energies), else NULL
 };
 
 namespace mafe {
@@ -180,6 +181,7 @@ int fast_tile_frames();
 constexpr int kFastNeedsPost = 1;
 int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale,
              float* out, int db_group);
+bool fast_has_aux_mel(const mafe_plan* p);
 }  // namespace mafe
 
 // ---- device helpers ----

@@ -53,6 +53,7 @@ struct F400Params {
   const float2* tw400;     // [25][32]  W400^(t kj), t = 0..31 (t >= 16: the rotated upper half-warp, see stftn16.cuh)
   const int* combine;      // [n_mels]: plane rows A | B << 8 holding the filter's partial sums
   float* out;              // [total_frames][n_mels]
+  float* aux_mel;          // mafe_frontend_run_aux: the mel energies before the log, same layout; or null
   int* queue_head;
   int* group_max;          // dB maxima (ordered-int keys) or null
   const int* utt_group;
@@ -359,9 +360,11 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_F400_CTAS) fbank400_kernel(
         const float* pa = planes + (crow & 0xff) * kPlaneStride;
         const float* pb = planes + (crow >> 8) * kPlaneStride;
         float* od = P.out + cur.out_row * (int64_t)nm + cm;
+        float* ad = P.aux_mel ? P.aux_mel + cur.out_row * (int64_t)nm + cm : nullptr;
 #pragma unroll 2
         for (int f = cg; f < cur.nf; f += G) {
           const float e = pa[f] + pb[f];
+          if (ad) ad[(int64_t)f * nm] = e;
           float o = e;
           if (P.log_kind == MAFE_LOG_DB) {
             float l2;

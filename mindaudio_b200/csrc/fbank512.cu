@@ -969,6 +969,11 @@ __global__ void fill_keys_kernel(int* p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
+bool fast_has_aux_mel(const mafe_plan* p) {   // kernels that can emit the mel energies beside the log-mel (mafe_frontend_run_aux)
+  const FastTablesHost* th = static_cast<const FastTablesHost*>(p->fast_tables);
+  return th != nullptr && th->f400 && p->d.out_kind >= MAFE_OUT_LOGMEL;
+}
+
 int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave, int wave_dtype, float wave_scale, float* out,
              int db_group) {
   if (b->n_tiles == 0) return MAFE_OK;
@@ -1022,6 +1027,7 @@ int fast_run(mafe_ctx* ctx, const mafe_plan* p, mafe_batch* b, const void* wave,
     F.log_arg = d.log_arg; F.log_mult = d.log_mult; F.log_offset = d.log_offset;
     F.window = th->dev.window; F.tw400 = th->tw400_dev; F.plane_rows = th->sweep400.zero_row + 1;
     F.combine = th->dev.combine; F.out = out; F.queue_head = b->queue_dev;
+    F.aux_mel = ctx->aux_mel;
     F.db_group = (d.log_kind == MAFE_LOG_DB && d.top_db >= 0.f && d.out_kind != MAFE_OUT_MEL) ? db_group : MAFE_DBGROUP_NONE;
     F.group_max = b->group_max_dev; F.utt_group = b->utt_group_dev;
     for (int i = 0; i < 16; ++i) F.tw25[i] = th->tw25[i];

@@ -119,7 +119,10 @@ def _postprocess(eng, d_feat, n_mats, t, dim, deltas, context, left, right):
 
 
 def _features(waveforms, plan_kw, n_out, deltas, context, left_frames, right_frames, win_length, hop_length,
-              window, n_fft):
+              window, n_fft, aux_mels=0):
+    """``aux_mels`` > 0 (``mel_and_fbank`` / ``mel_and_mfcc``): also return the mel spectrogram ``[..., aux_mels, T]`` the
+    features are the dB / DCT of, written by the same kernel launch (``mafe_frontend_run_aux``); kernels without the second
+    output run a ``MAFE_OUT_MEL`` plan on the uploaded waveform instead."""
     waveforms = np.asarray(waveforms)
     if waveforms.ndim not in (1, 2, 3):
         raise TypeError("Unsupported MelSpectrogram shape {}".format(waveforms.ndim + 1))
@@ -148,7 +151,25 @@ def _features(waveforms, plan_kw, n_out, deltas, context, left_frames, right_fra
             dw = eng.buf("wave", x.nbytes)
             do = eng.buf("out", 4 * max(b.total_frames, 1) * n_out)
             keep = eng.h2d(dw, x)
-            L.check(eng.lib.mafe_frontend_run(eng.ctx, plan.h, b.h, dw, L.WAVE_F32, 1.0, do, db_group))
+            mel = None
+            if aux_mels:
+                mel = np.empty((max(b.total_frames, 0), aux_mels), dtype=np.float32)
+                dm = eng.buf("aux", 4 * max(b.total_frames, 1) * aux_mels)
+                rc = eng.lib.mafe_frontend_run_aux(eng.ctx, plan.h, b.h, dw, L.WAVE_F32, 1.0, do, db_group, dm)
+                if rc == L.E_UNSUPPORTED:     # this kernel has no second output: a MAFE_OUT_MEL plan beside the feature plan
+                    mel_plan = _sp._spectrogram_plan(eng, n_fft, win_length, hop_length, window, 2.0, False, True, "reflect",
+                                                     out_kind=L.OUT_MEL, mel_fb=plan_kw["mel_fb"])
+                    b2 = eng.batch(mel_plan, _sp._dense_offsets(n_mats, x.shape[1]))
+                    try:
+                        L.check(eng.lib.mafe_frontend_run(eng.ctx, mel_plan.h, b2.h, dw, L.WAVE_F32, 1.0, dm, L.DBGROUP_NONE))
+                    finally:
+                        b2.close()
+                    rc = eng.lib.mafe_frontend_run(eng.ctx, plan.h, b.h, dw, L.WAVE_F32, 1.0, do, db_group)
+                L.check(rc)
+                if mel.size:
+                    eng.d2h(mel, dm)
+            else:
+                L.check(eng.lib.mafe_frontend_run(eng.ctx, plan.h, b.h, dw, L.WAVE_F32, 1.0, do, db_group))
             # [batch, channel, time] input: the reference's 4-D context route convolves along the channel
             # axis (features.py:108-126) -> done by context_window() on the finished array below
             ctx_dev = context and waveforms.ndim < 3
@@ -162,7 +183,11 @@ def _features(waveforms, plan_kw, n_out, deltas, context, left_frames, right_fra
             b.close()
     if context and not ctx_dev:
         out = context_window(out, left_frames, right_frames)
-    return out.astype(_sp._out_dtype(waveforms), copy=False)
+    out = out.astype(_sp._out_dtype(waveforms), copy=False)
+    if aux_mels:
+        mel = _sp._frames_to_ft(mel, lead, t, aux_mels).astype(_sp._out_dtype(waveforms), copy=False)
+        return mel, out
+    return out
 
 
 def fbank(
@@ -188,6 +213,36 @@ def fbank(
     out = _features(waveforms, kw, n_mels, deltas, context, left_frames, right_frames, win_length, hop_length,
                     window, n_fft)
     return out
+
+
+def mel_and_fbank(waveforms, n_mels=40, n_fft=400, sample_rate=16000, f_min=0.0, f_max=None, win_length=None, hop_length=None,
+                  window="hann"):
+    """EXTENSION (not in the reference): ``(melspectrogram(x, ...), fbank(x, ...))`` of the same waveforms with the same front-end
+    parameters from ONE transform -- what a pipeline that calls ``spectrum.melspectrogram`` (spectrum.py:609-698) next to
+    ``features.fbank`` (features.py:196-270) computes twice.  The two arrays equal the separate calls' results
+    (``melspectrogram(x, n_fft, win_length, hop_length, window=window, n_mels=n_mels, sample_rate=..., f_min=..., f_max=...)`` and
+    ``fbank(x, n_mels=n_mels, ...)``): the n_fft 400 kernel writes the mel energies beside their dB (``mafe_frontend_run_aux``)."""
+    bank = _sp._mel_bank(n_fft, n_mels, sample_rate, f_min, f_max, "none", "htk")
+    kw = dict(out_kind=L.OUT_LOGMEL, mel_fb=bank, log_kind=L.LOG_DB, log_arg=1e-10, log_mult=10.0,
+              log_offset=10.0 * np.log10(max(1e-10, 1.0)), top_db=80.0)
+    return _features(waveforms, kw, n_mels, False, False, 0, 0, win_length, hop_length, window, n_fft, aux_mels=n_mels)
+
+
+def mel_and_mfcc(waveforms, n_mels=23, n_mfcc=20, n_fft=400, sample_rate=16000, f_min=0.0, f_max=None, win_length=None,
+                 hop_length=None, norm="ortho", log_mels=False):
+    """EXTENSION (not in the reference): ``(melspectrogram(x, ...), mfcc(x, ..., deltas=False, context=False))`` from ONE transform
+    (BASELINE configs[3]: the ECAPA-TDNN / fastspeech2 style front-end asks for both); see :func:`mel_and_fbank`."""
+    norm = NormMode(norm)
+    if n_mfcc > n_mels:
+        raise ValueError("The number of MFCC coefficients must be no more than # mel bins.")
+    dct = T.dct_matrix(n_mfcc, n_mels, norm)
+    bank = _sp._mel_bank(n_fft, n_mels, sample_rate, f_min, f_max, "none", "htk")
+    if log_mels:
+        kw = dict(out_kind=L.OUT_MFCC, mel_fb=bank, dct=dct, log_kind=L.LOG_LN_PLUS, log_arg=1e-6)
+    else:
+        kw = dict(out_kind=L.OUT_MFCC, mel_fb=bank, dct=dct, log_kind=L.LOG_DB, log_arg=1e-10, log_mult=10.0,
+                  log_offset=0.0, top_db=80.0)
+    return _features(waveforms, kw, n_mfcc, False, False, 0, 0, win_length, hop_length, "hann", n_fft, aux_mels=n_mels)
 
 
 fbanks = fbank  # README.md:41 and the docstring example (features.py:247) call it ``fbanks``

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib._PROTOS, "no ctypes prototype for " + n
-    assert lib.mafe_version() == 101
+    assert lib.mafe_version() == 102
 
 
 def test_import_does_not_touch_cuda_and_fails_loudly_without_gpu():

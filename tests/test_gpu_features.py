@@ -447,6 +447,35 @@ def test_hpss_harmonic(ma):
 
 
 
+def test_mel_and_features_one_transform(ma):
+    """Extension mafe_frontend_run_aux (BASELINE configs[3] asks for melspectrogram AND mfcc of the same waveforms): the
+    n_fft 400 kernel writes the mel energies beside their dB, so (mel, fbank / mfcc) come from ONE transform.  Both arrays
+    must equal the separate reference-signature calls bit for bit (same kernel, same arithmetic) and meet the oracle;
+    kernels without the second output (n_fft 512 / 2048 here) take the two-plan route with the same results."""
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    x = synth(23, (3, 16000))
+    for kw in (dict(n_mels=80, n_fft=400, hop_length=160), dict(n_mels=40), dict(n_mels=64, n_fft=512, hop_length=128),
+               dict(n_mels=128, n_fft=2048, win_length=1200, hop_length=300)):
+        mel, fb = ma.mel_and_fbank(x, **kw)
+        mkw = dict(kw)
+        ref_mel = ma.melspectrogram(x, **mkw)
+        assert mel.shape == ref_mel.shape and mel.dtype == ref_mel.dtype and np.array_equal(mel, ref_mel), kw
+        ref_fb = ma.fbank(x, **kw)
+        assert fb.shape == ref_fb.shape and np.array_equal(fb, ref_fb), kw
+        assert rel(mel, R.melspectrogram(x, **mkw)) <= 1e-5, kw
+    for xs in (x, x[0], x.reshape(1, 3, 16000), x.astype(np.float64)):       # 2-D / 1-D / 3-D dB groups, float64 in and out
+        mel, mf = ma.mel_and_mfcc(xs, n_mels=80, n_mfcc=40, hop_length=160)
+        ref = ma.mfcc(xs, deltas=False, context=False, n_mels=80, n_mfcc=40, hop_length=160)
+        assert mf.shape == ref.shape and mf.dtype == ref.dtype and np.array_equal(mf, ref)
+        ref_mel = ma.melspectrogram(xs, n_mels=80, hop_length=160)
+        assert mel.shape == ref_mel.shape and mel.dtype == ref_mel.dtype and np.array_equal(mel, ref_mel)
+    mel, mf = ma.mel_and_mfcc(x, n_mels=40, n_mfcc=13, log_mels=True)
+    assert np.array_equal(mf, ma.mfcc(x, deltas=False, context=False, n_mels=40, n_mfcc=13, log_mels=True))
+    assert np.array_equal(mel, ma.melspectrogram(x, n_mels=40))
+    with pytest.raises(ValueError):
+        ma.mel_and_mfcc(x, n_mels=20, n_mfcc=21)
+
+
 def test_padded_pipeline_reference_order(ma):
     """the reference collate sorts by frame count, longest first, BEFORE spec_aug / pad_sequence
     (examples/conformer/dataset.py:483-489).  sort_by_length=True must equal a call on the pre-sorted list (same seed),
