@@ -89,3 +89,13 @@ def test_feature_errors_match_reference_python():
         with pytest.raises(Exception) as e2:
             fn(ma)
         assert type(e1.value) is type(e2.value) and str(e1.value) == str(e2.value)
+
+
+def test_extension_argument_errors_without_a_gpu():
+    """mel_and_mfcc / mel_and_fbank (extensions over features.mfcc / fbank) refuse what mfcc / melspectrogram refuse, with the
+    reference's messages (features.py:337 ff., spectrum.py:594 ff.), before any device work."""
+    import mindaudio_b200 as ma
+    with pytest.raises(ValueError, match="number of MFCC coefficients must be no more than"):
+        ma.mel_and_mfcc(X, n_mels=20, n_mfcc=21)
+    with pytest.raises(ValueError, match="should be no more than f_max"):
+        ma.mel_and_fbank(X, f_min=5000.0, f_max=4000.0)

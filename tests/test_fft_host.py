@@ -69,3 +69,73 @@ def test_sweep_program_replayed_on_host(tmp_path):
     wide.tofile(path)
     res = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=60)
     assert res.returncode == 3, res.stdout + res.stderr
+
+
+def test_front2048_decomposition_and_layouts():
+    """front2048.cuh on the host (numpy): the 2048 = 16 x 16 x 8 decomposition with the twiddles the kernel keeps in TMEM
+    reproduces the DFT; the three shared-memory layouts are injective inside the 2176-slot scratch and conflict free for the
+    8-byte accesses of a half-warp; the compile-time store offsets (k + k / 16 = k1 + 17 k2 + 272 k3) and the pair separation
+    hold; the staged part of a frame covers the window's support."""
+    import numpy as np
+    N = 2048
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    W = lambda n, e: np.exp(-2j * np.pi * (e % n) / n)
+    # stage A: thread t = 8 n2 + n3 transforms x[128 n1 + t] over n1, times W2048^(t k1)
+    t = np.arange(128)
+    A = np.fft.fft(x.reshape(16, 128), axis=0) * W(N, np.outer(np.arange(16), t))            # [k1][t]
+    # stage B: thread (k1, n3) transforms A[k1][8 n2 + n3] over n2, times W128^(n3 k2)
+    B = np.fft.fft(A.reshape(16, 16, 8), axis=1) * W(128, np.outer(np.arange(16), np.arange(8)))[None]   # [k1][k2][n3]
+    # stage C: 8-point DFT over n3 -> Z[k1 + 16 k2 + 256 k3]
+    Cc = np.fft.fft(B, axis=2)                                                                # [k1][k2][k3]
+    Z = np.empty(N, dtype=complex)
+    k1, k2, k3 = np.meshgrid(np.arange(16), np.arange(16), np.arange(8), indexing="ij")
+    Z[k1 + 16 * k2 + 256 * k3] = Cc
+    assert np.max(np.abs(Z - np.fft.fft(x))) <= 1e-9 * np.max(np.abs(Z))
+    # pair separation: a + i b -> X_a = (Z[k] + conj Z[N-k]) / 2, X_b = -i (Z[k] - conj Z[N-k]) / 2
+    a, b = x.real, x.imag
+    k = np.arange(1025)
+    zn = np.conj(Z[(N - k) % N])
+    assert np.allclose((Z[k] + zn) / 2, np.fft.rfft(a)) and np.allclose(-1j * (Z[k] - zn) / 2, np.fft.rfft(b))
+
+    def conflict_free(addr):   # 8-byte slots: a half-warp (16 consecutive threads) must hit 16 different bank pairs
+        addr = np.asarray(addr).reshape(-1, 16)
+        return all(len(set(row % 16)) == 16 for row in addr)
+    # layout 1 (A -> B): store [k1][t] at k1 * 136 + t, load thread (k1 = t >> 3, n3 = t & 7) at k1 * 136 + 8 n2 + n3
+    lay1 = (np.arange(16)[:, None] * 136 + t[None]).ravel()
+    assert len(set(lay1)) == lay1.size and lay1.max() < 2176
+    for kk in range(16):
+        assert conflict_free(kk * 136 + t)
+    for n2 in range(16):
+        assert conflict_free((t >> 3) * 136 + 8 * n2 + (t & 7))
+    # layout 2 (B -> C): store thread (k1, n3) at n3 * 257 + 16 k1 + (k2 ^ 8 (k1 & 1)) through the two bases dlo / dhi
+    lay2 = set()
+    for kk2 in range(16):
+        sw = ((t >> 3) & 1) << 3
+        dlo, dhi = (t & 7) * 257 + (t >> 3) * 16 + sw, (t & 7) * 257 + (t >> 3) * 16 + (sw ^ 8)
+        addr = dlo + kk2 if kk2 < 8 else dhi + (kk2 - 8)
+        assert np.array_equal(addr, (t & 7) * 257 + (t >> 3) * 16 + (kk2 ^ sw))
+        assert conflict_free(addr)
+        lay2 |= set(addr)
+    assert len(lay2) == 2048 and max(lay2) < 2176
+    for n3 in range(8):                          # stage C loads: combos (k1a = t >> 4, k2 = t & 15) and k1b = k1a + 8
+        for k1x in ((t >> 4), (t >> 4) + 8):
+            assert conflict_free(n3 * 257 + k1x * 16 + ((t & 15) ^ ((k1x & 1) << 3)))
+    # layout 3 (Z, skewed k + k / 16): stores from one base with compile-time offsets
+    kk = np.arange(N)
+    skew = kk + (kk >> 4)
+    assert len(set(skew)) == N and skew.max() < 2176
+    for kk3 in range(8):
+        for plus8 in (0, 8):
+            ka = (t >> 4) + plus8 + 16 * (t & 15) + 256 * kk3
+            addr = (t >> 4) + 17 * (t & 15) + 272 * kk3 + plus8
+            assert np.array_equal(addr, ka + (ka >> 4)) and conflict_free(addr)
+    for i in range(8):                           # pair-separation loads: bin t + 128 i and its partner
+        kb = t + 128 * i
+        assert conflict_free(kb + (kb >> 4))
+    # staged part of a frame: rows [j0, j1) of 128 samples must cover the centred window's support
+    for win in (1200, 2048, 1000, 900, 1):
+        lo_w = (N - win) // 2
+        j0, j1 = lo_w // 128, (lo_w + win + 127) // 128
+        assert 128 * j0 <= lo_w and lo_w + win <= 128 * j1 and 0 <= j0 < j1 <= 16
+    assert ((N - 1200) // 2 // 128, ((N - 1200) // 2 + 1200 + 127) // 128) == (3, 13)      # the <3, 13> instantiation
