@@ -69,6 +69,9 @@ __device__ __forceinline__ void dm_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 }
 __device__ __forceinline__ void dm_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
+// frames per batch tile: dct_run takes this kernel for 32-frame tiles only.  A compile-time constant on purpose: with the
+// run-time value every row index paid an integer division (40 per thread and item, ~1/3 of the kernel's instructions).
+constexpr int kDmTile = 32;
 template <int QUADS>   // QUADS = ceil(K / 16): groups of four 16-byte chunks per row
 __global__ void __launch_bounds__(256, 1) dct_mma_kernel(const DctMmaParams P) {
   extern __shared__ __align__(128) unsigned char dm_smem[];
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) dct_mma_kernel(const DctMmaParams P) {
   const uint32_t sbo = (uint32_t)K * 32;
   const uint32_t a_hi = dm_smem_u32(sA), a_lo = a_hi + a_bytes, bb_hi = dm_smem_u32(sB), bb_lo = bb_hi + b_bytes;
 
-  const int tpi = kDmRows / P.tile_frames;                       // batch tiles per work item (4)
+  const int tpi = kDmRows / kDmTile;                       // batch tiles per work item (4)
   const int n_items = (P.n_tiles + tpi - 1) / tpi;
   const int n_workers = gridDim.x * 2;
   const int per = (n_items + n_workers - 1) / n_workers;         // contiguous range of items per group
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) dct_mma_kernel(const DctMmaParams P) {
       const Tile tile = P.tiles[ti];
       const int64_t fo = P.frame_offsets[tile.utt];
       const int64_t T = P.frame_offsets[tile.utt + 1] - fo;
-      nf = (int)min((int64_t)P.tile_frames, T - tile.frame0);
+      nf = (int)min((int64_t)kDmTile, T - tile.frame0);
       row = fo + tile.frame0;
       if (P.db_group != MAFE_DBGROUP_NONE) {
         const int grp = P.db_group == MAFE_DBGROUP_UTT ? tile.utt : (P.db_group == MAFE_DBGROUP_BATCH ? 0 : P.utt_group[tile.utt]);
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) dct_mma_kernel(const DctMmaParams P) {
       const int blk = (t >> 5) + 4 * j;
       const int rg = blk / QUADS, cq = blk - rg * QUADS;
       const int r = 8 * rg + r8, k16 = 4 * cq + c;
-      const int q = r / P.tile_frames, f = r - q * P.tile_frames;
+      const int q = r / kDmTile, f = r - q * kDmTile;
       x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k16 < chunks && f < s_nf[8 * slot + q])
         x[j] = __ldg(reinterpret_cast<const float4*>(P.logmel + (s_row[8 * slot + q] + f) * K) + k16);
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) dct_mma_kernel(const DctMmaParams P) {
       const int rg = blk / QUADS, cq = blk - rg * QUADS;
       const int r = 8 * rg + r8, k16 = 4 * cq + c;
       if (k16 < chunks) {
-        const int q = r / P.tile_frames, f = r - q * P.tile_frames;
+        const int q = r / kDmTile, f = r - q * kDmTile;
         float4 v = x[j];
         if (f < s_nf[8 * slot + q]) {               // rows beyond the tile stay zero (no clamp: the floor may be positive)
           const float fl = s_floor[8 * slot + q];
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(256, 1) dct_mma_kernel(const DctMmaParams P) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- 3. one row per thread: accumulator columns -> global memory ----
     {
-      const int q = t / P.tile_frames, f = t - q * P.tile_frames;
+      const int q = t / kDmTile, f = t - q * kDmTile;
       const bool valid = f < s_nf[8 * slot + q];
       float* dst = P.out + (s_row[8 * slot + q] + f) * P.n_mfcc;
       const bool vec = (P.n_mfcc & 3) == 0;
