@@ -9,6 +9,10 @@ and ``hop = win // 4`` while the Spectrogram wrappers default to reflect and ``w
 returns complex64 whatever the input dtype; ``amplitude_to_dB`` on a 3-D batch clamps against the
 max of the WHOLE batch; it raises ``UserWarning`` on complex input.  Fixed: the AttributeError of
 ``spectrum.py:237`` (some lengths with ``hop > n_fft/2``) -- the defined result is returned.
+
+The small host utilities ``_pad_center``, ``_pad_shape``, ``compute_amplitude`` and ``resynthesize`` (a few lines each, off the hot
+path) follow the reference's bodies closely on purpose: other reference modules import them from here and rely on their exact
+shapes, dtypes and error messages.
 """
 from __future__ import annotations
 
