@@ -356,31 +356,57 @@ __global__ void __launch_bounds__(kFastThreads, MAFE_F400_CTAS) fbank400_kernel(
     //      track the dB maximum ----
     {
       float vmax = -INFINITY;
-      if (cg < G) {
-        const float* pa = planes + (crow & 0xff) * kPlaneStride;
-        const float* pb = planes + (crow >> 8) * kPlaneStride;
-        float* od = P.out + cur.out_row * (int64_t)nm + cm;
-        float* ad = P.aux_mel ? P.aux_mel + cur.out_row * (int64_t)nm + cm : nullptr;
+      if (cg < G && cg < cur.nf) {
+        // frames cg, cg + G, ... of the tile: running pointers (the loop used to rebuild two 64-bit addresses and walk the
+        // log-kind branches per element: ~35 instructions for 2 loads, 1 add, 1 log, 1-2 stores), log kind resolved outside
+        const float* pa = planes + (crow & 0xff) * kPlaneStride + cg;
+        const float* pb = planes + (crow >> 8) * kPlaneStride + cg;
+        const int64_t stride = (int64_t)G * nm;
+        float* od = P.out + (cur.out_row + cg) * (int64_t)nm + cm;
+        float* ad = P.aux_mel ? P.aux_mel + (cur.out_row + cg) * (int64_t)nm + cm : nullptr;
+        const int nf = cur.nf;
+        auto run = [&](auto emit) {
+          if (ad) {
 #pragma unroll 2
-        for (int f = cg; f < cur.nf; f += G) {
-          const float e = pa[f] + pb[f];
-          if (ad) ad[(int64_t)f * nm] = e;
-          float o = e;
-          if (P.log_kind == MAFE_LOG_DB) {
-            float l2;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(e, P.log_arg)));
-            o = fmaf(P.log_mult * 0.30102999566398119521f, l2, -P.log_offset);
-            vmax = fmaxf(vmax, o);
-          } else if (P.log_kind == MAFE_LOG_LN_PLUS) {
-            float l2;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e + P.log_arg));
-            o = l2 * 0.69314718055994530942f;
-          } else if (P.log_kind == MAFE_LOG_LN_EPS_IF_ZERO) {
-            float l2;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e == 0.f ? 2.220446049250313e-16f : e));
-            o = l2 * 0.69314718055994530942f;
+            for (int f = cg; f < nf; f += G, pa += G, pb += G, od += stride, ad += stride) {
+              const float e = *pa + *pb;
+              *ad = e;
+              *od = emit(e);
+            }
+          } else {
+#pragma unroll 2
+            for (int f = cg; f < nf; f += G, pa += G, pb += G, od += stride) *od = emit(*pa + *pb);
           }
-          od[(int64_t)f * nm] = o;
+        };
+        switch (P.log_kind) {
+          case MAFE_LOG_DB: {
+            const float fl = P.log_arg, mult = P.log_mult * 0.30102999566398119521f, noff = -P.log_offset;
+            run([&](float e) {
+              float l2;
+              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(e, fl)));
+              const float o = fmaf(mult, l2, noff);
+              vmax = fmaxf(vmax, o);
+              return o;
+            });
+            break;
+          }
+          case MAFE_LOG_LN_PLUS: {
+            const float add = P.log_arg;
+            run([&](float e) {
+              float l2;
+              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e + add));
+              return l2 * 0.69314718055994530942f;
+            });
+            break;
+          }
+          case MAFE_LOG_LN_EPS_IF_ZERO:
+            run([&](float e) {
+              float l2;
+              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(e == 0.f ? 2.220446049250313e-16f : e));
+              return l2 * 0.69314718055994530942f;
+            });
+            break;
+          default: run([](float e) { return e; }); break;
         }
       }
       if (P.log_kind == MAFE_LOG_DB && P.db_group != MAFE_DBGROUP_NONE) {
